@@ -1,0 +1,225 @@
+/*
+ * pymarl_b200.h - C ABI of libpymarl_b200.so: the PyMARL QMIX/VDN/IQL learner step and the
+ * batched agent forward / epsilon-greedy action selection as hand-written sm_100a CUDA.
+ *
+ * The reference (nicholasburden/pymarl) has no FFI for this path: its boundary is Python
+ * duck typing through four registries.  The Python mirror of that surface lives in
+ * pymarl_b200/ (QLearner, BasicMAC, RNNAgent, QMixer, VDNMixer, EpsilonGreedyActionSelector)
+ * and binds the entry points below with ctypes (pymarl_b200/_lib.py); INTEGRATION.md shows
+ * the stub.  Each entry point names the reference code it replaces (paths relative to
+ * /root/reference/src).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the library allocates nothing: workspaces are sized by pmb_*_workspace_bytes() and
+ *     allocated by the caller (torch caching allocator), so calls are CUDA-graph capturable
+ *   - calls are asynchronous on `stream`; return 0 on success, else a pmb_status (a message
+ *     is available from pmb_last_error()); nothing is printed, nothing throws
+ *   - not re-entrant on the same buffers; one learner per (process, device)
+ *
+ * Batch layout = the reference EpisodeBatch (components/episode_buffer.py:58-86,
+ * run.py:122-135): batch major, time second, innermost dims contiguous; only the batch
+ * stride is free (a `batch[:, :max_t]` slice keeps the full-T batch stride).
+ *
+ * Internal (workspace) activations are TIME major: x/h/q[t][p][.] with p = b*N + n.
+ */
+#ifndef PYMARL_B200_H
+#define PYMARL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pmb_stream;            /* cudaStream_t */
+
+enum pmb_status {
+    PMB_OK = 0,
+    PMB_ERR_INVALID = 1,             /* bad dims / null pointer / unsupported size */
+    PMB_ERR_CUDA = 2,                /* a CUDA runtime call failed; see pmb_last_error() */
+    PMB_ERR_WORKSPACE = 3            /* workspace too small */
+};
+
+enum pmb_mixer { PMB_MIXER_NONE = 0 /* IQL */, PMB_MIXER_VDN = 1, PMB_MIXER_QMIX = 2 };
+
+/* precision tiers (BASELINE.json north_star): FP32 = CUDA-core FFMA, parity 1e-5;
+ * BF16 = tcgen05 tensor cores with fp32 accumulate, parity 1e-2. */
+enum pmb_precision { PMB_PREC_FP32 = 0, PMB_PREC_BF16 = 1 };
+
+typedef struct pmb_dims {
+    int32_t B;                 /* episodes in the batch                                   */
+    int32_t T;                 /* batch.max_seq_length                                    */
+    int32_t N;                 /* n_agents                                                */
+    int32_t O;                 /* obs dim                                                 */
+    int32_t S;                 /* state dim                                               */
+    int32_t A;                 /* n_actions                                               */
+    int32_t H;                 /* rnn_hidden_dim  (16, 32 or 64)                          */
+    int32_t E;                 /* mixing_embed_dim (8, 16, 32 or 64)                      */
+    int32_t obs_last_action;   /* controllers/basic_controller.py:111                     */
+    int32_t obs_agent_id;      /* controllers/basic_controller.py:118                     */
+    int32_t mixer;             /* enum pmb_mixer (learners/q_learner.py:19-27)            */
+    int32_t double_q;          /* learners/q_learner.py:71                                */
+    int32_t precision;         /* enum pmb_precision                                      */
+    int32_t reserved;
+} pmb_dims;
+
+/* The EpisodeBatch fields the path reads.  *_sb = batch stride in ELEMENTS. */
+typedef struct pmb_batch {
+    const float*   obs;        int64_t obs_sb;          /* [B,T,N,O] f32 */
+    const float*   state;      int64_t state_sb;        /* [B,T,S]   f32 (QMIX only, else NULL) */
+    const int64_t* actions;    int64_t actions_sb;      /* [B,T,N,1] i64 */
+    const int32_t* avail;      int64_t avail_sb;        /* [B,T,N,A] i32 */
+    const float*   reward;     int64_t reward_sb;       /* [B,T,1]   f32 */
+    const uint8_t* terminated; int64_t terminated_sb;   /* [B,T,1]   u8  */
+    const int64_t* filled;     int64_t filled_sb;       /* [B,T,1]   i64 */
+} pmb_batch;
+
+/* Flat parameter layout.  Agent tensors keep the reference order (modules/agents/rnn_agent.py:19-21);
+ * the mixer puts the four hypernet weight matrices first so they form ONE [ (N+3)E, S ]
+ * matrix (hyper_w_1 | hyper_w_final | hyper_b_1 | V.0), then their biases in the same
+ * order, then V.2.weight, V.2.bias (modules/mixers/qmix.py:17-26). */
+enum pmb_param_id {
+    PMB_P_FC1_W = 0, PMB_P_FC1_B, PMB_P_W_IH, PMB_P_W_HH, PMB_P_B_IH, PMB_P_B_HH, PMB_P_FC2_W, PMB_P_FC2_B,
+    PMB_P_HW1_W, PMB_P_HWF_W, PMB_P_HB1_W, PMB_P_V0_W, PMB_P_HW1_B, PMB_P_HWF_B, PMB_P_HB1_B, PMB_P_V0_B,
+    PMB_P_V2_W, PMB_P_V2_B, PMB_P_COUNT
+};
+typedef struct pmb_layout {
+    int64_t offset[PMB_P_COUNT];     /* element offset of each tensor in the flat buffer  */
+    int64_t numel[PMB_P_COUNT];
+    int64_t n_agent;                 /* elements of the 8 agent tensors                   */
+    int64_t n_total;                 /* agent + mixer (mixer part is 0 unless QMIX)       */
+} pmb_layout;
+
+/* hyper-parameters of one train step (learners/q_learner.py:30,86,102,105) */
+typedef struct pmb_hparams {
+    float gamma, lr, alpha, eps, grad_norm_clip;
+    int32_t do_target_sync;          /* host decides: (episode_num - last)/interval >= 1  */
+    int32_t skip_update;             /* 1: stop after the gradients (multi-GPU: all-reduce, then pmb_clip_rmsprop_update) */
+    int32_t reserved;
+} pmb_hparams;
+
+/* stats buffer: 16 doubles on the device, written by the step */
+enum pmb_stat_id {
+    PMB_S_MASK_SUM = 0,      /* sum(mask)                       q_learner.py:97  */
+    PMB_S_TD2_SUM,           /* sum((td*mask)^2)                :97              */
+    PMB_S_TDABS_SUM,         /* sum(|td*mask|)                  :113             */
+    PMB_S_QTAKEN_SUM,        /* sum(chosen_q_tot*mask)          :114             */
+    PMB_S_TARGET_SUM,        /* sum(targets*mask)               :115             */
+    PMB_S_GRAD_NORM,         /* total grad norm before clipping :102             */
+    PMB_S_LOSS,              /* TD2_SUM / MASK_SUM                                */
+    PMB_S_CLIP_COEF,
+    PMB_S_COUNT = 16
+};
+
+const char* pmb_last_error(void);
+int  pmb_version(void);
+/* sm count, compute capability and opt-in shared memory of the current device */
+int  pmb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes);
+int  pmb_flat_layout(const pmb_dims* d, pmb_layout* out);
+/* bytes of scratch pmb_qlearner_train_step needs for these dims */
+int64_t pmb_learner_workspace_bytes(const pmb_dims* d);
+
+/* ---- K1: agent forward -------------------------------------------------------------- */
+/* fc1 over nt timesteps starting at t0, inputs never concatenated:
+ *   x = relu(W_obs obs + W_act[:, a_{t-1}] (0 at t == 0 or if step t-1 is padded) + W_id[:, n] + b)
+ * replaces BasicMAC._build_inputs + RNNAgent.fc1 (basic_controller.py:100-135, rnn_agent.py:32).
+ * x_out: [nt][B*N][H]. */
+int pmb_agent_fc1_fwd(const pmb_dims* d, const pmb_batch* b, int32_t t0, int32_t nt,
+                      const float* flat_agent, float* x_out, pmb_stream stream);
+/* same for an already concatenated input matrix inputs[R][D_in] (RNNAgent.forward called
+ * directly, rnn_agent.py:27-32). */
+int pmb_agent_fc1_dense_fwd(const pmb_dims* d, int64_t rows, int32_t d_in, const float* inputs,
+                            const float* flat_agent, float* x_out, pmb_stream stream);
+/* GRUCell + fc2 unrolled over nt steps for R = rows (rnn_agent.py:33-36, the t loops of
+ * q_learner.py:47-52,58-62).  h0 NULL = zeros (basic_controller.py:77-81).
+ * h_stash [(nt+1)][R][H] (slot 0 = h0) and gates [nt][R][4H] (r,z,n,W_hn h+b_hn) are
+ * written when non-NULL (needed by the backward); q [nt][R][A]; h_last [R][H] optional. */
+int pmb_agent_gru_unroll_fwd(const pmb_dims* d, int64_t rows, int32_t nt, const float* flat_agent,
+                             const float* x, const float* h0, float* h_stash, float* gates,
+                             float* q, float* h_last, pmb_stream stream);
+
+/* ---- K2: chosen-action gather, avail masking, double-Q target (q_learner.py:55-78) ---- */
+/* q_on, q_tg: [T][B*N][A] time major.  chosen, tmax: [B][T-1][N]; cur_max (int32, may be
+ * NULL): the arg-max action index.  Ties -> lowest index; masked value -9999999. */
+int pmb_target_select(const pmb_dims* d, const pmb_batch* b, const float* q_on, const float* q_tg,
+                      float* chosen, float* tmax, int32_t* cur_max, pmb_stream stream);
+
+/* ---- K3: mixers (modules/mixers/qmix.py:28-47, vdn.py:9-10) ---------------------------- */
+/* agent_qs [B][T-1][N]; uses state[:, t_off : t_off+T-1] (0 online, 1 target).
+ * QMIX: raw [B*(T-1)][(N+3)E] receives the hypernet outputs (kept for the backward).
+ * q_tot [B*(T-1)] (VDN) ; for PMB_MIXER_NONE the call is an error (IQL has no mixer). */
+int pmb_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs,
+                  int32_t t_off, float* raw, float* q_tot, pmb_stream stream);
+
+/* ---- K4: TD target, masked loss sums, dL/dq_tot (q_learner.py:39-44,86-97) ------------- */
+/* q_tot / t_tot: [B][T-1][W], W = 1 (QMIX/VDN) or N (IQL).  g_out same shape =
+ * 2 * td * mask * mask (NOT divided by sum(mask); the update kernel applies 1/sum(mask)).
+ * stats[0..4] accumulate (zero them first with pmb_stats_reset). */
+int pmb_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
+                float* g_out, double* stats, pmb_stream stream);
+int pmb_stats_reset(double* stats, pmb_stream stream);
+
+/* ---- K4b: mixer backward -------------------------------------------------------------- */
+/* QMIX: raw (in) is overwritten by d_raw; writes d_agent_qs [B][T-1][N] and ACCUMULATES
+ * nothing: flat_grad_mixer is overwritten.  scratch: pmb_mixer_bwd_workspace_bytes().
+ * VDN: d_agent_qs[m][n] = g[m]. */
+int64_t pmb_mixer_bwd_workspace_bytes(const pmb_dims* d);
+int pmb_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs,
+                  float* raw, const float* g, float* d_agent_qs, float* flat_grad_mixer,
+                  void* scratch, int64_t scratch_bytes, pmb_stream stream);
+
+/* ---- K5: agent backward (BPTT through q_learner.py:47-55) ------------------------------ */
+/* d_chosen [B][T-1][N].  gates (in) is overwritten by the gate pre-activation gradients.
+ * x_on: fc1 outputs [T][R][H]; dpre1: scratch [T][R][H].  flat_grad_agent is overwritten. */
+int64_t pmb_agent_bwd_workspace_bytes(const pmb_dims* d);
+int pmb_agent_unroll_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, const float* x_on,
+                         const float* h_stash, float* gates, const float* d_chosen, float* dpre1,
+                         float* flat_grad_agent, void* scratch, int64_t scratch_bytes, pmb_stream stream);
+
+/* ---- K6: grad-norm clip + RMSprop + optional hard target sync (q_learner.py:102-107) --- */
+/* g is the un-normalised gradient; stats[PMB_S_MASK_SUM] supplies the 1/sum(mask) factor.
+ * clip_grad_norm_: coef = min(1, clip / (norm + 1e-6)); RMSprop: v = a v + (1-a) g^2,
+ * p -= lr g / (sqrt(v) + eps).  flat_target may be NULL.  scratch: 4096 floats. */
+int pmb_clip_rmsprop_update(int64_t n, float* flat_p, float* flat_g, float* flat_sq, float* flat_target,
+                            int32_t do_target_sync, double* stats, float lr, float alpha, float eps,
+                            float grad_norm_clip, float* scratch, pmb_stream stream);
+
+/* ---- K7: epsilon-greedy action selection (components/action_selectors.py:44-62) --------- */
+/* q [rows_b][N][A] f32, avail [rows_b][N][A] i32.  Draw modes:
+ *   u != NULL, expo != NULL : injected draws (u [b][N] uniform, expo [b][N][A] Exp(1)), the
+ *                             reference's generator order -> bit-exact with the reference
+ *   else                     : in-kernel Philox4x32-10 keyed by (seed, offset)
+ * actions_out int64 [b][N]. */
+int pmb_epsilon_greedy(int64_t rows, int32_t A, const float* q, const int32_t* avail, float epsilon,
+                       const float* u, const float* expo, uint64_t seed, uint64_t offset,
+                       int64_t* actions_out, pmb_stream stream);
+
+/* one fused rollout step of BasicMAC.select_actions (basic_controller.py:30-38) for all B
+ * envs at time t: fc1 + GRU + fc2 + masking + epsilon-greedy.  hidden [B*N][H] is updated
+ * in place (NULL-initialise with zeros at t_ep == 0 yourself); q_out [B][N][A] optional. */
+int64_t pmb_select_actions_workspace_bytes(const pmb_dims* d);
+int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, const float* flat_agent,
+                            float* hidden, float epsilon, const float* u, const float* expo,
+                            uint64_t seed, uint64_t offset, int64_t* actions_out, float* q_out,
+                            void* scratch, int64_t scratch_bytes, pmb_stream stream);
+
+/* ---- whole learner step (learners/q_learner.py:37-107) ---------------------------------- */
+/* flat_p / flat_g / flat_sq: online params, grads, RMSprop square_avg (n_total floats);
+ * flat_target: target params.  workspace >= pmb_learner_workspace_bytes().  stats: 16 doubles. */
+int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hparams* hp,
+                            float* flat_p, float* flat_g, float* flat_sq, float* flat_target,
+                            void* workspace, int64_t workspace_bytes, double* stats, pmb_stream stream);
+
+/* views into the learner workspace, for tests and the Python mirror */
+typedef struct pmb_ws_views {
+    float *x_on, *x_tg, *h_stash, *gates, *q_on, *q_tg, *chosen, *tmax, *raw_on, *raw_tg,
+          *q_tot, *t_tot, *g, *d_chosen, *scratch;
+    int64_t scratch_bytes;
+} pmb_ws_views;
+int pmb_learner_workspace_views(const pmb_dims* d, void* workspace, int64_t workspace_bytes, pmb_ws_views* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMARL_B200_H */

@@ -1,0 +1,201 @@
+"""EpisodeBatch / ReplayBuffer with the reference's layout contract and call surface
+(reference: components/episode_buffer.py:8-298), written for this package so rollout and
+learner code keep working when the reference tree is not importable.
+
+Layout contract (what the CUDA path relies on): every per-timestep field is one tensor
+``[batch, max_seq_length, (group size,) *vshape]`` of the scheme dtype (default float32),
+episode-constant fields drop the time axis, and an int64 ``filled [batch, T, 1]`` marks
+written timesteps.  Slicing returns views that share storage (a ``[:, :t]`` slice keeps the
+full-T batch stride); indexing with an id list/array copies (advanced indexing).
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import torch as th
+
+
+def _as_tuple(v):
+    return (v,) if isinstance(v, int) else tuple(v)
+
+
+class EpisodeBatch:
+    def __init__(self, scheme, groups, batch_size, max_seq_length, data=None, preprocess=None, device="cpu"):
+        self.scheme = scheme.copy()
+        self.groups = groups
+        self.batch_size = batch_size
+        self.max_seq_length = max_seq_length
+        self.preprocess = {} if preprocess is None else preprocess
+        self.device = device
+        if data is not None:
+            self.data = data
+            return
+        self.data = SimpleNamespace(transition_data={}, episode_data={})
+        self._setup_data(self.scheme, self.groups, batch_size, max_seq_length, self.preprocess)
+
+    # ---- allocation ---------------------------------------------------------------------
+    def _setup_data(self, scheme, groups, batch_size, max_seq_length, preprocess):
+        for key, (new_key, transforms) in (preprocess or {}).items():
+            assert key in scheme, "preprocess key {} is not in the scheme".format(key)
+            vshape, dtype = self.scheme[key]["vshape"], self.scheme[key].get("dtype", th.float32)
+            for tr in transforms:
+                vshape, dtype = tr.infer_output_info(vshape, dtype)
+            entry = {"vshape": vshape, "dtype": dtype}
+            for carry in ("group", "episode_const"):
+                if carry in self.scheme[key]:
+                    entry[carry] = self.scheme[key][carry]
+            self.scheme[new_key] = entry
+        assert "filled" not in scheme, '"filled" is a reserved key for masking.'
+        scheme.update({"filled": {"vshape": (1,), "dtype": th.long}})
+        for key, info in scheme.items():
+            assert "vshape" in info, "Scheme must define vshape for {}".format(key)
+            shape = _as_tuple(info["vshape"])
+            group = info.get("group")
+            if group:
+                assert group in groups, "Group {} must have its number of members defined in _groups_".format(group)
+                shape = (groups[group],) + shape
+            dtype = info.get("dtype", th.float32)
+            if info.get("episode_const", False):
+                self.data.episode_data[key] = th.zeros((batch_size,) + shape, dtype=dtype, device=self.device)
+            else:
+                self.data.transition_data[key] = th.zeros((batch_size, max_seq_length) + shape, dtype=dtype,
+                                                          device=self.device)
+
+    def extend(self, scheme, groups=None):
+        self._setup_data(scheme, self.groups if groups is None else groups, self.batch_size, self.max_seq_length, None)
+
+    def to(self, device):
+        for store in (self.data.transition_data, self.data.episode_data):
+            for k in store:
+                store[k] = store[k].to(device)
+        self.device = device
+
+    # ---- writes ---------------------------------------------------------------------------
+    def update(self, data, bs=slice(None), ts=slice(None), mark_filled=True):
+        slices = self._parse_slices((bs, ts))
+        for k, v in data.items():
+            if k in self.data.transition_data:
+                store, sl = self.data.transition_data, tuple(slices)
+                if mark_filled:
+                    store["filled"][sl] = 1
+                    mark_filled = False
+            elif k in self.data.episode_data:
+                store, sl = self.data.episode_data, slices[0]
+            else:
+                raise KeyError("{} not found in transition or episode data".format(k))
+            dtype = self.scheme[k].get("dtype", th.float32)
+            v = th.as_tensor(v, dtype=dtype, device=self.device) if not isinstance(v, th.Tensor) \
+                else v.to(device=self.device, dtype=dtype)
+            dest = store[k][sl]
+            self._check_safe_view(v, dest)
+            store[k][sl] = v.view_as(dest)
+            if k in self.preprocess:
+                new_k, transforms = self.preprocess[k]
+                out = store[k][sl]
+                for tr in transforms:
+                    out = tr.transform(out)
+                store[new_k][sl] = out.view_as(store[new_k][sl])
+
+    @staticmethod
+    def _check_safe_view(v, dest):
+        idx = len(v.shape) - 1
+        for s in dest.shape[::-1]:
+            if idx < 0 or v.shape[idx] != s:
+                if s != 1:
+                    raise ValueError("Unsafe reshape of {} to {}".format(v.shape, dest.shape))
+            else:
+                idx -= 1
+
+    # ---- reads ----------------------------------------------------------------------------
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            if item in self.data.episode_data:
+                return self.data.episode_data[item]
+            if item in self.data.transition_data:
+                return self.data.transition_data[item]
+            raise ValueError(item)
+        if isinstance(item, tuple) and all(isinstance(it, str) for it in item):
+            new = SimpleNamespace(transition_data={}, episode_data={})
+            for key in item:
+                if key in self.data.transition_data:
+                    new.transition_data[key] = self.data.transition_data[key]
+                elif key in self.data.episode_data:
+                    new.episode_data[key] = self.data.episode_data[key]
+                else:
+                    raise KeyError("Unrecognised key {}".format(key))
+            scheme = {key: self.scheme[key] for key in item}
+            groups = {self.scheme[key]["group"]: self.groups[self.scheme[key]["group"]]
+                      for key in item if "group" in self.scheme[key]}
+            return EpisodeBatch(scheme, groups, self.batch_size, self.max_seq_length, data=new, device=self.device)
+        sl = self._parse_slices(item)
+        new = SimpleNamespace(transition_data={}, episode_data={})
+        for k, v in self.data.transition_data.items():
+            new.transition_data[k] = v[tuple(sl)]
+        for k, v in self.data.episode_data.items():
+            new.episode_data[k] = v[sl[0]]
+        return EpisodeBatch(self.scheme, self.groups, self._num_items(sl[0], self.batch_size),
+                            self._num_items(sl[1], self.max_seq_length), data=new, device=self.device)
+
+    @staticmethod
+    def _num_items(idx, max_size):
+        if isinstance(idx, (list, np.ndarray)):
+            return len(idx)
+        if isinstance(idx, th.Tensor):
+            return idx.numel()
+        lo, hi, step = idx.indices(max_size)
+        return 1 + (hi - lo - 1) // step
+
+    @staticmethod
+    def _parse_slices(items):
+        if isinstance(items, (slice, int, list, np.ndarray, th.Tensor)):
+            items = (items, slice(None))
+        if isinstance(items[1], list):
+            raise IndexError("Indexing across Time must be contiguous")
+        return [slice(it, it + 1) if isinstance(it, int) else it for it in items]
+
+    def max_t_filled(self):
+        return th.sum(self.data.transition_data["filled"], 1).max(0)[0]
+
+    def __repr__(self):
+        return "EpisodeBatch. Batch Size:{} Max_seq_len:{} Keys:{} Groups:{}".format(
+            self.batch_size, self.max_seq_length, self.scheme.keys(), self.groups.keys())
+
+
+class ReplayBuffer(EpisodeBatch):
+    """Ring buffer of episodes with uniform sampling (episode_buffer.py:263-298).  Sampling
+    draws ids on the legacy global numpy RandomState exactly like the reference, so a shared
+    ``np.random.seed`` yields the same episode ids."""
+
+    def __init__(self, scheme, groups, buffer_size, max_seq_length, preprocess=None, device="cpu"):
+        super().__init__(scheme, groups, buffer_size, max_seq_length, preprocess=preprocess, device=device)
+        self.buffer_size = buffer_size
+        self.buffer_index = 0
+        self.episodes_in_buffer = 0
+
+    def insert_episode_batch(self, ep_batch):
+        n = ep_batch.batch_size
+        if self.buffer_index + n > self.buffer_size:          # wrap: split at the end of the ring
+            left = self.buffer_size - self.buffer_index
+            self.insert_episode_batch(ep_batch[0:left, :])
+            self.insert_episode_batch(ep_batch[left:, :])
+            return
+        where = slice(self.buffer_index, self.buffer_index + n)
+        self.update(ep_batch.data.transition_data, where, slice(0, ep_batch.max_seq_length), mark_filled=False)
+        self.update(ep_batch.data.episode_data, where)
+        self.buffer_index += n
+        self.episodes_in_buffer = max(self.episodes_in_buffer, self.buffer_index)
+        self.buffer_index %= self.buffer_size
+        assert self.buffer_index < self.buffer_size
+
+    def can_sample(self, batch_size):
+        return self.episodes_in_buffer >= batch_size
+
+    def sample(self, batch_size):
+        assert self.can_sample(batch_size)
+        if self.episodes_in_buffer == batch_size:
+            return self[:batch_size]
+        ep_ids = np.random.choice(self.episodes_in_buffer, batch_size, replace=False)
+        return self[ep_ids]
+
+    def __repr__(self):
+        return "ReplayBuffer. {}/{} episodes. Keys:{} Groups:{}".format(
+            self.episodes_in_buffer, self.buffer_size, self.scheme.keys(), self.groups.keys())

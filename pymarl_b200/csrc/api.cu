@@ -1,0 +1,437 @@
+// extern "C" surface of libpymarl_b200.so (see include/pymarl_b200.h) and the orchestration of
+// the whole learner step (learners/q_learner.py:37-107).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace pmb {
+
+// launchers defined in the other translation units
+int gru_fwd_dispatch(const pmb_dims* d, const AgentParams& p, int64_t R, int nt, const float* x, const float* h0,
+                     float* h_stash, float* gates, float* q, float* h_last, cudaStream_t s);
+int gru_bwd_dispatch(const pmb_dims* d, const pmb_batch* b, const AgentParams& p, const float* x,
+                     const float* h_stash, float* gates, const float* d_chosen, float* dpre1, cudaStream_t s);
+int64_t scatter_scratch_bytes(const pmb_dims* d);
+int scatter_grads_dispatch(const pmb_dims* d, const pmb_batch* b, const float* h_stash, const float* dpre1,
+                           const float* d_chosen, AgentGrads gr, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+int launch_target_select(const pmb_dims* d, const pmb_batch* b, const float* q_on, const float* q_tg, float* chosen,
+                         float* tmax, int32_t* cur_max, cudaStream_t s);
+int launch_epsilon_greedy(int64_t rows, int N, int A, const float* q, const int32_t* avail, int64_t avail_sb,
+                          float epsilon, const float* u, const float* expo, uint64_t seed, uint64_t offset,
+                          int64_t* actions_out, cudaStream_t s);
+int launch_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs,
+                     int t_off, float* raw, float* q_tot, cudaStream_t s);
+int64_t mixer_bwd_scratch_bytes(const pmb_dims* d);
+int launch_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs, float* raw,
+                     const float* g, float* d_agent_qs, float* flat_grad_mixer, void* scratch, int64_t scratch_bytes,
+                     cudaStream_t s);
+int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
+                   float* g_out, double* stats, cudaStream_t s);
+int launch_stats_reset(double* stats, cudaStream_t s);
+int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target, int do_sync, double* stats, float lr,
+                        float alpha, float eps, float clip, float* scratch, cudaStream_t s);
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorName(e), file, line, what);
+    return PMB_ERR_CUDA;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;          // B200
+    }
+    return cached;
+}
+
+int validate_dims(const pmb_dims* d) {
+    PMB_REQUIRE(d != nullptr, "dims is NULL");
+    PMB_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->O > 0 && d->A > 0, "B, T, N, O, A must be positive");
+    PMB_REQUIRE(d->H == 16 || d->H == 32 || d->H == 64, "rnn_hidden_dim %d unsupported (16, 32, 64)", d->H);
+    PMB_REQUIRE(d->mixer >= PMB_MIXER_NONE && d->mixer <= PMB_MIXER_QMIX, "unknown mixer id %d", d->mixer);
+    if (d->mixer == PMB_MIXER_QMIX) {
+        PMB_REQUIRE(d->S > 0, "QMIX needs a positive state dim");
+        PMB_REQUIRE(d->E > 0 && d->E <= 64, "mixing_embed_dim %d unsupported (1..64)", d->E);
+    }
+    return PMB_OK;
+}
+
+void compute_layout(const pmb_dims* d, pmb_layout* L) {
+    const int64_t H = d->H, A = d->A, Din = d_in_of(d), S = d->S, N = d->N, E = d->E;
+    int64_t numel[PMB_P_COUNT] = {H * Din, H, 3 * H * H, 3 * H * H, 3 * H, 3 * H, A * H, A,
+                                  N * E * S, E * S, E * S, E * S, N * E, E, E, E, E, 1};
+    int64_t off = 0;
+    for (int i = 0; i < PMB_P_COUNT; ++i) {
+        bool is_mixer = i >= PMB_P_HW1_W;
+        L->numel[i] = (is_mixer && d->mixer != PMB_MIXER_QMIX) ? 0 : numel[i];
+        L->offset[i] = off;
+        off += L->numel[i];
+        if (i == PMB_P_FC2_B) L->n_agent = off;
+    }
+    L->n_total = off;
+}
+
+namespace {
+
+struct WsPlan {
+    int64_t off[15];
+    int64_t scratch_bytes;
+    int64_t total;
+};
+
+int64_t agent_bwd_scratch(const pmb_dims* d) {
+    const int64_t rows = (int64_t)d->T * d->B * d->N;
+    int64_t a = gemm_atb_scratch_bytes(3 * d->H, d->H, rows);
+    int64_t b = gemm_atb_scratch_bytes(d->H, d->O, rows);
+    int64_t c = scatter_scratch_bytes(d);
+    int64_t m = a > b ? a : b;
+    return m > c ? m : c;
+}
+
+WsPlan plan_workspace(const pmb_dims* d) {
+    const int64_t R = (int64_t)d->B * d->N, T = d->T, H = d->H, A = d->A, N = d->N;
+    const int64_t M = (int64_t)d->B * (T - 1);
+    const int64_t C = (int64_t)(N + 3) * d->E;
+    const bool qmix = d->mixer == PMB_MIXER_QMIX, iql = d->mixer == PMB_MIXER_NONE;
+    const int64_t W = iql ? N : 1;
+    int64_t sizes[15] = {
+        T * R * H,                 // 0 x_on
+        T * R * H,                 // 1 x_tg (reused as dpre1 in the backward)
+        (T + 1) * R * H,           // 2 h_stash
+        T * R * 4 * H,             // 3 gates
+        T * R * A,                 // 4 q_on
+        T * R * A,                 // 5 q_tg
+        M * N,                     // 6 chosen
+        M * N,                     // 7 tmax
+        qmix ? M * C : 0,          // 8 raw (target pass first, then online: one buffer)
+        0,                         // 9 (raw_tg aliases raw)
+        iql ? 0 : M,               // 10 q_tot
+        iql ? 0 : M,               // 11 t_tot
+        M * W,                     // 12 g
+        iql ? 0 : M * N,           // 13 d_chosen
+        0                          // 14 scratch (bytes, below)
+    };
+    WsPlan p;
+    int64_t off = 0;
+    for (int i = 0; i < 14; ++i) {
+        p.off[i] = off;
+        off += align_up(sizes[i] * 4, 256);
+    }
+    int64_t sc = agent_bwd_scratch(d);
+    int64_t mb = mixer_bwd_scratch_bytes(d);
+    if (mb > sc) sc = mb;
+    if (sc < 4096 * 4) sc = 4096 * 4;
+    p.off[14] = off;
+    p.scratch_bytes = align_up(sc, 256);
+    p.total = off + p.scratch_bytes;
+    return p;
+}
+
+void fill_views(const pmb_dims* d, void* ws, const WsPlan& p, pmb_ws_views* v) {
+    char* base = static_cast<char*>(ws);
+    auto f = [&](int i) { return reinterpret_cast<float*>(base + p.off[i]); };
+    const bool iql = d->mixer == PMB_MIXER_NONE;
+    v->x_on = f(0); v->x_tg = f(1); v->h_stash = f(2); v->gates = f(3); v->q_on = f(4); v->q_tg = f(5);
+    v->chosen = f(6); v->tmax = f(7); v->raw_on = f(8); v->raw_tg = f(8);
+    v->q_tot = iql ? v->chosen : f(10);
+    v->t_tot = iql ? v->tmax : f(11);
+    v->g = f(12);
+    v->d_chosen = iql ? v->g : f(13);
+    v->scratch = f(14);
+    v->scratch_bytes = p.scratch_bytes;
+}
+
+int fc1_fwd(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& ap, float* x_out,
+            cudaStream_t s) {
+    const int64_t M = (int64_t)d->B * nt * d->N;
+    RowMap map{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, nt, d->N};
+    Fc1Epilogue ep;
+    ep.fc1_w = ap.fc1_w; ep.fc1_b = ap.fc1_b;
+    ep.actions = b->actions; ep.actions_sb = b->actions_sb;
+    ep.filled = b->filled; ep.filled_sb = b->filled_sb;
+    ep.x_out = x_out;
+    ep.T_batch = d->T; ep.t0 = t0; ep.nt = nt; ep.N = d->N; ep.O = d->O; ep.A = d->A; ep.H = d->H;
+    ep.D_in = d_in_of(d); ep.use_act = d->obs_last_action; ep.use_id = d->obs_agent_id;
+    ep.R = (int64_t)d->B * d->N;
+    return launch_fc1_gemm(b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, ap.fc1_w, ep.D_in, d->H, ep, s);
+}
+
+int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, const float* x_on, const float* h_stash,
+              float* gates, const float* d_chosen, float* dpre1, float* flat_grad_agent, void* scratch,
+              int64_t scratch_bytes, cudaStream_t s) {
+    AgentParams ap = agent_params(d, flat_agent);
+    AgentGrads gr = agent_grads(d, flat_grad_agent);
+    const int64_t R = (int64_t)d->B * d->N, rows = (int64_t)d->T * R;
+    const int H = d->H;
+    int rc = gru_bwd_dispatch(d, b, ap, x_on, h_stash, gates, d_chosen, dpre1, s);
+    if (rc) return rc;
+    // rnn.weight_ih / bias_ih:  [da_r | da_z | da_n]^T . x
+    rc = launch_gemm_atb(gates, dense_map(4 * H), 3 * H, x_on, dense_map(H), H, rows, gr.w_ih, H, gr.b_ih, scratch,
+                         scratch_bytes, s);
+    if (rc) return rc;
+    // rnn.weight_hh / bias_hh:  [da_r | da_z | da_n * r]^T . h_{t-1}   (h_stash slot t holds h_{t-1})
+    rc = launch_gemm_atb(gates, dense_map(4 * H), 2 * H, h_stash, dense_map(H), H, rows, gr.w_hh, H, gr.b_hh, scratch,
+                         scratch_bytes, s);
+    if (rc) return rc;
+    rc = launch_gemm_atb(gates + 3 * H, dense_map(4 * H), H, h_stash, dense_map(H), H, rows,
+                         gr.w_hh + (int64_t)2 * H * H, H, gr.b_hh + 2 * H, scratch, scratch_bytes, s);
+    if (rc) return rc;
+    // fc1.weight[:, :O] / fc1.bias:  dpre1^T . obs   (dpre1 time major, obs batch major)
+    RowMap dmap{(int64_t)d->N * H, R * H, (int64_t)H, d->T, d->N};
+    RowMap omap{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, d->T, d->N};
+    rc = launch_gemm_atb(dpre1, dmap, H, b->obs, omap, d->O, rows, gr.fc1_w, d_in_of(d), gr.fc1_b, scratch,
+                         scratch_bytes, s);
+    if (rc) return rc;
+    return scatter_grads_dispatch(d, b, h_stash, dpre1, d_chosen, gr, scratch, scratch_bytes, s);
+}
+
+}  // namespace
+}  // namespace pmb
+
+using namespace pmb;
+
+extern "C" {
+
+const char* pmb_last_error(void) { return g_err; }
+int pmb_version(void) { return 100; }
+
+int pmb_device_info(int32_t* sm, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin) {
+    int dev = 0;
+    PMB_CUDA(cudaGetDevice(&dev));
+    int v = 0;
+    PMB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); if (sm) *sm = v;
+    PMB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); if (cc_major) *cc_major = v;
+    PMB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); if (cc_minor) *cc_minor = v;
+    PMB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)); if (smem_optin) *smem_optin = v;
+    return PMB_OK;
+}
+
+int pmb_flat_layout(const pmb_dims* d, pmb_layout* out) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(out != nullptr, "layout out is NULL");
+    compute_layout(d, out);
+    return PMB_OK;
+}
+
+int64_t pmb_learner_workspace_bytes(const pmb_dims* d) {
+    if (validate_dims(d) || d->T < 2) return -1;
+    return plan_workspace(d).total;
+}
+
+int pmb_learner_workspace_views(const pmb_dims* d, void* workspace, int64_t workspace_bytes, pmb_ws_views* out) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2, "T must be >= 2");
+    WsPlan p = plan_workspace(d);
+    if (workspace_bytes < p.total) { set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)p.total); return PMB_ERR_WORKSPACE; }
+    fill_views(d, workspace, p, out);
+    return PMB_OK;
+}
+
+int pmb_agent_fc1_fwd(const pmb_dims* d, const pmb_batch* b, int32_t t0, int32_t nt, const float* flat_agent,
+                      float* x_out, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(b && b->obs && flat_agent && x_out, "fc1_fwd: NULL pointer");
+    PMB_REQUIRE(t0 >= 0 && nt > 0 && t0 + nt <= d->T, "fc1_fwd: bad time range [%d, %d) for T = %d", t0, t0 + nt, d->T);
+    PMB_REQUIRE(!d->obs_last_action || (b->actions && b->filled), "fc1_fwd: obs_last_action needs actions and filled");
+    return fc1_fwd(d, b, t0, nt, agent_params(d, flat_agent), x_out, (cudaStream_t)stream);
+}
+
+int pmb_agent_fc1_dense_fwd(const pmb_dims* d, int64_t rows, int32_t d_in, const float* inputs, const float* flat_agent,
+                            float* x_out, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(inputs && flat_agent && x_out, "fc1_dense_fwd: NULL pointer");
+    PMB_REQUIRE(d_in == d_in_of(d), "fc1_dense_fwd: input width %d != %d", d_in, d_in_of(d));
+    AgentParams ap = agent_params(d, flat_agent);
+    return launch_gemm_tn(inputs, dense_map(d_in), rows, d_in, ap.fc1_w, d_in, d->H, ap.fc1_b, x_out, d->H, 1,
+                          (cudaStream_t)stream);
+}
+
+int pmb_agent_gru_unroll_fwd(const pmb_dims* d, int64_t rows, int32_t nt, const float* flat_agent, const float* x,
+                             const float* h0, float* h_stash, float* gates, float* q, float* h_last,
+                             pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(flat_agent && x && q, "gru_unroll_fwd: NULL pointer");
+    PMB_REQUIRE(rows > 0 && nt > 0, "gru_unroll_fwd: rows and nt must be positive");
+    return gru_fwd_dispatch(d, agent_params(d, flat_agent), rows, nt, x, h0, h_stash, gates, q, h_last,
+                            (cudaStream_t)stream);
+}
+
+int pmb_target_select(const pmb_dims* d, const pmb_batch* b, const float* q_on, const float* q_tg, float* chosen,
+                      float* tmax, int32_t* cur_max, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2, "target_select: T must be >= 2");
+    PMB_REQUIRE(b && b->avail && b->actions && q_on && q_tg && chosen && tmax, "target_select: NULL pointer");
+    return launch_target_select(d, b, q_on, q_tg, chosen, tmax, cur_max, (cudaStream_t)stream);
+}
+
+int pmb_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs,
+                  int32_t t_off, float* raw, float* q_tot, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2 && (t_off == 0 || t_off == 1), "mixer_fwd: bad T / t_off");
+    PMB_REQUIRE(agent_qs && q_tot, "mixer_fwd: NULL pointer");
+    return launch_mixer_fwd(d, b, flat_mixer, agent_qs, t_off, raw, q_tot, (cudaStream_t)stream);
+}
+
+int pmb_stats_reset(double* stats, pmb_stream stream) {
+    PMB_REQUIRE(stats, "stats is NULL");
+    return launch_stats_reset(stats, (cudaStream_t)stream);
+}
+
+int pmb_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
+                float* g_out, double* stats, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2, "td_loss: T must be >= 2");
+    PMB_REQUIRE(b && b->reward && b->terminated && b->filled && q_tot && t_tot && g_out && stats, "td_loss: NULL pointer");
+    return launch_td_loss(d, b, q_tot, t_tot, gamma, g_out, stats, (cudaStream_t)stream);
+}
+
+int64_t pmb_mixer_bwd_workspace_bytes(const pmb_dims* d) {
+    if (validate_dims(d) || d->T < 2) return -1;
+    return mixer_bwd_scratch_bytes(d);
+}
+
+int pmb_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs, float* raw,
+                  const float* g, float* d_agent_qs, float* flat_grad_mixer, void* scratch, int64_t scratch_bytes,
+                  pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2 && g && d_agent_qs, "mixer_bwd: bad arguments");
+    return launch_mixer_bwd(d, b, flat_mixer, agent_qs, raw, g, d_agent_qs, flat_grad_mixer, scratch, scratch_bytes,
+                            (cudaStream_t)stream);
+}
+
+int64_t pmb_agent_bwd_workspace_bytes(const pmb_dims* d) {
+    if (validate_dims(d)) return -1;
+    return agent_bwd_scratch(d);
+}
+
+int pmb_agent_unroll_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, const float* x_on,
+                         const float* h_stash, float* gates, const float* d_chosen, float* dpre1,
+                         float* flat_grad_agent, void* scratch, int64_t scratch_bytes, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2, "agent_unroll_bwd: T must be >= 2");
+    PMB_REQUIRE(b && b->obs && b->actions && b->filled && flat_agent && x_on && h_stash && gates && d_chosen && dpre1 &&
+                    flat_grad_agent && scratch, "agent_unroll_bwd: NULL pointer");
+    return agent_bwd(d, b, flat_agent, x_on, h_stash, gates, d_chosen, dpre1, flat_grad_agent, scratch, scratch_bytes,
+                     (cudaStream_t)stream);
+}
+
+int pmb_clip_rmsprop_update(int64_t n, float* flat_p, float* flat_g, float* flat_sq, float* flat_target,
+                            int32_t do_target_sync, double* stats, float lr, float alpha, float eps,
+                            float grad_norm_clip, float* scratch, pmb_stream stream) {
+    PMB_REQUIRE(n > 0 && flat_p && flat_g && flat_sq && stats && scratch, "clip_rmsprop_update: bad arguments");
+    return launch_clip_rmsprop(n, flat_p, flat_g, flat_sq, flat_target, do_target_sync, stats, lr, alpha, eps,
+                               grad_norm_clip, scratch, (cudaStream_t)stream);
+}
+
+int pmb_epsilon_greedy(int64_t rows, int32_t A, const float* q, const int32_t* avail, float epsilon, const float* u,
+                       const float* expo, uint64_t seed, uint64_t offset, int64_t* actions_out, pmb_stream stream) {
+    PMB_REQUIRE(rows >= 0 && A > 0 && q && avail && actions_out, "epsilon_greedy: bad arguments");
+    PMB_REQUIRE((u == nullptr) == (expo == nullptr), "epsilon_greedy: inject both u and expo or neither");
+    return launch_epsilon_greedy(rows, 1, A, q, avail, A, epsilon, u, expo, seed, offset, actions_out,
+                                 (cudaStream_t)stream);
+}
+
+int64_t pmb_select_actions_workspace_bytes(const pmb_dims* d) {
+    if (validate_dims(d)) return -1;
+    const int64_t R = (int64_t)d->B * d->N;
+    return align_up(R * d->H * 4, 256) + align_up(R * d->A * 4, 256);
+}
+
+int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, const float* flat_agent, float* hidden,
+                            float epsilon, const float* u, const float* expo, uint64_t seed, uint64_t offset,
+                            int64_t* actions_out, float* q_out, void* scratch, int64_t scratch_bytes,
+                            pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(b && b->obs && b->avail && flat_agent && hidden && scratch, "select_actions_step: NULL pointer");
+    PMB_REQUIRE(t >= 0 && t < d->T, "select_actions_step: t = %d outside [0, %d)", t, d->T);
+    PMB_REQUIRE((u == nullptr) == (expo == nullptr), "select_actions_step: inject both u and expo or neither");
+    if (scratch_bytes < pmb_select_actions_workspace_bytes(d)) { set_error("select_actions_step: scratch too small"); return PMB_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t R = (int64_t)d->B * d->N;
+    float* x = static_cast<float*>(scratch);
+    float* q = q_out ? q_out : reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(R * d->H * 4, 256));
+    AgentParams ap = agent_params(d, flat_agent);
+    rc = fc1_fwd(d, b, t, 1, ap, x, s);
+    if (rc) return rc;
+    rc = gru_fwd_dispatch(d, ap, R, 1, x, hidden, nullptr, nullptr, q, hidden, s);
+    if (rc) return rc;
+    if (!actions_out) return PMB_OK;
+    return launch_epsilon_greedy(R, d->N, d->A, q, b->avail + (int64_t)t * d->N * d->A, b->avail_sb, epsilon, u, expo,
+                                 seed, offset, actions_out, s);
+}
+
+int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hparams* hp, float* flat_p, float* flat_g,
+                            float* flat_sq, float* flat_target, void* workspace, int64_t workspace_bytes,
+                            double* stats, pmb_stream stream) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2, "train_step: T must be >= 2");
+    PMB_REQUIRE(b && hp && flat_p && flat_g && flat_sq && flat_target && workspace && stats, "train_step: NULL pointer");
+    PMB_REQUIRE(b->obs && b->actions && b->avail && b->reward && b->terminated && b->filled, "train_step: batch field is NULL");
+    PMB_REQUIRE(d->mixer != PMB_MIXER_QMIX || b->state, "train_step: QMIX needs batch.state");
+    cudaStream_t s = (cudaStream_t)stream;
+    WsPlan plan = plan_workspace(d);
+    if (workspace_bytes < plan.total) { set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)plan.total); return PMB_ERR_WORKSPACE; }
+    pmb_ws_views v;
+    fill_views(d, workspace, plan, &v);
+    pmb_layout L;
+    compute_layout(d, &L);
+    const int64_t R = (int64_t)d->B * d->N;
+    AgentParams on = agent_params(d, flat_p), tg = agent_params(d, flat_target);
+
+    if ((rc = launch_stats_reset(stats, s))) return rc;
+    // q_learner.py:47-52 / 58-62: both nets over all T steps
+    if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
+    if ((rc = fc1_fwd(d, b, 0, d->T, tg, v.x_tg, s))) return rc;
+    if ((rc = gru_fwd_dispatch(d, on, R, d->T, v.x_on, nullptr, v.h_stash, v.gates, v.q_on, nullptr, s))) return rc;
+    if ((rc = gru_fwd_dispatch(d, tg, R, d->T, v.x_tg, nullptr, nullptr, nullptr, v.q_tg, nullptr, s))) return rc;
+    // :55-78
+    if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
+    // :81-83 (target mixer first: both passes share the raw buffer, the online one must survive)
+    if (d->mixer != PMB_MIXER_NONE) {
+        if ((rc = launch_mixer_fwd(d, b, flat_target + L.n_agent, v.tmax, 1, v.raw_tg, v.t_tot, s))) return rc;
+        if ((rc = launch_mixer_fwd(d, b, flat_p + L.n_agent, v.chosen, 0, v.raw_on, v.q_tot, s))) return rc;
+    }
+    // :86-97
+    if ((rc = launch_td_loss(d, b, v.q_tot, v.t_tot, hp->gamma, v.g, stats, s))) return rc;
+    // :100-101 backward
+    if (d->mixer != PMB_MIXER_NONE) {
+        if ((rc = launch_mixer_bwd(d, b, flat_p + L.n_agent, v.chosen, v.raw_on, v.g, v.d_chosen, flat_g + L.n_agent,
+                                   v.scratch, v.scratch_bytes, s))) return rc;
+    }
+    if ((rc = agent_bwd(d, b, flat_p, v.x_on, v.h_stash, v.gates, v.d_chosen, v.x_tg, flat_g, v.scratch,
+                        v.scratch_bytes, s))) return rc;
+    // :102-107
+    if (!hp->skip_update) {
+        if ((rc = launch_clip_rmsprop(L.n_total, flat_p, flat_g, flat_sq, flat_target, hp->do_target_sync, stats, hp->lr,
+                                      hp->alpha, hp->eps, hp->grad_norm_clip, v.scratch, s))) return rc;
+    }
+    return PMB_OK;
+}
+
+}  // extern "C"

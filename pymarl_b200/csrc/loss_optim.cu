@@ -1,0 +1,155 @@
+// K4: TD target + masked loss sums + dL/dq_tot   (learners/q_learner.py:39-44, 86-97, 109-116)
+// K6: grad-norm clip + RMSprop + hard target sync  (learners/q_learner.py:102-107, 118-122)
+#include "common.cuh"
+
+namespace pmb {
+
+namespace {
+
+// block-wide sum of 5 doubles, result valid in thread 0
+__device__ __forceinline__ void block_sum5(double (&v)[5], double (*sh)[5]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) sh[w][i] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int ww = 1; ww < (int)(blockDim.x >> 5); ++ww)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) v[i] += sh[ww][i];
+    }
+}
+
+// element index i = m*W + w,  m = b*(T-1) + t.  W = 1 (QMIX / VDN) or N (IQL: mask.expand_as(td)).
+__global__ void __launch_bounds__(256)
+td_loss_kernel(int B, int T, int W, float gamma, const float* __restrict__ q_tot, const float* __restrict__ t_tot,
+               const float* __restrict__ reward, int64_t reward_sb, const uint8_t* __restrict__ terminated,
+               int64_t term_sb, const int64_t* __restrict__ filled, int64_t filled_sb, float* __restrict__ g_out,
+               double* __restrict__ stats) {
+    __shared__ double sh[8][5];
+    const int64_t total = (int64_t)B * (T - 1) * W;
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t m = i / W;
+        int64_t b = m / (T - 1);
+        int t = (int)(m - b * (T - 1));
+        float term = (float)__ldg(terminated + b * term_sb + t);
+        float mask = (float)__ldg(filled + b * filled_sb + t);
+        if (t > 0) mask = mask * (1.f - (float)__ldg(terminated + b * term_sb + (t - 1)));
+        float r = __ldg(reward + b * reward_sb + t);
+        float q = __ldg(q_tot + i);
+        float y = r + (gamma * (1.f - term)) * __ldg(t_tot + i);
+        float td = q - y;
+        float mtd = td * mask;
+        g_out[i] = 2.f * mtd * mask;
+        acc[0] += (double)mask;
+        acc[1] += (double)(mtd * mtd);
+        acc[2] += (double)fabsf(mtd);
+        acc[3] += (double)(q * mask);
+        acc[4] += (double)(y * mask);
+    }
+    block_sum5(acc, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) atomicAdd(stats + i, acc[i]);
+    }
+}
+
+__global__ void stats_reset_kernel(double* stats) {
+    if (threadIdx.x < PMB_S_COUNT) stats[threadIdx.x] = 0.0;
+}
+
+constexpr int OPT_BLOCKS = 256, OPT_THREADS = 256;
+
+// fixed grid-stride assignment -> the partial sums, and their fixed-order total, are deterministic
+__global__ void __launch_bounds__(OPT_THREADS)
+grad_sumsq_kernel(int64_t n, const float* __restrict__ g, double* __restrict__ partial) {
+    __shared__ double sh[OPT_THREADS / 32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = (double)g[i];
+        s += v * v;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < OPT_THREADS / 32; ++w) tot += sh[w];
+        partial[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+rmsprop_apply_kernel(int64_t n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ sq,
+                     float* __restrict__ target, int do_sync, const double* __restrict__ partial,
+                     double* __restrict__ stats, float lr, float alpha, float eps, float clip) {
+    __shared__ float s_scale, s_coef;
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int b = 0; b < OPT_BLOCKS; ++b) tot += partial[b];
+        double mask_sum = stats[PMB_S_MASK_SUM];
+        float scale = (float)(1.0 / mask_sum);
+        float norm = (float)(sqrt(tot) / mask_sum);                 // norm of the normalised gradient
+        float coef = clip / (norm + 1e-6f);
+        coef = coef < 1.f ? coef : 1.f;
+        s_scale = scale;
+        s_coef = coef;
+        if (blockIdx.x == 0) {
+            stats[PMB_S_GRAD_NORM] = (double)norm;
+            stats[PMB_S_CLIP_COEF] = (double)coef;
+            stats[PMB_S_LOSS] = stats[PMB_S_TD2_SUM] / mask_sum;
+        }
+    }
+    __syncthreads();
+    const float scale = s_scale, coef = s_coef;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gv = (g[i] * scale) * coef;
+        float v = sq[i] * alpha + ((1.f - alpha) * gv) * gv;
+        float avg = sqrtf(v) + eps;
+        float pv = p[i] + (-lr * gv) / avg;
+        g[i] = gv;
+        sq[i] = v;
+        p[i] = pv;
+        if (do_sync && target) target[i] = pv;
+    }
+}
+
+}  // namespace
+
+int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
+                   float* g_out, double* stats, cudaStream_t s) {
+    const int W = d->mixer == PMB_MIXER_NONE ? d->N : 1;
+    const int64_t total = (int64_t)d->B * (d->T - 1) * W;
+    if (total <= 0) return PMB_OK;
+    int64_t grid = ceil_div(total, 256);
+    int64_t cap = 8 * (int64_t)sm_count();
+    if (grid > cap) grid = cap;
+    td_loss_kernel<<<(unsigned)grid, 256, 0, s>>>(d->B, d->T, W, gamma, q_tot, t_tot, b->reward, b->reward_sb,
+                                                  b->terminated, b->terminated_sb, b->filled, b->filled_sb, g_out,
+                                                  stats);
+    PMB_LAUNCH_CHECK("td_loss_kernel");
+    return PMB_OK;
+}
+
+int launch_stats_reset(double* stats, cudaStream_t s) {
+    stats_reset_kernel<<<1, 32, 0, s>>>(stats);
+    PMB_LAUNCH_CHECK("stats_reset_kernel");
+    return PMB_OK;
+}
+
+int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target, int do_sync, double* stats, float lr,
+                        float alpha, float eps, float clip, float* scratch, cudaStream_t s) {
+    if (n <= 0) return PMB_OK;
+    double* partial = reinterpret_cast<double*>(scratch);          // OPT_BLOCKS doubles (<= 4096 floats)
+    grad_sumsq_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, s>>>(n, g, partial);
+    PMB_LAUNCH_CHECK("grad_sumsq_kernel");
+    rmsprop_apply_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, s>>>(n, p, g, sq, target, do_sync, partial, stats, lr, alpha,
+                                                           eps, clip);
+    PMB_LAUNCH_CHECK("rmsprop_apply_kernel");
+    return PMB_OK;
+}
+
+}  // namespace pmb

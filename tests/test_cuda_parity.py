@@ -1,0 +1,305 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the
+Python mirror and the C ABI, against (a) the golden fixtures produced by the reference and
+(b) the numpy oracle on seeded synthetic batches.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8c): integer outputs bit-exact;
+fp32 tier: Q, Q_tot, loss, grad_norm, gradients and post-update parameters within 1e-5
+norm-wise relative error (max|a-b| / max|b|)."""
+import copy
+
+import numpy as np
+import pytest
+import torch as th
+
+from golden_utils import Golden, LEARNER_CASES, rel_err
+from oracle import qlearner_oracle as orc
+from pymarl_b200.synthetic import SmacShape, numpy_episode_fields, default_args, SMAC_SHAPES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _tm_to_bm(x, B, N):
+    """time-major [T, B*N, A] -> batch-major [B, T, N, A]"""
+    T = x.shape[0]
+    return x.view(T, B, N, -1).permute(1, 0, 2, 3).contiguous().cpu().numpy()
+
+
+@pytest.mark.parametrize("case", LEARNER_CASES)
+def test_forward_and_grads_match_reference(case):
+    from cuda_utils import learner_from_golden, to_batch
+    g = Golden(case)
+    learner, _ = learner_from_golden(g, grad_norm_clip=1e30)
+    batch = to_batch(g.shape, g.batch_fields())
+    learner.train(batch, 0, 0)
+    B, N = batch.batch_size, g.shape.n_agents
+    ws = learner.workspace_views(learner._last_dims)
+    ref = g.group("f32/fw")
+    ref64 = g.group("f64/fw")
+    assert rel_err(_tm_to_bm(ws["q_on"], B, N), ref["mac_out"]) < TOL
+    assert rel_err(_tm_to_bm(ws["q_tg"], B, N), ref["target_mac_out"]) < TOL
+    assert rel_err(ws["chosen"].cpu().numpy(), ref["chosen"]) < TOL
+    # the double-Q arg-max can legitimately flip on fp32 near-ties; fp64 referee decides
+    tm = ws["tmax"].cpu().numpy()
+    bad = np.abs(tm - ref["target_max"]) > TOL * np.abs(ref["target_max"]).max()
+    assert bad.mean() < 0.02, "target_max mismatches: %d" % bad.sum()
+    if not bad.any():
+        if g.meta["mixer"] is not None:
+            assert rel_err(ws["q_tot"].cpu().numpy(), ref["q_tot"]) < TOL
+            assert rel_err(ws["t_tot"].cpu().numpy(), ref["target_tot"]) < TOL
+        st = learner.stats()
+        for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+            r = float(g["f32/step0/stat/" + key]) if key != "grad_norm" else None
+            if r is not None:
+                assert abs(st[key] - r) <= TOL * max(1.0, abs(r)), (key, st[key], r)
+        # raw gradients (clip disabled): .grad views hold the normalised gradient
+        for k, v in g.group("f32/grad/agent").items():
+            got = dict(learner.mac.agent.named_parameters())[k].grad.cpu().numpy()
+            assert rel_err(got, v) < 2 * TOL, k
+        for k, v in g.group("f32/grad/mixer").items():
+            got = dict(learner.mixer.named_parameters())[k].grad.cpu().numpy()
+            assert rel_err(got, v) < 2 * TOL, k
+    del ref64
+
+
+@pytest.mark.parametrize("case", LEARNER_CASES)
+def test_train_steps_match_reference(case):
+    from cuda_utils import learner_from_golden, to_batch, state_np
+    g = Golden(case)
+    learner, logger = learner_from_golden(g)
+    batch = to_batch(g.shape, g.batch_fields())
+    for step, (t_env, ep) in enumerate(g.episode_schedule()):
+        learner.train(batch, t_env, ep)
+        st = learner.stats()
+        for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+            r = float(g["f32/step%d/stat/%s" % (step, key)])
+            assert abs(st[key] - r) <= 3 * TOL * max(1.0, abs(r)), (step, key, st[key], r)
+            assert abs(logger.stats[key][-1][1] - r) <= 3 * TOL * max(1.0, abs(r)), (step, key)
+        pre = "f32/step%d/" % step
+        # post-update parameters: RMSprop turns tiny gradient noise into +-lr-sized steps, so the
+        # comparison is relative to the tensor magnitude and refereed by the fp64 reference run
+        for k, v in g.group(pre + "agent").items():
+            assert rel_err(state_np(learner.mac.agent)[k], v) < 5 * TOL, (step, k)
+        for k, v in g.group(pre + "mixer").items():
+            assert rel_err(state_np(learner.mixer)[k], v) < 5 * TOL, (step, k)
+        for k, v in g.group(pre + "target_agent").items():
+            assert rel_err(state_np(learner.target_mac.agent)[k], v) < 5 * TOL, (step, k)
+        for k, v in g.group(pre + "target_mixer").items():
+            assert rel_err(state_np(learner.target_mixer)[k], v) < 5 * TOL, (step, k)
+    assert logger.infos.count("Updated target network") == 1
+    sd = learner.optimiser.state_dict()
+    flat = np.concatenate([sd["state"][i]["square_avg"].cpu().numpy().ravel() for i in range(len(learner.params))])
+    last = g.meta["n_steps"] - 1
+    assert rel_err(flat, g["f32/step%d/square_avg_flat" % last]) < 1e-4
+
+
+def _oracle_learner(shape, args, seed):
+    rng = np.random.default_rng(seed)
+    d_in = shape.obs_dim + (shape.n_actions if args.obs_last_action else 0) + (shape.n_agents if args.obs_agent_id else 0)
+    agent = orc.init_params(orc.agent_param_shapes(d_in, args.rnn_hidden_dim, shape.n_actions), rng)
+    mixer = orc.init_params(orc.qmix_param_shapes(shape.state_dim, shape.n_agents, args.mixing_embed_dim), rng) \
+        if args.mixer == "qmix" else {}
+    lr = orc.OracleQLearner(agent, mixer, args)
+    for k in lr.target_agent:
+        lr.target_agent[k] = (lr.target_agent[k] + 0.05 * rng.standard_normal(lr.target_agent[k].shape)).astype(np.float32)
+    for k in lr.target_mixer_p:
+        lr.target_mixer_p[k] = (lr.target_mixer_p[k] + 0.02 * rng.standard_normal(lr.target_mixer_p[k].shape)).astype(np.float32)
+    return lr
+
+
+@pytest.mark.parametrize("shape_name,B,T,mixer,strided", [
+    ("3m", 32, 60, "qmix", False),            # BASELINE config 1, full size
+    ("2s3z", 24, 30, "qmix", True),
+    ("MMM2", 12, 20, "vdn", False),
+    ("MMM2", 12, 20, None, True),
+    ("27m_vs_30m", 6, 12, "qmix", False),
+])
+def test_train_step_matches_oracle(shape_name, B, T, mixer, strided):
+    """Seeded synthetic SMAC-shaped batches, one full train step vs the numpy oracle (which is
+    itself pinned to the reference by tests/test_oracle_golden.py)."""
+    from cuda_utils import build_learner, to_batch, state_np
+    shape = SMAC_SHAPES[shape_name]
+    args = default_args(shape, mixer=mixer, learner_log_interval=0)
+    T_full = T + 5 if strided else T
+    fields = numpy_episode_fields(shape, B, T_full, seed=42, ragged=True)
+    olr = _oracle_learner(shape, copy.copy(args), seed=7)
+    learner, _ = build_learner(shape, args, olr.agent, olr.target_agent, olr.mixer_p, olr.target_mixer_p)
+    batch = to_batch(shape, fields)
+    if strided:
+        # run.py:211-212: batch[:, :max_t_filled] keeps the full-T batch stride
+        fields = {k: v[:, :T] for k, v in fields.items()}
+        batch = batch[:, :T]
+        assert not batch["obs"].is_contiguous()
+    stats, raw_grads, fw = olr.train(fields, 0, 200)            # includes a target sync
+    learner.train(batch, 0, 200)
+    st = learner.stats()
+    for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+        assert abs(st[key] - stats[key]) <= 2 * TOL * max(1.0, abs(stats[key])), (key, st[key], stats[key])
+    ws = learner.workspace_views(learner._last_dims)
+    assert rel_err(_tm_to_bm(ws["q_on"], B, shape.n_agents), fw["mac_out"]) < TOL
+    for k, v in olr.agent.items():
+        assert rel_err(state_np(learner.mac.agent)[k], v) < 5 * TOL, k
+        assert rel_err(state_np(learner.target_mac.agent)[k], olr.target_agent[k]) < 5 * TOL, k
+    for k, v in olr.mixer_p.items():
+        assert rel_err(state_np(learner.mixer)[k], v) < 5 * TOL, k
+
+
+def test_target_select_bit_exact_on_reference_q():
+    """K2 in isolation on the reference's own Q tensors: indices and gathered values bit-exact."""
+    import ctypes as C
+    from pymarl_b200 import _lib
+    for case in LEARNER_CASES:
+        g = Golden(case)
+        ref, f = g.group("f32/fw"), g.batch_fields()
+        B, T, N, A = ref["mac_out"].shape
+        dims = _lib.make_dims(B, T, N, g.shape.obs_dim, g.shape.state_dim, A, 16, 8, mixer=None,
+                              double_q=g.meta["double_q"])
+        tm = lambda x: th.from_numpy(x).permute(1, 0, 2, 3).reshape(T, B * N, A).contiguous().cuda()
+        q_on, q_tg = tm(ref["mac_out"]), tm(ref["target_mac_out"])
+        keep = []
+        fields = {k: th.from_numpy(v).cuda() for k, v in f.items()}
+        pb = _lib.make_batch(fields, need_state=False, keep=keep)
+        chosen = th.empty(B, T - 1, N, device="cuda")
+        tmax = th.empty(B, T - 1, N, device="cuda")
+        cur = th.empty(B, T - 1, N, dtype=th.int32, device="cuda")
+        _lib.check(_lib.lib().pmb_target_select(C.byref(dims), C.byref(pb), _lib.ptr(q_on), _lib.ptr(q_tg),
+                                                _lib.ptr(chosen), _lib.ptr(tmax), _lib.ptr(cur), _lib.stream_ptr()))
+        np.testing.assert_array_equal(cur.cpu().numpy(), ref["cur_max_actions"])
+        np.testing.assert_array_equal(chosen.cpu().numpy(), ref["chosen"])
+        np.testing.assert_array_equal(tmax.cpu().numpy(), ref["target_max"])
+
+
+def test_epsilon_greedy_bit_exact():
+    from pymarl_b200.components.action_selectors import EpsilonGreedyActionSelector
+    import ctypes as C
+    from pymarl_b200 import _lib
+    g = Golden("select_actions")
+    for ci in range(int(g["n_sel"])):
+        p = "sel%d/" % ci
+        q, avail = th.from_numpy(g[p + "q"]).cuda(), th.from_numpy(g[p + "avail"]).cuda()
+        u, expo = th.from_numpy(g[p + "u"]).cuda().contiguous(), th.from_numpy(g[p + "expo"]).cuda().contiguous()
+        b, n, a = q.shape
+        out = th.empty(b, n, dtype=th.int64, device="cuda")
+        _lib.check(_lib.lib().pmb_epsilon_greedy(b * n, a, _lib.ptr(q), _lib.ptr(avail), C.c_float(float(g[p + "epsilon"])),
+                                                 _lib.ptr(u), _lib.ptr(expo), 0, 0, _lib.ptr(out), _lib.stream_ptr()))
+        np.testing.assert_array_equal(out.cpu().numpy(), g[p + "actions"])
+    # philox mode: legal actions only, greedy when epsilon = 0, ~uniform over legal actions when epsilon = 1
+    args = default_args(SmacShape("t", 4, 17, 23, 7, 9), action_rng="philox")
+    sel = EpsilonGreedyActionSelector(args)
+    q = th.randn(4096, 4, 7, device="cuda")
+    avail = (th.rand(4096, 4, 7, device="cuda") < 0.5).int()
+    avail[..., 3] = 1
+    acts = sel.select_action(q, avail, t_env=0)                      # epsilon = 1
+    assert bool(avail.gather(2, acts[..., None]).all())
+    greedy = sel.select_action(q, avail, t_env=0, test_mode=True)
+    ref = q.masked_fill(avail == 0, -float("inf")).argmax(2)
+    assert bool((greedy == ref).all())
+    frac3 = (acts == 3).float().mean().item()
+    exp3 = (1.0 / avail.sum(-1).float()).mean().item()
+    assert abs(frac3 - exp3) < 0.02, (frac3, exp3)
+
+
+def test_mac_select_actions_bit_exact():
+    """BasicMAC.select_actions over three consecutive timesteps against the reference's MAC
+    (same generator draws injected): actions bit-exact, hidden state within 1e-5."""
+    from cuda_utils import to_batch
+    from pymarl_b200 import mac_REGISTRY
+    from pymarl_b200.synthetic import make_scheme
+    g = Golden("select_actions")
+    shape = SmacShape("tiny", 4, 17, 23, 7, 9)
+    args = default_args(shape, device="cuda")
+    scheme, groups = make_scheme(shape)
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    mac.cuda()
+    mac.agent.load_state_dict({k: th.from_numpy(v) for k, v in g.group("mac/agent").items()})
+    fields = g.group("mac/in")
+    for device in ("cuda", "cpu"):                     # device-resident and host-resident runner batch
+        batch = to_batch(shape, fields, device=device)
+        mac.init_hidden(batch.batch_size)
+        for t in range(3):
+            u, expo = th.from_numpy(g["mac/t%d/u" % t]).cuda(), th.from_numpy(g["mac/t%d/expo" % t]).cuda()
+            mac.action_selector.draw = lambda q, u=u, expo=expo: (u.contiguous(), expo.reshape(-1, expo.shape[-1]).contiguous())
+            acts = mac.select_actions(batch, t_ep=t, t_env=20000)
+            np.testing.assert_array_equal(acts.cpu().numpy(), g["mac/t%d/actions" % t])
+            assert rel_err(mac.hidden_states.cpu().numpy(), g["mac/t%d/hidden" % t]) < TOL
+            assert mac.action_selector.epsilon == float(g["mac/t%d/epsilon" % t])
+
+
+def test_modules_forward_match_oracle():
+    """RNNAgent.forward and QMixer.forward as standalone modules (the reference's module API)."""
+    from pymarl_b200.modules.agents import REGISTRY as agent_REGISTRY
+    from pymarl_b200 import QMixer
+    shape = SMAC_SHAPES["2s3z"]
+    args = default_args(shape)
+    rng = np.random.default_rng(3)
+    d_in = shape.obs_dim + shape.n_actions + shape.n_agents
+    agent = agent_REGISTRY["rnn"]({"1d": (d_in,)}, args).cuda()
+    p = {k: v.detach().cpu().numpy() for k, v in agent.state_dict().items()}
+    x = rng.standard_normal((37, d_in)).astype(np.float32)
+    h = rng.standard_normal((37, 64)).astype(np.float32)
+    q, h2 = agent(th.from_numpy(x).cuda(), th.from_numpy(h).cuda())
+    qo, ho = orc.rnn_agent_forward(p, x, h)
+    assert rel_err(q.cpu().numpy(), qo) < TOL and rel_err(h2.cpu().numpy(), ho) < TOL
+    mixer = QMixer(args).cuda()
+    mp = {k: v.detach().cpu().numpy() for k, v in mixer.state_dict().items()}
+    qs = rng.standard_normal((5, 9, shape.n_agents)).astype(np.float32)
+    st = rng.standard_normal((5, 9, shape.state_dim)).astype(np.float32)
+    y = mixer(th.from_numpy(qs).cuda(), th.from_numpy(st).cuda())
+    assert y.shape == (5, 9, 1)
+    assert rel_err(y.cpu().numpy(), orc.qmixer_forward(mp, qs, st)) < TOL
+
+
+def test_step_is_deterministic_and_host_batch_equals_device_batch():
+    """Run-to-run bit reproducibility (no float atomics on the gradient path) and the e2e
+    path (host-resident batch, H2D inside train) gives the same bits as a device batch."""
+    from cuda_utils import build_learner, to_batch, state_np
+    shape = SMAC_SHAPES["2s3z"]
+    fields = numpy_episode_fields(shape, 64, 40, seed=9, ragged=True)
+    outs = []
+    for device in ("cuda", "cuda", "cpu"):
+        args = default_args(shape, mixer="qmix", learner_log_interval=0)
+        olr = _oracle_learner(shape, copy.copy(args), seed=11)
+        learner, _ = build_learner(shape, args, olr.agent, olr.target_agent, olr.mixer_p, olr.target_mixer_p)
+        batch = to_batch(shape, fields, device=device)
+        for step in range(2):
+            learner.train(batch, step, 0)
+        outs.append((state_np(learner.mac.agent), state_np(learner.mixer), learner.stats()))
+    for other in outs[1:]:
+        for k in outs[0][0]:
+            np.testing.assert_array_equal(outs[0][0][k], other[0][k])
+        for k in outs[0][1]:
+            np.testing.assert_array_equal(outs[0][1][k], other[1][k])
+        assert outs[0][2]["grad_norm"] == other[2]["grad_norm"]
+
+
+def test_full_size_properties_27m():
+    """BASELINE config 4 shapes at a GPU-sized batch: properties that do not need the oracle.
+    (1) VDN-style linearity of the loss sums: the stats of a batch equal the sum of the stats
+    of its two halves; (2) un-normalised gradients add up the same way (data-parallel
+    invariant used by the NCCL path); (3) padded episodes do not change the result."""
+    from cuda_utils import build_learner, to_batch
+    shape = SMAC_SHAPES["27m_vs_30m"]
+    B, T = 64, 60
+    fields = numpy_episode_fields(shape, B, T, seed=5, ragged=True)
+    args = default_args(shape, mixer="qmix", learner_log_interval=0, grad_norm_clip=1e30)
+    olr = _oracle_learner(shape, copy.copy(args), seed=13)
+
+    def run(sub):
+        a = copy.copy(args)
+        learner, _ = build_learner(shape, a, olr.agent, olr.target_agent, olr.mixer_p, olr.target_mixer_p)
+        learner.train(to_batch(shape, sub), 0, 0)
+        st = learner.last_stats.clone().cpu().numpy()
+        g = learner._flat["g"].clone().double().cpu().numpy() * st[0]       # back to the un-normalised gradient
+        return st, g
+    full_st, full_g = run(fields)
+    h1_st, h1_g = run({k: v[:B // 2] for k, v in fields.items()})
+    h2_st, h2_g = run({k: v[B // 2:] for k, v in fields.items()})
+    for i in range(5):
+        assert abs(full_st[i] - (h1_st[i] + h2_st[i])) <= 1e-5 * max(1.0, abs(full_st[i])), i
+    assert rel_err(h1_g + h2_g, full_g) < 1e-4
+    # (3) append all-padding episodes: loss sums and gradients unchanged
+    pad = {k: np.concatenate([v, np.zeros_like(v[:8])], 0) for k, v in fields.items()}
+    pad_st, pad_g = run(pad)
+    for i in range(5):
+        assert abs(full_st[i] - pad_st[i]) <= 1e-6 * max(1.0, abs(full_st[i])), i
+    assert rel_err(pad_g, full_g) < 1e-5
