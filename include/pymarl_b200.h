@@ -211,6 +211,13 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
                             float* flat_p, float* flat_g, float* flat_sq, float* flat_target,
                             void* workspace, int64_t workspace_bytes, double* stats, pmb_stream stream);
 
+/* Per-kernel timing of the calls issued between begin and end (CUDA events recorded on the
+ * launch stream between the kernels; bench.py uses it for the roofline of the dominant
+ * kernel).  ms_host[i] / names_host[i*names_stride] are HOST buffers. */
+int64_t pmb_launch_count(void);      /* kernels launched by this library since it was loaded */
+int pmb_profile_begin(void);
+int pmb_profile_end(float* ms_host, char* names_host, int32_t names_stride, int32_t max_phases, int32_t* n_out);
+
 /* views into the learner workspace, for tests and the Python mirror */
 typedef struct pmb_ws_views {
     float *x_on, *x_tg, *h_stash, *gates, *q_on, *q_tg, *chosen, *tmax, *raw_on, *raw_tg,

@@ -68,6 +68,9 @@ _P = C.c_void_p
 _SIGS = {
     "pmb_last_error": (C.c_char_p, []),
     "pmb_version": (C.c_int, []),
+    "pmb_launch_count": (C.c_int64, []),
+    "pmb_profile_begin": (C.c_int, []),
+    "pmb_profile_end": (C.c_int, [C.POINTER(C.c_float), C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "pmb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)]),
     "pmb_flat_layout": (C.c_int, [C.POINTER(Dims), C.POINTER(Layout)]),
     "pmb_learner_workspace_bytes": (C.c_int64, [C.POINTER(Dims)]),
@@ -109,6 +112,20 @@ def lib():
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def profile_begin():
+    check(lib().pmb_profile_begin(), "pmb_profile_begin")
+
+
+def profile_end(max_phases=48, stride=40):
+    """-> list of (phase name, milliseconds) for the calls issued since profile_begin()."""
+    ms = (C.c_float * max_phases)()
+    names = C.create_string_buffer(max_phases * stride)
+    n = C.c_int32(0)
+    check(lib().pmb_profile_end(ms, names, stride, max_phases, C.byref(n)), "pmb_profile_end")
+    raw = names.raw
+    return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]
 
 
 def check(rc, what=""):

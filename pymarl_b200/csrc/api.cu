@@ -32,6 +32,34 @@ int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target,
                         float alpha, float eps, float clip, float* scratch, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
+
+// ---- optional per-phase timing (pmb_profile_begin / pmb_profile_end) --------------------------
+// When armed, the step records a CUDA event on the launch stream between its kernels; the
+// host reads the elapsed times after the step.  Disarmed (the default) it costs one branch.
+constexpr int kMaxPhases = 48;
+struct PhaseTimer {
+    bool armed = false;
+    int n = 0;
+    cudaEvent_t ev[kMaxPhases + 1];
+    const char* name[kMaxPhases];
+    bool created = false;
+};
+static PhaseTimer g_timer;
+
+static void phase_mark(cudaStream_t s, const char* name) {
+    PhaseTimer& t = g_timer;
+    if (!t.armed) return;
+    if (!t.created) {
+        for (int i = 0; i <= kMaxPhases; ++i) cudaEventCreate(&t.ev[i]);
+        t.created = true;
+    }
+    if (t.n > kMaxPhases) return;
+    cudaEventRecord(t.ev[t.n], s);           // event i closes phase i-1 and opens phase i
+    if (t.n < kMaxPhases) t.name[t.n] = name;
+    t.n++;
+}
+#define PHASE(s, name) phase_mark(s, name)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -177,8 +205,10 @@ int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, co
     AgentGrads gr = agent_grads(d, flat_grad_agent);
     const int64_t R = (int64_t)d->B * d->N, rows = (int64_t)d->T * R;
     const int H = d->H;
+    PHASE(s, "gru_unroll_bwd");
     int rc = gru_bwd_dispatch(d, b, ap, x_on, h_stash, gates, d_chosen, dpre1, s);
     if (rc) return rc;
+    PHASE(s, "dW_rnn_gemm_atb");
     // rnn.weight_ih / bias_ih:  [da_r | da_z | da_n]^T . x
     rc = launch_gemm_atb(gates, dense_map(4 * H), 3 * H, x_on, dense_map(H), H, rows, gr.w_ih, H, gr.b_ih, scratch,
                          scratch_bytes, s);
@@ -190,12 +220,14 @@ int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, co
     rc = launch_gemm_atb(gates + 3 * H, dense_map(4 * H), H, h_stash, dense_map(H), H, rows,
                          gr.w_hh + (int64_t)2 * H * H, H, gr.b_hh + 2 * H, scratch, scratch_bytes, s);
     if (rc) return rc;
+    PHASE(s, "dW_fc1_gemm_atb");
     // fc1.weight[:, :O] / fc1.bias:  dpre1^T . obs   (dpre1 time major, obs batch major)
     RowMap dmap{(int64_t)d->N * H, R * H, (int64_t)H, d->T, d->N};
     RowMap omap{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, d->T, d->N};
     rc = launch_gemm_atb(dpre1, dmap, H, b->obs, omap, d->O, rows, gr.fc1_w, d_in_of(d), gr.fc1_b, scratch,
                          scratch_bytes, s);
     if (rc) return rc;
+    PHASE(s, "agent_scatter_grads");
     return scatter_grads_dispatch(d, b, h_stash, dpre1, d_chosen, gr, scratch, scratch_bytes, s);
 }
 
@@ -207,6 +239,35 @@ using namespace pmb;
 extern "C" {
 
 const char* pmb_last_error(void) { return g_err; }
+
+int64_t pmb_launch_count(void) { return (int64_t)g_launch_count; }
+
+int pmb_profile_begin(void) {
+    g_timer.armed = true;
+    g_timer.n = 0;
+    return PMB_OK;
+}
+
+int pmb_profile_end(float* ms_host, char* names_host, int32_t names_stride, int32_t max_phases, int32_t* n_out) {
+    PhaseTimer& t = g_timer;
+    t.armed = false;
+    int n = t.n > 0 ? t.n - 1 : 0;                 // n+1 events delimit n phases
+    if (n > kMaxPhases) n = kMaxPhases;
+    if (n > 0) PMB_CUDA(cudaEventSynchronize(t.ev[n]));
+    int m = n < max_phases ? n : max_phases;
+    for (int i = 0; i < m; ++i) {
+        float ms = 0.f;
+        PMB_CUDA(cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]));
+        if (ms_host) ms_host[i] = ms;
+        if (names_host && names_stride > 0) {
+            strncpy(names_host + (size_t)i * names_stride, t.name[i], names_stride - 1);
+            names_host[(size_t)i * names_stride + names_stride - 1] = 0;
+        }
+    }
+    if (n_out) *n_out = m;
+    t.n = 0;
+    return PMB_OK;
+}
 int pmb_version(void) { return 100; }
 
 int pmb_device_info(int32_t* sm, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin) {
@@ -406,20 +467,29 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
 
     if ((rc = launch_stats_reset(stats, s))) return rc;
     // q_learner.py:47-52 / 58-62: both nets over all T steps
+    PHASE(s, "fc1_fwd_online");
     if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
+    PHASE(s, "fc1_fwd_target");
     if ((rc = fc1_fwd(d, b, 0, d->T, tg, v.x_tg, s))) return rc;
+    PHASE(s, "gru_unroll_fwd_online");
     if ((rc = gru_fwd_dispatch(d, on, R, d->T, v.x_on, nullptr, v.h_stash, v.gates, v.q_on, nullptr, s))) return rc;
+    PHASE(s, "gru_unroll_fwd_target");
     if ((rc = gru_fwd_dispatch(d, tg, R, d->T, v.x_tg, nullptr, nullptr, nullptr, v.q_tg, nullptr, s))) return rc;
     // :55-78
+    PHASE(s, "target_select");
     if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
     // :81-83 (target mixer first: both passes share the raw buffer, the online one must survive)
     if (d->mixer != PMB_MIXER_NONE) {
+        PHASE(s, "mixer_fwd_target");
         if ((rc = launch_mixer_fwd(d, b, flat_target + L.n_agent, v.tmax, 1, v.raw_tg, v.t_tot, s))) return rc;
+        PHASE(s, "mixer_fwd_online");
         if ((rc = launch_mixer_fwd(d, b, flat_p + L.n_agent, v.chosen, 0, v.raw_on, v.q_tot, s))) return rc;
     }
     // :86-97
+    PHASE(s, "td_loss");
     if ((rc = launch_td_loss(d, b, v.q_tot, v.t_tot, hp->gamma, v.g, stats, s))) return rc;
     // :100-101 backward
+    PHASE(s, "mixer_bwd");
     if (d->mixer != PMB_MIXER_NONE) {
         if ((rc = launch_mixer_bwd(d, b, flat_p + L.n_agent, v.chosen, v.raw_on, v.g, v.d_chosen, flat_g + L.n_agent,
                                    v.scratch, v.scratch_bytes, s))) return rc;
@@ -427,10 +497,12 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     if ((rc = agent_bwd(d, b, flat_p, v.x_on, v.h_stash, v.gates, v.d_chosen, v.x_tg, flat_g, v.scratch,
                         v.scratch_bytes, s))) return rc;
     // :102-107
+    PHASE(s, "clip_rmsprop_update");
     if (!hp->skip_update) {
         if ((rc = launch_clip_rmsprop(L.n_total, flat_p, flat_g, flat_sq, flat_target, hp->do_target_sync, stats, hp->lr,
                                       hp->alpha, hp->eps, hp->grad_norm_clip, v.scratch, s))) return rc;
     }
+    PHASE(s, "end");
     return PMB_OK;
 }
 

@@ -16,8 +16,10 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         cudaError_t _e = (call);                                                    \
         if (_e != cudaSuccess) return ::pmb::cuda_fail(_e, #call, __FILE__, __LINE__); \
     } while (0)
+extern long long g_launch_count;     // kernels launched by this library (pmb_launch_count)
 #define PMB_LAUNCH_CHECK(name)                                                      \
     do {                                                                            \
+        ++::pmb::g_launch_count;                                                    \
         cudaError_t _e = cudaGetLastError();                                        \
         if (_e != cudaSuccess) return ::pmb::cuda_fail(_e, name, __FILE__, __LINE__); \
     } while (0)
