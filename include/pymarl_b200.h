@@ -204,6 +204,13 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
                             uint64_t seed, uint64_t offset, int64_t* actions_out, float* q_out,
                             void* scratch, int64_t scratch_bytes, pmb_stream stream);
 
+/* ---- bf16 tensor-core GEMM (tcgen05, fp32 accumulate):  c[m][n] = sum_k a[m][k] w[n][k] + bias[n] ----
+ * a [m][k], w [n][k], c [m][n] fp32 row major.  The building block of the bf16 tier, exported
+ * for unit tests and diagnostics. */
+int64_t pmb_gemm_bf16_workspace_bytes(int32_t n, int32_t k);
+int pmb_gemm_bf16_tn(int64_t m, int32_t n, int32_t k, const float* a, const float* w, const float* bias, float* c,
+                     void* scratch, int64_t scratch_bytes, pmb_stream stream);
+
 /* ---- whole learner step (learners/q_learner.py:37-107) ---------------------------------- */
 /* flat_p / flat_g / flat_sq: online params, grads, RMSprop square_avg (n_total floats);
  * flat_target: target params.  workspace >= pmb_learner_workspace_bytes().  stats: 16 doubles. */

@@ -92,6 +92,8 @@ _SIGS = {
     "pmb_select_actions_workspace_bytes": (C.c_int64, [C.POINTER(Dims)]),
     "pmb_select_actions_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.c_int32, _P, _P, C.c_float, _P, _P,
                                           C.c_uint64, C.c_uint64, _P, _P, _P, C.c_int64, _P]),
+    "pmb_gemm_bf16_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "pmb_gemm_bf16_tn": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "pmb_qlearner_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.POINTER(HParams), _P, _P, _P, _P, _P,
                                           C.c_int64, _P, _P]),
 }

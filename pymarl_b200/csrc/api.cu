@@ -2,6 +2,7 @@
 // the whole learner step (learners/q_learner.py:37-107).
 #include <stdarg.h>
 #include <string.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace pmb {
@@ -30,6 +31,20 @@ int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, co
 int launch_stats_reset(double* stats, cudaStream_t s);
 int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target, int do_sync, double* stats, float lr,
                         float alpha, float eps, float clip, float* scratch, cudaStream_t s);
+
+// tc_gemm.cu (bf16 tcgen05 tier)
+int64_t tc_packed_elems(int Ncols, int K);
+int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nseg, int K, __nv_bfloat16* out,
+              cudaStream_t s);
+int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
+                  const float* bias, float* C, int64_t ldc, cudaStream_t s);
+int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
+                    float* x_on, float* x_tg, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+int64_t tc_fc1_scratch_bytes(const pmb_dims* d);
+int64_t tc_mixer_scratch_bytes(const pmb_dims* d);
+int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
+                 __nv_bfloat16* raw_out, float* raw_f32, float* q_tot, void* scratch, int64_t scratch_bytes,
+                 cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
@@ -162,6 +177,11 @@ WsPlan plan_workspace(const pmb_dims* d) {
     int64_t sc = agent_bwd_scratch(d);
     int64_t mb = mixer_bwd_scratch_bytes(d);
     if (mb > sc) sc = mb;
+    if (d->precision == PMB_PREC_BF16) {
+        int64_t f = tc_fc1_scratch_bytes(d);
+        if (f > sc) sc = f;
+        if (d->mixer == PMB_MIXER_QMIX) { int64_t m2 = tc_mixer_scratch_bytes(d); if (m2 > sc) sc = m2; }
+    }
     if (sc < 4096 * 4) sc = 4096 * 4;
     p.off[14] = off;
     p.scratch_bytes = align_up(sc, 256);
@@ -446,6 +466,23 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
                                  seed, offset, actions_out, s);
 }
 
+int64_t pmb_gemm_bf16_workspace_bytes(int32_t n, int32_t k) {
+    return align_up(tc_packed_elems((int)align_up(n, 32), k) * 2, 256);
+}
+
+int pmb_gemm_bf16_tn(int64_t m, int32_t n, int32_t k, const float* a, const float* w, const float* bias, float* c,
+                     void* scratch, int64_t scratch_bytes, pmb_stream stream) {
+    PMB_REQUIRE(m > 0 && n > 0 && k > 0 && a && w && c && scratch, "gemm_bf16_tn: bad arguments");
+    if (scratch_bytes < pmb_gemm_bf16_workspace_bytes(n, k)) { set_error("gemm_bf16_tn: scratch too small"); return PMB_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
+    const float* ptrs[1] = {w};
+    int rows[1] = {n}, lds[1] = {k};
+    int rc = tc_pack_w(ptrs, rows, lds, 1, k, wp, s);
+    if (rc) return rc;
+    return tc_gemm_plain(a, dense_map(k), m, k, wp, (int)align_up(n, 32), n, bias, c, n, s);
+}
+
 int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hparams* hp, float* flat_p, float* flat_g,
                             float* flat_sq, float* flat_target, void* workspace, int64_t workspace_bytes,
                             double* stats, pmb_stream stream) {
@@ -467,10 +504,17 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
 
     if ((rc = launch_stats_reset(stats, s))) return rc;
     // q_learner.py:47-52 / 58-62: both nets over all T steps
-    PHASE(s, "fc1_fwd_online");
-    if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
-    PHASE(s, "fc1_fwd_target");
-    if ((rc = fc1_fwd(d, b, 0, d->T, tg, v.x_tg, s))) return rc;
+    const bool tc_agent = d->precision == PMB_PREC_BF16 && d->H == 64;
+    const bool tc_mixer = d->precision == PMB_PREC_BF16 && d->mixer == PMB_MIXER_QMIX && d->E == 32;
+    if (tc_agent) {
+        PHASE(s, "fc1_fwd_both_tc");
+        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, v.scratch, v.scratch_bytes, s))) return rc;
+    } else {
+        PHASE(s, "fc1_fwd_online");
+        if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
+        PHASE(s, "fc1_fwd_target");
+        if ((rc = fc1_fwd(d, b, 0, d->T, tg, v.x_tg, s))) return rc;
+    }
     PHASE(s, "gru_unroll_fwd_online");
     if ((rc = gru_fwd_dispatch(d, on, R, d->T, v.x_on, nullptr, v.h_stash, v.gates, v.q_on, nullptr, s))) return rc;
     PHASE(s, "gru_unroll_fwd_target");
@@ -479,7 +523,14 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     PHASE(s, "target_select");
     if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
     // :81-83 (target mixer first: both passes share the raw buffer, the online one must survive)
-    if (d->mixer != PMB_MIXER_NONE) {
+    if (tc_mixer) {
+        PHASE(s, "mixer_fwd_target_tc");
+        if ((rc = tc_mixer_fwd(d, b, mixer_params(d, flat_target + L.n_agent), v.tmax, 1, nullptr, nullptr, v.t_tot,
+                               v.scratch, v.scratch_bytes, s))) return rc;
+        PHASE(s, "mixer_fwd_online_tc");
+        if ((rc = tc_mixer_fwd(d, b, mixer_params(d, flat_p + L.n_agent), v.chosen, 0, nullptr, v.raw_on, v.q_tot,
+                               v.scratch, v.scratch_bytes, s))) return rc;
+    } else if (d->mixer != PMB_MIXER_NONE) {
         PHASE(s, "mixer_fwd_target");
         if ((rc = launch_mixer_fwd(d, b, flat_target + L.n_agent, v.tmax, 1, v.raw_tg, v.t_tot, s))) return rc;
         PHASE(s, "mixer_fwd_online");

@@ -1,0 +1,502 @@
+// bf16 tensor-core tier: C[m, n] = sum_k A[m, k] * W[n, k] on tcgen05 with fp32 accumulation in TMEM.
+//
+//   A  fp32 in global memory, addressed through RowMap (the EpisodeBatch fields are consumed in
+//      place).  Eight producer warps stream it with coalesced loads, convert to bf16 in registers
+//      and write the 128-byte-swizzled K-major operand tile into shared memory.
+//   W  packed once per step (pack_w_kernel) into bf16 tiles that already are the shared-memory image
+//      (K-major, 128B swizzle), so one elected thread brings a tile in with a single bulk async copy
+//      (cp.async.bulk, completion on an mbarrier) - no tensor map needed.
+//   D  128 x <=256 fp32 accumulator in TMEM, double buffered (2 x 256 columns): the four epilogue warps
+//      drain pass p with tcgen05.ld while the MMA thread already accumulates pass p+1.
+//
+// Warp roles (448 threads): 0-3 epilogue (warp i owns TMEM lanes 32i..32i+31 = tile rows),
+// 4 TMEM allocator + single-thread tcgen05.mma issuer, 5 W bulk-copy issuer, 6-13 A producers.
+// Pipelines: 4 shared-memory stages (full/empty mbarriers), 2 accumulator buffers (tmem_full/tmem_empty).
+// Persistent over 128-row tiles: grid = min(#tiles, #SMs).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pmb {
+namespace tc {
+
+constexpr int BM = 128;              // rows per tile = UMMA M
+constexpr int BK = 64;               // bf16 elements per k-chunk = one 128-byte swizzle row
+constexpr int BN_MAX = 256;          // columns per pass = UMMA N
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * 128;          // 16 KB
+constexpr int W_STAGE_BYTES = BN_MAX * 128;      // 32 KB
+constexpr int N_EPI_WARPS = 4, MMA_WARP = 4, WLOAD_WARP = 5, FIRST_PROD_WARP = 6, N_PROD_WARPS = 8;
+constexpr int THREADS = 32 * (FIRST_PROD_WARP + N_PROD_WARPS);     // 448
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 256;
+
+struct GemmParams {
+    const float* A;
+    RowMap amap;
+    int64_t M;
+    int K;                 // real reduction length
+    int n_chunks;          // ceil(K / 64)
+    const __nv_bfloat16* Wp;   // packed tiles: pass-major, then k-chunk; each tile ncols_p rows x 128 B
+    int Ncols;             // multiple of 32
+};
+
+__host__ __device__ inline int pass_cols(int Ncols, int p) {
+    int left = Ncols - p * BN_MAX;
+    return left < BN_MAX ? left : BN_MAX;
+}
+__host__ __device__ inline int64_t packed_tile_offset(int Ncols, int n_chunks, int p, int c) {   // in elements
+    return ((int64_t)p * BN_MAX * n_chunks + (int64_t)c * pass_cols(Ncols, p)) * BK;
+}
+
+// ------------------------------------------------------------------------------------------
+// W packing: up to 4 row segments of fp32 [rows, ld] matrices -> bf16 swizzled tiles
+// ------------------------------------------------------------------------------------------
+struct PackSegs {
+    const float* ptr[4];
+    int rows[4];
+    int ld[4];
+    int nseg;
+};
+
+__global__ void __launch_bounds__(256)
+pack_w_kernel(PackSegs segs, int K, int n_chunks, int Ncols, __nv_bfloat16* __restrict__ out) {
+    // one thread per 16-byte chunk (8 bf16) of the packed image
+    const int64_t total = (int64_t)Ncols * n_chunks * 8;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int j = (int)(i & 7);
+    int64_t rc = i >> 3;
+    int col = (int)(rc % Ncols);
+    int c = (int)(rc / Ncols);
+    int p = col / BN_MAX, r = col - p * BN_MAX;
+    const float* src = nullptr;
+    int rr = col;
+    for (int s = 0; s < segs.nseg; ++s) {
+        if (rr < segs.rows[s]) { src = segs.ptr[s] + (int64_t)rr * segs.ld[s]; break; }
+        rr -= segs.rows[s];
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int k = c * BK + j * 8 + q * 2;
+        float lo = (src && k < K) ? src[k] : 0.f;
+        float hi = (src && k + 1 < K) ? src[k + 1] : 0.f;
+        w[q] = pack_bf16x2(lo, hi);
+    }
+    char* tile = reinterpret_cast<char*>(out + packed_tile_offset(Ncols, n_chunks, p, c));
+    *reinterpret_cast<uint4*>(tile + sw128_offset((uint32_t)r, (uint32_t)j)) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_stage = smem;
+    uint8_t* w_stage = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + W_STAGE_BYTES));
+    uint64_t* full = bars;                 // [STAGES]  producers + W bytes landed
+    uint64_t* empty = bars + STAGES;       // [STAGES]  MMAs that read the stage retired
+    uint64_t* tfull = bars + 2 * STAGES;   // [2]       accumulator complete
+    uint64_t* tempty = tfull + 2;          // [2]       accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], N_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], N_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_tiles = (P.M + BM - 1) / BM;
+    const int n_pass = (P.Ncols + BN_MAX - 1) / BN_MAX;
+
+    if (warp >= FIRST_PROD_WARP) {
+        // ===== A producers: fp32 global -> bf16 swizzled smem =====
+        const int pw = warp - FIRST_PROD_WARP;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // lane l (< 16) keeps the pointer of tile row (pw + 8 l)
+            const float* myptr = nullptr;
+            if (lane < BM / N_PROD_WARPS) {
+                int64_t row = tile * BM + pw + N_PROD_WARPS * lane;
+                if (row < P.M) myptr = P.A + P.amap.offset(row);
+            }
+            for (int p = 0; p < n_pass; ++p) {
+                for (int c = 0; c < P.n_chunks; ++c, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* dst = a_stage + s * A_STAGE_BYTES;
+                    const int k = c * BK + 2 * lane;
+                    float v0[BM / N_PROD_WARPS], v1[BM / N_PROD_WARPS];
+#pragma unroll
+                    for (int l = 0; l < BM / N_PROD_WARPS; ++l) {
+                        const float* rp = reinterpret_cast<const float*>(
+                            __shfl_sync(0xffffffffu, reinterpret_cast<uintptr_t>(myptr), l));
+                        float a = 0.f, b = 0.f;
+                        if (rp != nullptr) {
+                            if (k + 1 < P.K && ((reinterpret_cast<uintptr_t>(rp + k) & 7) == 0)) {
+                                float2 t = __ldg(reinterpret_cast<const float2*>(rp + k));
+                                a = t.x; b = t.y;
+                            } else {
+                                if (k < P.K) a = __ldg(rp + k);
+                                if (k + 1 < P.K) b = __ldg(rp + k + 1);
+                            }
+                        }
+                        v0[l] = a; v1[l] = b;
+                    }
+#pragma unroll
+                    for (int l = 0; l < BM / N_PROD_WARPS; ++l) {
+                        const uint32_t r = pw + N_PROD_WARPS * l;
+                        *reinterpret_cast<uint32_t*>(dst + sw128_offset(r, lane >> 2) + (lane & 3) * 4) =
+                            pack_bf16x2(v0[l], v1[l]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                }
+            }
+        }
+    } else if (warp == WLOAD_WARP) {
+        // ===== W loader: one bulk copy per (pass, k-chunk) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int p = 0; p < n_pass; ++p) {
+                    const uint32_t bytes = (uint32_t)pass_cols(P.Ncols, p) * 128u;
+                    for (int c = 0; c < P.n_chunks; ++c, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&full[s], bytes);
+                        bulk_copy_g2s(w_stage + s * W_STAGE_BYTES, P.Wp + packed_tile_offset(P.Ncols, P.n_chunks, p, c),
+                                      bytes, &full[s]);
+                    }
+                }
+        }
+    } else if (warp == MMA_WARP) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, acc_it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int p = 0; p < n_pass; ++p, ++acc_it) {
+                    const int b = acc_it & 1;
+                    const uint32_t idesc = umma_idesc_bf16(BM, pass_cols(P.Ncols, p), 0, 0);
+                    mbar_wait(&tempty[b], ((acc_it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)b * BN_MAX;
+                    for (int c = 0; c < P.n_chunks; ++c, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&full[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(a_stage + s * A_STAGE_BYTES);
+                        const uint32_t w_addr = smem_u32(w_stage + s * W_STAGE_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            umma_bf16(tmem_d, umma_desc_sw128(a_addr + kk * 32, 16, 1024),
+                                      umma_desc_sw128(w_addr + kk * 32, 16, 1024), idesc, (c | kk) != 0);
+                        }
+                        umma_commit(&empty[s]);
+                    }
+                    umma_commit(&tfull[b]);
+                }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> Epi =====
+        uint32_t acc_it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t m = tile * BM + warp * 32 + lane;
+            const bool valid = m < P.M;
+            typename Epi::Row row;
+            epi.begin(row, m, valid);
+            for (int p = 0; p < n_pass; ++p, ++acc_it) {
+                const int b = acc_it & 1;
+                const int ncols = pass_cols(P.Ncols, p);
+                mbar_wait(&tfull[b], (acc_it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t)b * BN_MAX + ((uint32_t)(warp * 32) << 16);
+                for (int g = 0; g < ncols; g += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + g, v);
+                    tmem_wait_ld();
+                    epi.cols(row, m, valid, p * BN_MAX + g, v);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[b]);
+            }
+            epi.end(row, m, valid);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogues
+// ------------------------------------------------------------------------------------------
+struct PlainEpi {           // C[m*ldc + n] = acc + bias[n]
+    struct Row {};
+    float* C; int64_t ldc; const float* bias; int Nreal;
+    __device__ void begin(Row&, int64_t, bool) const {}
+    __device__ void cols(Row&, int64_t m, bool valid, int col0, const uint32_t (&v)[32]) const {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < Nreal) C[m * ldc + col0 + j] = __uint_as_float(v[j]) + (bias ? bias[col0 + j] : 0.f);
+    }
+    __device__ void end(Row&, int64_t, bool) const {}
+};
+
+// fc1 for the online and the target net in one GEMM: columns [0, 64) online, [64, 128) target.
+//   x = relu(acc + tab_id[net][n][h] (bias folded in) + tab_act[net][a_prev][h])
+struct Fc1Epi {
+    struct Row { int64_t out_off; int n; int a_prev; };
+    const float* tab_act;       // [2][A][64]
+    const float* tab_id;        // [2][N][64]   W_id[:, n] + b1 (or just b1 when obs_agent_id is off)
+    const int64_t* actions; int64_t actions_sb;
+    const int64_t* filled;  int64_t filled_sb;
+    float* x_on; float* x_tg;   // [nt][R][64] time major
+    int t0, nt, N, A, use_act;
+    int64_t R;
+    __device__ void begin(Row& r, int64_t m, bool valid) const {
+        r.out_off = 0; r.n = 0; r.a_prev = -1;
+        if (!valid) return;
+        const int tn = nt * N;
+        int64_t b = m / tn;
+        int rem = (int)(m - b * tn);
+        int tl = rem / N;
+        r.n = rem - tl * N;
+        int t = t0 + tl;
+        if (use_act && t > 0 && filled[b * filled_sb + (t - 1)] != 0)
+            r.a_prev = (int)actions[b * actions_sb + (int64_t)(t - 1) * N + r.n];
+        r.out_off = ((int64_t)tl * R + b * N + r.n) * 64;
+    }
+    __device__ void cols(Row& r, int64_t, bool valid, int col0, const uint32_t (&v)[32]) const {
+        if (!valid) return;
+        const int net = col0 >> 6, h0 = col0 & 63;
+        float* out = (net ? x_tg : x_on) + r.out_off + h0;
+        const float4* tid = reinterpret_cast<const float4*>(tab_id + ((int64_t)net * N + r.n) * 64 + h0);
+        const float4* tac = r.a_prev >= 0 ? reinterpret_cast<const float4*>(tab_act + ((int64_t)net * A + r.a_prev) * 64 + h0)
+                                          : nullptr;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float4 bi = __ldg(tid + q);
+            float4 ac = tac ? __ldg(tac + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v[4 * q + 0]) + ac.x + bi.x, 0.f);
+            o.y = fmaxf(__uint_as_float(v[4 * q + 1]) + ac.y + bi.y, 0.f);
+            o.z = fmaxf(__uint_as_float(v[4 * q + 2]) + ac.z + bi.z, 0.f);
+            o.w = fmaxf(__uint_as_float(v[4 * q + 3]) + ac.w + bi.w, 0.f);
+            reinterpret_cast<float4*>(out)[q] = o;
+        }
+    }
+    __device__ void end(Row&, int64_t, bool) const {}
+};
+
+// QMIX mixing on the hypernet outputs, E = 32.  Packed column order: [ w1 (N*32) | b1 | w_final | v0 ].
+//   hidden = ELU(sum_n q[n] |w1[n, :]| + b1);  q_tot = hidden . |w_final| + V.2(ReLU(v0))
+// raw_out (optional, bf16 [M][(N+3)*32], packed column order) keeps the hypernet outputs for the backward.
+struct MixEpi {
+    struct Row { float hidden[32]; float y; };
+    const float* bias;          // [(N+3)*32] packed order
+    const float* agent_qs;      // [M][N]
+    const float* v2_w; const float* v2_b;
+    float* q_tot;               // [M]
+    __nv_bfloat16* raw_out;
+    float* raw_f32;             // optional fp32 copy in the FLAT column order [w1 | w_final | b1 | v0]
+    int N;
+    __device__ void begin(Row& r, int64_t, bool) const {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r.hidden[e] = 0.f;
+        r.y = 0.f;
+    }
+    __device__ void cols(Row& r, int64_t m, bool valid, int col0, const uint32_t (&v)[32]) const {
+        const int grp = col0 >> 5;
+        float raw[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) raw[e] = __uint_as_float(v[e]) + __ldg(bias + col0 + e);
+        if (raw_out && valid) {
+            uint4* o = reinterpret_cast<uint4*>(raw_out + m * (int64_t)((N + 3) * 32) + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                o[q] = make_uint4(pack_bf16x2(raw[8 * q], raw[8 * q + 1]), pack_bf16x2(raw[8 * q + 2], raw[8 * q + 3]),
+                                  pack_bf16x2(raw[8 * q + 4], raw[8 * q + 5]), pack_bf16x2(raw[8 * q + 6], raw[8 * q + 7]));
+        }
+        if (raw_f32 && valid) {
+            const int fgrp = grp < N ? grp : (grp == N ? N + 1 : (grp == N + 1 ? N : N + 2));
+            float4* o = reinterpret_cast<float4*>(raw_f32 + m * (int64_t)((N + 3) * 32) + fgrp * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+        }
+        if (grp < N) {
+            const float qn = valid ? __ldg(agent_qs + m * N + grp) : 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r.hidden[e] = fmaf(qn, fabsf(raw[e]), r.hidden[e]);
+        } else if (grp == N) {                      // b1 -> hidden = ELU(pre)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                float pre = r.hidden[e] + raw[e];
+                r.hidden[e] = pre > 0.f ? pre : expm1f(pre);
+            }
+        } else if (grp == N + 1) {                  // w_final
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r.y = fmaf(r.hidden[e], fabsf(raw[e]), r.y);
+        } else {                                    // v0
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r.y = fmaf(fmaxf(raw[e], 0.f), __ldg(v2_w + e), r.y);
+        }
+    }
+    __device__ void end(Row& r, int64_t m, bool valid) const {
+        if (valid) q_tot[m] = r.y + __ldg(v2_b);
+    }
+};
+
+template <class Epi>
+int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
+    if (P.M <= 0) return PMB_OK;
+    auto kern = tc_gemm_kernel<Epi>;
+    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int64_t n_tiles = (P.M + BM - 1) / BM;
+    int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    kern<<<grid, THREADS, SMEM_BYTES, s>>>(P, epi);
+    PMB_LAUNCH_CHECK("tc_gemm_kernel");
+    return PMB_OK;
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------
+// host entry points used by api.cu
+// ------------------------------------------------------------------------------------------
+int64_t tc_packed_elems(int Ncols, int K) {
+    int n_chunks = (K + tc::BK - 1) / tc::BK;
+    return (int64_t)Ncols * n_chunks * tc::BK;
+}
+
+int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nseg, int K, __nv_bfloat16* out,
+              cudaStream_t s) {
+    tc::PackSegs segs;
+    int Ncols = 0;
+    segs.nseg = nseg;
+    for (int i = 0; i < 4; ++i) {
+        segs.ptr[i] = i < nseg ? ptrs[i] : nullptr;
+        segs.rows[i] = i < nseg ? rows[i] : 0;
+        segs.ld[i] = i < nseg ? lds[i] : 0;
+        Ncols += segs.rows[i];
+    }
+    Ncols = (int)align_up(Ncols, 32);
+    int n_chunks = (K + tc::BK - 1) / tc::BK;
+    int64_t total = (int64_t)Ncols * n_chunks * 8;
+    tc::pack_w_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(segs, K, n_chunks, Ncols, out);
+    PMB_LAUNCH_CHECK("pack_w_kernel");
+    return PMB_OK;
+}
+
+// plain C = A . W^T + bias  (diagnostics / unit test of the tcgen05 pipeline)
+int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
+                  const float* bias, float* C, int64_t ldc, cudaStream_t s) {
+    tc::GemmParams P{A, amap, M, K, (K + tc::BK - 1) / tc::BK, Wp, Ncols_padded};
+    tc::PlainEpi epi{C, ldc, bias, Nreal};
+    return tc::launch_tc_gemm(P, epi, s);
+}
+
+// tables for the fc1 epilogue: tab_act[net][a][h] = fc1_w[h][O + a];  tab_id[net][n][h] = fc1_w[h][O + A' + n] + b1[h]
+__global__ void fc1_tables_kernel(const float* __restrict__ w_on, const float* __restrict__ b_on,
+                                  const float* __restrict__ w_tg, const float* __restrict__ b_tg, int O, int A, int N,
+                                  int D_in, int use_act, int use_id, float* __restrict__ tab_act,
+                                  float* __restrict__ tab_id) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_act = 2 * A * 64, n_id = 2 * N * 64;
+    if (i < n_act) {
+        int net = i / (A * 64), r = i - net * A * 64, a = r / 64, h = r - a * 64;
+        const float* w = net ? w_tg : w_on;
+        tab_act[i] = use_act ? w[(int64_t)h * D_in + O + a] : 0.f;
+    } else if (i < n_act + n_id) {
+        int k = i - n_act;
+        int net = k / (N * 64), r = k - net * N * 64, n = r / 64, h = r - n * 64;
+        const float* w = net ? w_tg : w_on;
+        const float* b = net ? b_tg : b_on;
+        tab_id[k] = b[h] + (use_id ? w[(int64_t)h * D_in + O + (use_act ? A : 0) + n] : 0.f);
+    }
+}
+
+int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
+                    float* x_on, float* x_tg, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+    // scratch: packed W (128 x Kpad bf16) | tab_act | tab_id
+    const int D_in = d_in_of(d);
+    int64_t wp_bytes = align_up(tc_packed_elems(128, d->O) * 2, 256);
+    int64_t ta_bytes = align_up((int64_t)2 * d->A * 64 * 4, 256);
+    int64_t ti_bytes = align_up((int64_t)2 * d->N * 64 * 4, 256);
+    if (scratch_bytes < wp_bytes + ta_bytes + ti_bytes) { set_error("tc_fc1: scratch too small"); return PMB_ERR_WORKSPACE; }
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
+    float* tab_act = reinterpret_cast<float*>(static_cast<char*>(scratch) + wp_bytes);
+    float* tab_id = reinterpret_cast<float*>(static_cast<char*>(scratch) + wp_bytes + ta_bytes);
+    const float* ptrs[2] = {on.fc1_w, tg.fc1_w};
+    int rows[2] = {64, 64}, lds[2] = {D_in, D_in};
+    int rc = tc_pack_w(ptrs, rows, lds, 2, d->O, wp, s);
+    if (rc) return rc;
+    int n_tab = 2 * (d->A + d->N) * 64;
+    fc1_tables_kernel<<<(unsigned)ceil_div(n_tab, 256), 256, 0, s>>>(on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A,
+                                                                     d->N, D_in, d->obs_last_action, d->obs_agent_id,
+                                                                     tab_act, tab_id);
+    PMB_LAUNCH_CHECK("fc1_tables_kernel");
+    const int64_t M = (int64_t)d->B * nt * d->N;
+    RowMap map{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, nt, d->N};
+    tc::GemmParams P{b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, (d->O + tc::BK - 1) / tc::BK, wp, 128};
+    tc::Fc1Epi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb, x_on, x_tg,
+                   t0, nt, d->N, d->A, d->obs_last_action, (int64_t)d->B * d->N};
+    return tc::launch_tc_gemm(P, epi, s);
+}
+int64_t tc_fc1_scratch_bytes(const pmb_dims* d) {
+    return align_up(tc_packed_elems(128, d->O) * 2, 256) + align_up((int64_t)2 * d->A * 64 * 4, 256) +
+           align_up((int64_t)2 * d->N * 64 * 4, 256);
+}
+
+// permuted bias for the mixer: packed order [w1 | b1 | w_final | v0] from flat order [w1 | w_final | b1 | v0]
+__global__ void mix_bias_perm_kernel(const float* __restrict__ b_cat, int N, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int C = (N + 3) * 32;
+    if (i >= C) return;
+    int grp = i >> 5, e = i & 31;
+    int src_grp = grp < N ? grp : (grp == N ? N + 1 : (grp == N + 1 ? N : N + 2));
+    out[i] = b_cat[src_grp * 32 + e];
+}
+
+int64_t tc_mixer_scratch_bytes(const pmb_dims* d) {
+    const int C = (d->N + 3) * 32;
+    return align_up(tc_packed_elems((int)align_up(C, 32), d->S) * 2, 256) + align_up((int64_t)C * 4, 256);
+}
+
+int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
+                 __nv_bfloat16* raw_out, float* raw_f32, float* q_tot, void* scratch, int64_t scratch_bytes,
+                 cudaStream_t s) {
+    const int N = d->N, S = d->S, C = (N + 3) * 32;
+    if (scratch_bytes < tc_mixer_scratch_bytes(d)) { set_error("tc_mixer: scratch too small"); return PMB_ERR_WORKSPACE; }
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
+    float* bias = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(tc_packed_elems(C, S) * 2, 256));
+    // flat W_cat rows: [w1 (N*32) | w_final (32) | b1 (32) | v0 (32)]  ->  packed [w1 | b1 | w_final | v0]
+    const float* ptrs[4] = {mp.w_cat, mp.w_cat + (int64_t)(N + 1) * 32 * S, mp.w_cat + (int64_t)N * 32 * S,
+                            mp.w_cat + (int64_t)(N + 2) * 32 * S};
+    int rows[4] = {N * 32, 32, 32, 32}, lds[4] = {S, S, S, S};
+    int rc = tc_pack_w(ptrs, rows, lds, 4, S, wp, s);
+    if (rc) return rc;
+    mix_bias_perm_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, s>>>(mp.b_cat, N, bias);
+    PMB_LAUNCH_CHECK("mix_bias_perm_kernel");
+    const int64_t M = (int64_t)d->B * (d->T - 1);
+    RowMap smap{b->state_sb, (int64_t)S, 0, d->T - 1, 1};
+    tc::GemmParams P{b->state + (int64_t)t_off * S, smap, M, S, (S + tc::BK - 1) / tc::BK, wp, C};
+    tc::MixEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_out, raw_f32, N};
+    return tc::launch_tc_gemm(P, epi, s);
+}
+
+}  // namespace pmb

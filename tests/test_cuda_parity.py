@@ -303,3 +303,60 @@ def test_full_size_properties_27m():
     for i in range(5):
         assert abs(full_st[i] - pad_st[i]) <= 1e-6 * max(1.0, abs(full_st[i])), i
     assert rel_err(pad_g, full_g) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# bf16 tensor-core tier (tcgen05): parity 1e-2 (BASELINE.json north_star)
+# ------------------------------------------------------------------------------------------
+TOL_BF16 = 1e-2
+
+
+def _bf16_round(x):
+    return th.from_numpy(x).to(th.bfloat16).to(th.float64).numpy()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (1000, 128, 285), (300, 960, 1170), (5, 32, 7), (4096, 64, 129),
+                                   (257, 512, 320)])
+def test_tc_gemm_matches_bf16_reference(m, n, k):
+    """The tcgen05 pipeline alone (descriptors, swizzle, mbarrier pipeline, TMEM epilogue): the
+    result must equal an exact product of the bf16-rounded operands up to fp32 accumulation."""
+    import ctypes as C
+    from pymarl_b200 import _lib
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = rng.standard_normal((n, k)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    A, W, Bv = th.from_numpy(a).cuda(), th.from_numpy(w).cuda(), th.from_numpy(bias).cuda()
+    Cout = th.full((m, n), float("nan"), device="cuda")
+    need = _lib.lib().pmb_gemm_bf16_workspace_bytes(n, k)
+    scratch = th.empty(need, dtype=th.uint8, device="cuda")
+    _lib.check(_lib.lib().pmb_gemm_bf16_tn(m, n, k, _lib.ptr(A), _lib.ptr(W), _lib.ptr(Bv), _lib.ptr(Cout),
+                                           _lib.ptr(scratch), need, _lib.stream_ptr()), "pmb_gemm_bf16_tn")
+    ref = _bf16_round(a) @ _bf16_round(w).T + bias.astype(np.float64)
+    got = Cout.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) < 2e-5, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("shape_name,B,T,mixer", [("3m", 32, 60, "qmix"), ("2s3z", 40, 30, "qmix"),
+                                                   ("MMM2", 16, 20, "vdn"), ("27m_vs_30m", 8, 12, "qmix")])
+def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
+    from cuda_utils import build_learner, to_batch, state_np
+    shape = SMAC_SHAPES[shape_name]
+    args = default_args(shape, mixer=mixer, learner_log_interval=0, precision="bf16")
+    fields = numpy_episode_fields(shape, B, T, seed=21, ragged=True)
+    olr = _oracle_learner(shape, copy.copy(args), seed=8)
+    learner, _ = build_learner(shape, args, olr.agent, olr.target_agent, olr.mixer_p, olr.target_mixer_p)
+    stats, raw_grads, fw = olr.train(fields, 0, 0)
+    learner.train(to_batch(shape, fields), 0, 0)
+    st = learner.stats()
+    ws = learner.workspace_views(learner._last_dims)
+    assert rel_err(_tm_to_bm(ws["q_on"], B, shape.n_agents), fw["mac_out"]) < TOL_BF16
+    if mixer == "qmix":
+        assert rel_err(ws["q_tot"].cpu().numpy(), fw["q_tot"]) < TOL_BF16
+    for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+        assert abs(st[key] - stats[key]) <= 2 * TOL_BF16 * max(1.0, abs(stats[key])), (key, st[key], stats[key])
+    for k, v in olr.agent.items():
+        assert rel_err(state_np(learner.mac.agent)[k], v) < TOL_BF16, k
+    for k, v in olr.mixer_p.items():
+        assert rel_err(state_np(learner.mixer)[k], v) < TOL_BF16, k
