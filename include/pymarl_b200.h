@@ -211,6 +211,12 @@ int64_t pmb_gemm_bf16_workspace_bytes(int32_t n, int32_t k);
 int pmb_gemm_bf16_tn(int64_t m, int32_t n, int32_t k, const float* a, const float* w, const float* bias, float* c,
                      void* scratch, int64_t scratch_bytes, pmb_stream stream);
 
+/* out[c][k] = sum_m d[m][c] a[m][k] (weight-gradient form, reduction over rows), bias_out[c] = sum_m d[m][c].
+ * d [m][ldd], a [m][lda] fp32; out [c][k] fp32. */
+int64_t pmb_gemm_bf16_atb_workspace_bytes(int64_t m, int32_t c, int32_t k);
+int pmb_gemm_bf16_atb(int64_t m, int32_t c, int32_t k, const float* d, int64_t ldd, const float* a, int64_t lda,
+                      float* out, float* bias_out, void* scratch, int64_t scratch_bytes, pmb_stream stream);
+
 /* ---- whole learner step (learners/q_learner.py:37-107) ---------------------------------- */
 /* flat_p / flat_g / flat_sq: online params, grads, RMSprop square_avg (n_total floats);
  * flat_target: target params.  workspace >= pmb_learner_workspace_bytes().  stats: 16 doubles. */

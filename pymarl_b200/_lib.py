@@ -94,6 +94,9 @@ _SIGS = {
                                           C.c_uint64, C.c_uint64, _P, _P, _P, C.c_int64, _P]),
     "pmb_gemm_bf16_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "pmb_gemm_bf16_tn": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "pmb_gemm_bf16_atb_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "pmb_gemm_bf16_atb": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P, _P, _P,
+                                    C.c_int64, _P]),
     "pmb_qlearner_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.POINTER(HParams), _P, _P, _P, _P, _P,
                                           C.c_int64, _P, _P]),
 }

@@ -392,23 +392,41 @@ agent_scatter_grads_kernel(int A, int N, int T, int64_t R, const float* __restri
     const int64_t total = (int64_t)T * R;
     const int64_t beg = (int64_t)blockIdx.x * items_per_cta;
     const int64_t end = beg + items_per_cta < total ? beg + items_per_cta : total;
-    for (int64_t it = beg + g; it < end; it += G) {
-        int t = (int)(it / R);
-        int64_t row = it - (int64_t)t * R;
-        int64_t b = row / N;
-        int n = (int)(row - b * N);
-        float dp = __ldg(dpre1 + it * H + j);
-        if (use_id) acc_id[n * H + j] += dp;
-        if (use_act && t > 0 && __ldg(filled + b * filled_sb + (t - 1)) != 0) {
-            int ap = (int)__ldg(actions + b * actions_sb + (int64_t)(t - 1) * N + n);
-            acc_act[ap * H + j] += dp;
+    // batches of U items: all loads of a batch are issued before the first accumulation (the loop is
+    // latency bound otherwise); accumulation order stays item order -> deterministic
+    constexpr int U = 8;
+    for (int64_t it0 = beg + g; it0 < end; it0 += (int64_t)G * U) {
+        float dp[U], dq[U], hv[U];
+        int nn[U], ap[U], aa[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t it = it0 + (int64_t)u * G;
+            dp[u] = 0.f; dq[u] = 0.f; hv[u] = 0.f; nn[u] = -1; ap[u] = -1; aa[u] = -1;
+            if (it < end) {
+                int t = (int)(it / R);
+                int64_t row = it - (int64_t)t * R;
+                int64_t b = row / N;
+                int n = (int)(row - b * N);
+                nn[u] = n;
+                dp[u] = __ldg(dpre1 + it * H + j);
+                if (use_act && t > 0 && __ldg(filled + b * filled_sb + (t - 1)) != 0)
+                    ap[u] = (int)__ldg(actions + b * actions_sb + (int64_t)(t - 1) * N + n);
+                if (t < T - 1) {
+                    dq[u] = __ldg(d_chosen + (b * (T - 1) + t) * N + n);
+                    aa[u] = (int)__ldg(actions + b * actions_sb + (int64_t)t * N + n);
+                    hv[u] = __ldg(h_stash + ((int64_t)(t + 1) * R + row) * H + j);
+                }
+            }
         }
-        if (t < T - 1) {
-            float dq = __ldg(d_chosen + (b * (T - 1) + t) * N + n);
-            int a = (int)__ldg(actions + b * actions_sb + (int64_t)t * N + n);
-            float hv = __ldg(h_stash + ((int64_t)(t + 1) * R + row) * H + j);
-            acc_w2[a * H + j] = fmaf(dq, hv, acc_w2[a * H + j]);
-            if (j == 0) acc_b2[a] += dq;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (nn[u] < 0) continue;
+            if (use_id) acc_id[nn[u] * H + j] += dp[u];
+            if (ap[u] >= 0) acc_act[ap[u] * H + j] += dp[u];
+            if (aa[u] >= 0) {
+                acc_w2[aa[u] * H + j] = fmaf(dq[u], hv[u], acc_w2[aa[u] * H + j]);
+                if (j == 0) acc_b2[aa[u]] += dq[u];
+            }
         }
     }
     __syncthreads();

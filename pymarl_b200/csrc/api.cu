@@ -138,8 +138,8 @@ struct WsPlan {
 
 int64_t agent_bwd_scratch(const pmb_dims* d) {
     const int64_t rows = (int64_t)d->T * d->B * d->N;
-    int64_t a = gemm_atb_scratch_bytes(3 * d->H, d->H, rows);
-    int64_t b = gemm_atb_scratch_bytes(d->H, d->O, rows);
+    int64_t a = atb_scratch_bytes(d->precision, 3 * d->H, d->H, rows);
+    int64_t b = atb_scratch_bytes(d->precision, d->H, d->O, rows);
     int64_t c = scatter_scratch_bytes(d);
     int64_t m = a > b ? a : b;
     return m > c ? m : c;
@@ -230,22 +230,23 @@ int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, co
     if (rc) return rc;
     PHASE(s, "dW_rnn_gemm_atb");
     // rnn.weight_ih / bias_ih:  [da_r | da_z | da_n]^T . x
-    rc = launch_gemm_atb(gates, dense_map(4 * H), 3 * H, x_on, dense_map(H), H, rows, gr.w_ih, H, gr.b_ih, scratch,
-                         scratch_bytes, s);
+    const int prec = d->precision;
+    rc = gemm_atb_any(prec, gates, dense_map(4 * H), 3 * H, x_on, dense_map(H), H, rows, gr.w_ih, H, gr.b_ih, scratch,
+                      scratch_bytes, s);
     if (rc) return rc;
     // rnn.weight_hh / bias_hh:  [da_r | da_z | da_n * r]^T . h_{t-1}   (h_stash slot t holds h_{t-1})
-    rc = launch_gemm_atb(gates, dense_map(4 * H), 2 * H, h_stash, dense_map(H), H, rows, gr.w_hh, H, gr.b_hh, scratch,
-                         scratch_bytes, s);
+    rc = gemm_atb_any(prec, gates, dense_map(4 * H), 2 * H, h_stash, dense_map(H), H, rows, gr.w_hh, H, gr.b_hh, scratch,
+                      scratch_bytes, s);
     if (rc) return rc;
-    rc = launch_gemm_atb(gates + 3 * H, dense_map(4 * H), H, h_stash, dense_map(H), H, rows,
-                         gr.w_hh + (int64_t)2 * H * H, H, gr.b_hh + 2 * H, scratch, scratch_bytes, s);
+    rc = gemm_atb_any(prec, gates + 3 * H, dense_map(4 * H), H, h_stash, dense_map(H), H, rows,
+                      gr.w_hh + (int64_t)2 * H * H, H, gr.b_hh + 2 * H, scratch, scratch_bytes, s);
     if (rc) return rc;
     PHASE(s, "dW_fc1_gemm_atb");
     // fc1.weight[:, :O] / fc1.bias:  dpre1^T . obs   (dpre1 time major, obs batch major)
     RowMap dmap{(int64_t)d->N * H, R * H, (int64_t)H, d->T, d->N};
     RowMap omap{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, d->T, d->N};
-    rc = launch_gemm_atb(dpre1, dmap, H, b->obs, omap, d->O, rows, gr.fc1_w, d_in_of(d), gr.fc1_b, scratch,
-                         scratch_bytes, s);
+    rc = gemm_atb_any(prec, dpre1, dmap, H, b->obs, omap, d->O, rows, gr.fc1_w, d_in_of(d), gr.fc1_b, scratch,
+                      scratch_bytes, s);
     if (rc) return rc;
     PHASE(s, "agent_scatter_grads");
     return scatter_grads_dispatch(d, b, h_stash, dpre1, d_chosen, gr, scratch, scratch_bytes, s);
@@ -481,6 +482,15 @@ int pmb_gemm_bf16_tn(int64_t m, int32_t n, int32_t k, const float* a, const floa
     int rc = tc_pack_w(ptrs, rows, lds, 1, k, wp, s);
     if (rc) return rc;
     return tc_gemm_plain(a, dense_map(k), m, k, wp, (int)align_up(n, 32), n, bias, c, n, s);
+}
+
+int64_t pmb_gemm_bf16_atb_workspace_bytes(int64_t m, int32_t c, int32_t k) { return tc_atb_scratch_bytes(c, k, m); }
+
+int pmb_gemm_bf16_atb(int64_t m, int32_t c, int32_t k, const float* d, int64_t ldd, const float* a, int64_t lda,
+                      float* out, float* bias_out, void* scratch, int64_t scratch_bytes, pmb_stream stream) {
+    PMB_REQUIRE(m > 0 && c > 0 && k > 0 && d && a && out && scratch, "gemm_bf16_atb: bad arguments");
+    return tc_gemm_atb(d, dense_map(ldd), c, a, dense_map(lda), k, m, out, k, bias_out, scratch, scratch_bytes,
+                       (cudaStream_t)stream);
 }
 
 int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hparams* hp, float* flat_p, float* flat_g,

@@ -43,7 +43,14 @@ struct RowMap {
     int64_t sb, st, sn;
     int32_t T, N;
     __host__ __device__ inline int64_t offset(int64_t m) const {
-        int64_t tn = (int64_t)T * N;
+        if (T == 1 && N == 1) return m * sb;                       // dense matrix
+        const int64_t tn = (int64_t)T * N;
+        if (((uint64_t)m | (uint64_t)tn) >> 31 == 0) {             // 32-bit divisions (the common case)
+            const uint32_t mm = (uint32_t)m, tnn = (uint32_t)tn;
+            const uint32_t b = mm / tnn, r = mm - b * tnn;
+            const uint32_t t = r / (uint32_t)N, n = r - t * (uint32_t)N;
+            return (int64_t)b * sb + (int64_t)t * st + (int64_t)n * sn;
+        }
         int64_t b = m / tn;
         int32_t r = (int32_t)(m - b * tn);
         int32_t t = r / N;
@@ -127,5 +134,19 @@ int launch_gemm_tn(const float* A, RowMap map, int64_t M, int32_t K, const float
 int64_t gemm_atb_scratch_bytes(int32_t C, int32_t K, int64_t M);
 int launch_gemm_atb(const float* D, RowMap dmap, int32_t C, const float* A, RowMap amap, int32_t K, int64_t M,
                     float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+
+// tc_atb.cu: same contract on tcgen05 (bf16 operands, fp32 accumulate)
+int64_t tc_atb_scratch_bytes(int C, int K, int64_t M);
+int tc_gemm_atb(const float* D, RowMap dmap, int C, const float* A, RowMap amap, int K, int64_t M, float* out,
+                int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+// dispatch on the precision tier
+inline int64_t atb_scratch_bytes(int prec, int C, int K, int64_t M) {
+    return prec == PMB_PREC_BF16 ? tc_atb_scratch_bytes(C, K, M) : gemm_atb_scratch_bytes(C, K, M);
+}
+inline int gemm_atb_any(int prec, const float* D, RowMap dmap, int C, const float* A, RowMap amap, int K, int64_t M,
+                        float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+    return prec == PMB_PREC_BF16 ? tc_gemm_atb(D, dmap, C, A, amap, K, M, out, ldo, bias_out, scratch, scratch_bytes, s)
+                                 : launch_gemm_atb(D, dmap, C, A, amap, K, M, out, ldo, bias_out, scratch, scratch_bytes, s);
+}
 
 }  // namespace pmb

@@ -160,7 +160,7 @@ int64_t mixer_bwd_scratch_bytes(const pmb_dims* d) {
     if (d->mixer != PMB_MIXER_QMIX) return 256;
     const int64_t M = (int64_t)d->B * (d->T - 1);
     const int C = (d->N + 3) * d->E;
-    return gemm_atb_scratch_bytes(C, d->S, M) + align_up((int64_t)mixb_grid(M) * (d->E + 1) * 4, 256);
+    return atb_scratch_bytes(d->precision, C, d->S, M) + align_up((int64_t)mixb_grid(M) * (d->E + 1) * 4, 256);
 }
 
 int launch_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer, const float* agent_qs, float* raw,
@@ -193,8 +193,8 @@ int launch_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mi
     PMB_LAUNCH_CHECK("v2_reduce_kernel");
     // hypernet weights and biases:  dW_cat = d_raw^T . state[:, :-1],  db_cat = column sums
     RowMap smap{b->state_sb, (int64_t)d->S, 0, d->T - 1, 1};
-    return launch_gemm_atb(raw, dense_map(C), C, b->state, smap, d->S, M, gbase + L.offset[PMB_P_HW1_W], d->S,
-                           gbase + L.offset[PMB_P_HW1_B], atb_scratch, atb_bytes, s);
+    return gemm_atb_any(d->precision, raw, dense_map(C), C, b->state, smap, d->S, M, gbase + L.offset[PMB_P_HW1_W],
+                        d->S, gbase + L.offset[PMB_P_HW1_B], atb_scratch, atb_bytes, s);
 }
 
 }  // namespace pmb
