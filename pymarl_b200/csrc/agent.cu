@@ -376,7 +376,15 @@ agent_scatter_grads_kernel(int A, int N, int T, int64_t R, const float* __restri
                            const float* __restrict__ dpre1, const float* __restrict__ d_chosen,
                            const int64_t* __restrict__ actions, int64_t actions_sb,
                            const int64_t* __restrict__ filled, int64_t filled_sb, int use_act, int use_id,
-                           int64_t items_per_cta, float* __restrict__ partial) {
+                           int64_t items_per_cta, float* __restrict__ partial, int ti_tiles) {
+    // ti_tiles > 0: h_stash and dpre1 are bf16 tile images [t][ti_tiles][16 KB] (bf16 tier)
+    auto ti_fetch = [&](const float* base, int64_t t, int64_t row, int jj) -> float {
+        const uint8_t* tile = reinterpret_cast<const uint8_t*>(base) + (t * ti_tiles + (row >> 7)) * 16384;
+        const uint32_t rr = (uint32_t)(row & 127);
+        const uint16_t w = *reinterpret_cast<const uint16_t*>(tile + rr * 128u + ((((uint32_t)jj >> 3) ^ (rr & 7u)) << 4) +
+                                                              ((uint32_t)jj & 7u) * 2u);
+        return __uint_as_float((uint32_t)w << 16);
+    };
     constexpr int G = NT / H;
     extern __shared__ __align__(16) float smem[];
     // per group: w2 [A][H], b2 [A], act [A][H], id [N][H]
@@ -408,13 +416,14 @@ agent_scatter_grads_kernel(int A, int N, int T, int64_t R, const float* __restri
                 int64_t b = row / N;
                 int n = (int)(row - b * N);
                 nn[u] = n;
-                dp[u] = __ldg(dpre1 + it * H + j);
+                dp[u] = ti_tiles > 0 ? ti_fetch(dpre1, t, row, j) : __ldg(dpre1 + it * H + j);
                 if (use_act && t > 0 && __ldg(filled + b * filled_sb + (t - 1)) != 0)
                     ap[u] = (int)__ldg(actions + b * actions_sb + (int64_t)(t - 1) * N + n);
                 if (t < T - 1) {
                     dq[u] = __ldg(d_chosen + (b * (T - 1) + t) * N + n);
                     aa[u] = (int)__ldg(actions + b * actions_sb + (int64_t)t * N + n);
-                    hv[u] = __ldg(h_stash + ((int64_t)(t + 1) * R + row) * H + j);
+                    hv[u] = ti_tiles > 0 ? ti_fetch(h_stash, t + 1, row, j)
+                                         : __ldg(h_stash + ((int64_t)(t + 1) * R + row) * H + j);
                 }
             }
         }
@@ -541,7 +550,7 @@ int64_t scatter_scratch_bytes(const pmb_dims* d) {
 
 int scatter_grads_dispatch(const pmb_dims* d, const pmb_batch* b, const float* h_stash, const float* dpre1,
                            const float* d_chosen, AgentGrads gr, void* scratch, int64_t scratch_bytes,
-                           cudaStream_t s) {
+                           cudaStream_t s, int ti_tiles) {
     int64_t R = (int64_t)d->B * d->N, items = (int64_t)d->T * R;
     int n_cta = scatter_ctas(items);
     if (scatter_scratch_bytes(d) > scratch_bytes) {
@@ -558,7 +567,7 @@ int scatter_grads_dispatch(const pmb_dims* d, const pmb_batch* b, const float* h
         PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
         kern<<<n_cta, NT, smem, s>>>(d->A, d->N, d->T, R, h_stash, dpre1, d_chosen, b->actions, b->actions_sb,    \
                                      b->filled, b->filled_sb, d->obs_last_action, d->obs_agent_id, items_per_cta, \
-                                     partial);                                                                    \
+                                     partial, ti_tiles);                                                          \
     }                                                                                                             \
     break
     switch (d->H) {

@@ -4,6 +4,7 @@
 #include <string.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "gru_tc.cuh"
 
 namespace pmb {
 
@@ -14,7 +15,8 @@ int gru_bwd_dispatch(const pmb_dims* d, const pmb_batch* b, const AgentParams& p
                      const float* h_stash, float* gates, const float* d_chosen, float* dpre1, cudaStream_t s);
 int64_t scatter_scratch_bytes(const pmb_dims* d);
 int scatter_grads_dispatch(const pmb_dims* d, const pmb_batch* b, const float* h_stash, const float* dpre1,
-                           const float* d_chosen, AgentGrads gr, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+                           const float* d_chosen, AgentGrads gr, void* scratch, int64_t scratch_bytes, cudaStream_t s,
+                           int ti_tiles = 0);
 int launch_target_select(const pmb_dims* d, const pmb_batch* b, const float* q_on, const float* q_tg, float* chosen,
                          float* tmax, int32_t* cur_max, cudaStream_t s);
 int launch_epsilon_greedy(int64_t rows, int N, int A, const float* q, const int32_t* avail, int64_t avail_sb,
@@ -39,7 +41,11 @@ int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nse
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
                   const float* bias, float* C, int64_t ldc, cudaStream_t s);
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
-                    float* x_on, float* x_tg, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+                    float* x_on, float* x_tg, int tile_images, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+// tc_atb.cu (tile-image D operand)
+int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, const float* A, RowMap amap, int K,
+                   float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+int64_t tc_atb_ti_scratch_bytes(int T, int n_tiles, int K);
 int64_t tc_fc1_scratch_bytes(const pmb_dims* d);
 int64_t tc_mixer_scratch_bytes(const pmb_dims* d);
 int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
@@ -151,11 +157,14 @@ WsPlan plan_workspace(const pmb_dims* d) {
     const int64_t C = (int64_t)(N + 3) * d->E;
     const bool qmix = d->mixer == PMB_MIXER_QMIX, iql = d->mixer == PMB_MIXER_NONE;
     const int64_t W = iql ? N : 1;
+    // the bf16 tier stores x / h / gates as bf16 tile images (128-row tiles, 16 KB each); take the larger size
+    const int64_t n_tiles = ceil_div(R, 128), ti = d->precision == PMB_PREC_BF16 ? 4096 : 0;   // floats per tile
+    auto mx = [](int64_t a, int64_t b) { return a > b ? a : b; };
     int64_t sizes[15] = {
-        T * R * H,                 // 0 x_on
-        T * R * H,                 // 1 x_tg (reused as dpre1 in the backward)
-        (T + 1) * R * H,           // 2 h_stash
-        T * R * 4 * H,             // 3 gates
+        mx(T * R * H, T * n_tiles * ti),               // 0 x_on
+        mx(T * R * H, T * n_tiles * ti),               // 1 x_tg (reused as dpre1 in the backward)
+        mx((T + 1) * R * H, (T + 1) * n_tiles * ti),   // 2 h_stash
+        mx(T * R * 4 * H, T * n_tiles * 4 * ti),       // 3 gates
         T * R * A,                 // 4 q_on
         T * R * A,                 // 5 q_tg
         M * N,                     // 6 chosen
@@ -180,6 +189,10 @@ WsPlan plan_workspace(const pmb_dims* d) {
     if (d->precision == PMB_PREC_BF16) {
         int64_t f = tc_fc1_scratch_bytes(d);
         if (f > sc) sc = f;
+        int64_t g = 131072 + tc_gru_dw_scratch_bytes();
+        if (g > sc) sc = g;
+        int64_t a2 = tc_atb_ti_scratch_bytes(d->T, (int)ceil_div((int64_t)d->B * d->N, 128), d->O);
+        if (a2 > sc) sc = a2;
         if (d->mixer == PMB_MIXER_QMIX) { int64_t m2 = tc_mixer_scratch_bytes(d); if (m2 > sc) sc = m2; }
     }
     if (sc < 4096 * 4) sc = 4096 * 4;
@@ -514,21 +527,57 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
 
     if ((rc = launch_stats_reset(stats, s))) return rc;
     // q_learner.py:47-52 / 58-62: both nets over all T steps
-    const bool tc_agent = d->precision == PMB_PREC_BF16 && d->H == 64;
+    const bool tc_agent = d->precision == PMB_PREC_BF16 && d->H == 64 && d->A <= 64;
     const bool tc_mixer = d->precision == PMB_PREC_BF16 && d->mixer == PMB_MIXER_QMIX && d->E == 32;
+    const int n_tiles = (int)ceil_div(R, 128);
+    uint8_t *x_on_ti = reinterpret_cast<uint8_t*>(v.x_on), *x_tg_ti = reinterpret_cast<uint8_t*>(v.x_tg);
+    uint8_t *h_ti = reinterpret_cast<uint8_t*>(v.h_stash), *g_ti = reinterpret_cast<uint8_t*>(v.gates);
+    // GRU weight images live at the start of the scratch area: [online: w_ih | w_hh | w2][target: same]
+    auto pack_gru = [&](const AgentParams& ap, char* base) -> int {
+        const float* p1[1] = {ap.w_ih}; const float* p2[1] = {ap.w_hh}; const float* p3[2] = {ap.fc2_w, nullptr};
+        int r1[1] = {192}, l1[1] = {64}, r3[2] = {d->A, 64 - d->A}, l3[2] = {64, 64};
+        int e;
+        if ((e = tc_pack_w(p1, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base), s))) return e;
+        if ((e = tc_pack_w(p2, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base + 24576), s))) return e;
+        return tc_pack_w(p3, r3, l3, 2, 64, reinterpret_cast<__nv_bfloat16*>(base + 49152), s);
+    };
+    char* gru_img = reinterpret_cast<char*>(v.scratch);
     if (tc_agent) {
+        if ((rc = tc_ti_zero_pad(x_on_ti, d->T, n_tiles, R, s))) return rc;
+        if ((rc = tc_ti_zero_pad(x_tg_ti, d->T, n_tiles, R, s))) return rc;
+        if ((rc = tc_ti_zero_pad(h_ti, d->T + 1, n_tiles, R, s))) return rc;
         PHASE(s, "fc1_fwd_both_tc");
-        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, v.scratch, v.scratch_bytes, s))) return rc;
+        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, v.scratch, v.scratch_bytes, s))) return rc;
+        PHASE(s, "gru_unroll_fwd_online_tc");
+        if ((rc = pack_gru(on, gru_img))) return rc;
+        if ((rc = pack_gru(tg, gru_img + 57344))) return rc;
+        tc::GruFwdParams fp;
+        fp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img);
+        fp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576);
+        fp.w2_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 49152);
+        fp.b_ih = on.b_ih; fp.b_hh = on.b_hh; fp.b2 = on.fc2_b;
+        fp.x_ti = x_on_ti; fp.h0 = nullptr; fp.h_ti = h_ti; fp.g_ti = g_ti; fp.q = v.q_on; fp.h_last = nullptr;
+        fp.R = R; fp.nt = d->T; fp.A = d->A; fp.n_tiles = n_tiles;
+        if ((rc = tc_gru_fwd(fp, s))) return rc;
+        PHASE(s, "gru_unroll_fwd_target_tc");
+        fp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 57344);
+        fp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 57344 + 24576);
+        fp.w2_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 57344 + 49152);
+        fp.b_ih = tg.b_ih; fp.b_hh = tg.b_hh; fp.b2 = tg.fc2_b;
+        fp.x_ti = x_tg_ti; fp.h_ti = nullptr; fp.g_ti = nullptr; fp.q = v.q_tg;
+        if ((rc = tc_gru_fwd(fp, s))) return rc;
     } else {
         PHASE(s, "fc1_fwd_online");
         if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
         PHASE(s, "fc1_fwd_target");
         if ((rc = fc1_fwd(d, b, 0, d->T, tg, v.x_tg, s))) return rc;
     }
-    PHASE(s, "gru_unroll_fwd_online");
-    if ((rc = gru_fwd_dispatch(d, on, R, d->T, v.x_on, nullptr, v.h_stash, v.gates, v.q_on, nullptr, s))) return rc;
-    PHASE(s, "gru_unroll_fwd_target");
-    if ((rc = gru_fwd_dispatch(d, tg, R, d->T, v.x_tg, nullptr, nullptr, nullptr, v.q_tg, nullptr, s))) return rc;
+    if (!tc_agent) {
+        PHASE(s, "gru_unroll_fwd_online");
+        if ((rc = gru_fwd_dispatch(d, on, R, d->T, v.x_on, nullptr, v.h_stash, v.gates, v.q_on, nullptr, s))) return rc;
+        PHASE(s, "gru_unroll_fwd_target");
+        if ((rc = gru_fwd_dispatch(d, tg, R, d->T, v.x_tg, nullptr, nullptr, nullptr, v.q_tg, nullptr, s))) return rc;
+    }
     // :55-78
     PHASE(s, "target_select");
     if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
@@ -555,8 +604,31 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         if ((rc = launch_mixer_bwd(d, b, flat_p + L.n_agent, v.chosen, v.raw_on, v.g, v.d_chosen, flat_g + L.n_agent,
                                    v.scratch, v.scratch_bytes, s))) return rc;
     }
-    if ((rc = agent_bwd(d, b, flat_p, v.x_on, v.h_stash, v.gates, v.d_chosen, v.x_tg, flat_g, v.scratch,
-                        v.scratch_bytes, s))) return rc;
+    if (tc_agent) {
+        AgentGrads gr = agent_grads(d, flat_g);
+        PHASE(s, "gru_unroll_bwd_tc");
+        if ((rc = pack_gru(on, gru_img))) return rc;
+        tc::GruBwdParams bp;
+        bp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img);
+        bp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576);
+        bp.fc2_w = on.fc2_w;
+        bp.x_ti = x_on_ti; bp.h_ti = h_ti; bp.g_ti = g_ti; bp.dpre1_ti = x_tg_ti;
+        bp.d_chosen = v.d_chosen; bp.actions = b->actions; bp.actions_sb = b->actions_sb;
+        bp.R = R; bp.T = d->T; bp.N = d->N; bp.n_tiles = n_tiles;
+        if ((rc = tc_gru_bwd(bp, s))) return rc;
+        PHASE(s, "dW_rnn_tc");
+        char* sc2 = reinterpret_cast<char*>(v.scratch) + 131072;
+        if ((rc = tc_gru_dw(g_ti, x_on_ti, h_ti, d->T, n_tiles, gr.w_ih, gr.w_hh, gr.b_ih, gr.b_hh, sc2,
+                            v.scratch_bytes - 131072, s))) return rc;
+        PHASE(s, "dW_fc1_tc");
+        RowMap omap{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, d->T, d->N};
+        if ((rc = tc_gemm_atb_ti(x_tg_ti, d->T, d->N, R, n_tiles, b->obs, omap, d->O, gr.fc1_w, d_in_of(d), gr.fc1_b,
+                                 v.scratch, v.scratch_bytes, s))) return rc;
+        PHASE(s, "agent_scatter_grads");
+        if ((rc = scatter_grads_dispatch(d, b, v.h_stash, v.x_tg, v.d_chosen, gr, v.scratch, v.scratch_bytes, s,
+                                         n_tiles))) return rc;
+    } else if ((rc = agent_bwd(d, b, flat_p, v.x_on, v.h_stash, v.gates, v.d_chosen, v.x_tg, flat_g, v.scratch,
+                               v.scratch_bytes, s))) return rc;
     // :102-107
     PHASE(s, "clip_rmsprop_update");
     if (!hp->skip_update) {

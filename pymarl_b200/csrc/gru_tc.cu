@@ -1,0 +1,668 @@
+// bf16 tensor-core tier: the RNNAgent recurrence on tcgen05.
+//
+// Activations of this tier are stored as bf16 "tile images": a [rows x 64] matrix is cut into tiles of
+// 128 rows; a tile is the exact shared-memory image of a K-major / 128-byte-swizzle UMMA operand
+// (row r at byte r*128, 16-byte chunk j at ((j ^ (r & 7)) << 4)), 16 KB.  One bulk async copy brings
+// a tile in, and the same bytes serve as K-major A operand (forward) and as MN-major operand (weight
+// gradients) - only the descriptor changes.
+//
+//   gru_fwd_tc : one CTA per 128-row tile, persistent over t.  W_ih / W_hh / fc2 images stay in shared
+//                memory, the hidden state stays in registers (fp32, one row per epilogue thread) and in
+//                a bf16 operand tile.  Per step: 16 tcgen05.mma for the gates (r|z fused over [x|h],
+//                n input part, n hidden part), gate math out of TMEM, 4 mma for fc2, q out of TMEM.
+//                2 CTAs per SM so one tile's gate math overlaps the other tile's MMAs.
+//   gru_bwd_tc : BPTT, two 128-row sub-tiles per CTA in ping-pong (the gate-gradient math of one
+//                overlaps the 24 mma of the other); dh stays in fp32 registers.
+//   gru_dw_tc  : rnn.weight_ih / weight_hh / biases: sum over (t, tile) of [dg]^T . [x | h | 1] with
+//                every operand bulk-copied (no conversion) - a pure HBM-bandwidth kernel.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "gru_tc.cuh"
+
+namespace pmb {
+namespace tc {
+
+constexpr int TILE_ROWS = 128;
+constexpr int TILE_BYTES = TILE_ROWS * 128;      // 16 KB
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 16 fp32 values (columns 16c .. 16c+15 of row r) -> two 16-byte chunks of a tile image
+__device__ __forceinline__ void store_row16(uint8_t* tile, uint32_t r, int c16, const float (&f)[16]) {
+    uint4 a = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    uint4 b = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                         pack_bf16x2(f[14], f[15]));
+    *reinterpret_cast<uint4*>(tile + sw128_offset(r, 2 * c16)) = a;
+    *reinterpret_cast<uint4*>(tile + sw128_offset(r, 2 * c16 + 1)) = b;
+}
+__device__ __forceinline__ void load_row16(const uint8_t* tile, uint32_t r, int c16, float (&f)[16]) {
+    uint4 a = *reinterpret_cast<const uint4*>(tile + sw128_offset(r, 2 * c16));
+    uint4 b = *reinterpret_cast<const uint4*>(tile + sw128_offset(r, 2 * c16 + 1));
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { f[2 * i] = bf16_lo(w[i]); f[2 * i + 1] = bf16_hi(w[i]); }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+namespace gf {
+constexpr int WIH = 0, WHH = 24576, W2 = 49152, XB = 57344, HT = 90112, BIAS = 106496;   // byte offsets
+constexpr int BIAS_FLOATS = 128 + 64 + 64 + 64;                                         // brz | bin | bhn | b2
+constexpr int BARS = BIAS + BIAS_FLOATS * 4;
+constexpr int SMEM_BYTES = 1024 + BARS + 128;
+constexpr int THREADS = 192;
+}  // namespace gf
+
+
+__global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams P) {
+    using namespace gf;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* bias = reinterpret_cast<float*>(smem + BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* w_full = bars;             // weights landed
+    uint64_t* x_full = bars + 1;         // [2]
+    uint64_t* x_empty = bars + 3;        // [2]
+    uint64_t* gates_full = bars + 5;
+    uint64_t* q_full = bars + 6;
+    uint64_t* h_ready = bars + 7;        // epilogue wrote the h operand tile
+    uint64_t* tmem_free = bars + 8;      // epilogue finished reading q
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int A_pad = (P.A + 15) & ~15;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1);
+        mbar_init(&x_empty[0], 1); mbar_init(&x_empty[1], 1);
+        mbar_init(gates_full, 1); mbar_init(q_full, 1);
+        mbar_init(h_ready, 4); mbar_init(tmem_free, 4);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    // biases: brz = b_ih + b_hh for r, z ; bin = b_ih[n] ; bhn = b_hh[n] ; b2
+    for (int i = threadIdx.x; i < 128; i += THREADS) bias[i] = P.b_ih[i] + P.b_hh[i];
+    for (int i = threadIdx.x; i < 64; i += THREADS) {
+        bias[128 + i] = P.b_ih[128 + i];
+        bias[192 + i] = P.b_hh[128 + i];
+        bias[256 + i] = i < P.A ? P.b2[i] : 0.f;
+    }
+    // initial hidden state: registers (fp32) + operand tile (bf16)
+    float h[64];
+    const uint32_t r = warp * 32 + lane;                      // tile row of an epilogue thread
+    const int64_t row = (int64_t)tile * TILE_ROWS + r;
+    const bool valid = warp < 4 && row < P.R;
+    if (warp < 4) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) h[j] = 0.f;
+        if (valid && P.h0) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) h[j] = P.h0[row * 64 + j];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = h[16 * c + j];
+            store_row16(smem + HT, r, c, f);
+            if (P.h_ti) store_row16(P.h_ti + (int64_t)tile * TILE_BYTES, r, c, f);
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 5) {
+        // ===== loader: weights once, then one x tile per step =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, 24576 + 24576 + 8192);
+            bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
+            bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
+            bulk_copy_g2s(smem + W2, P.w2_img, 8192, w_full);
+            for (int t = 0; t < P.nt; ++t) {
+                const int b = t & 1;
+                mbar_wait(&x_empty[b], ((t >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&x_full[b], TILE_BYTES);
+                bulk_copy_g2s(smem + XB + b * TILE_BYTES, P.x_ti + ((int64_t)t * P.n_tiles + tile) * TILE_BYTES, TILE_BYTES,
+                              &x_full[b]);
+            }
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH), w2 = smem_u32(smem + W2);
+            const uint32_t ht = smem_u32(smem + HT);
+            const uint32_t id128 = umma_idesc_bf16(128, 128, 0, 0), id64 = umma_idesc_bf16(128, 64, 0, 0);
+            const uint32_t idq = umma_idesc_bf16(128, A_pad, 0, 0);
+            mbar_wait(w_full, 0);
+            for (int t = 0; t < P.nt; ++t) {
+                const int b = t & 1;
+                const uint32_t xt = smem_u32(smem + XB + b * TILE_BYTES);
+                mbar_wait(&x_full[b], (t >> 1) & 1);
+                mbar_wait(tmem_free, (t & 1) ^ 1);             // q(t-1) drained (passes at t = 0)
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {               // r|z : x . W_i{r,z}^T
+                    umma_bf16(tmem_base, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024),
+                              id128, kk != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {               //       + h . W_h{r,z}^T
+                    umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024),
+                              id128, 1);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {               // n, input part
+                    umma_bf16(tmem_base + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
+                              umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {               // n, hidden part
+                    umma_bf16(tmem_base + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
+                              umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+                }
+                umma_commit(&x_empty[b]);
+                umma_commit(gates_full);
+                // fc2 on the new hidden state
+                mbar_wait(h_ready, t & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(w2 + kk * 32, 16, 1024),
+                              idq, kk != 0);
+                }
+                umma_commit(q_full);
+            }
+        }
+    } else {
+        // ===== epilogue: gate math, hidden state update, q =====
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int t = 0; t < P.nt; ++t) {
+            mbar_wait(gates_full, t & 1);
+            tc_fence_after();
+            uint8_t* hti = P.h_ti ? P.h_ti + ((int64_t)(t + 1) * P.n_tiles + tile) * TILE_BYTES : nullptr;
+            uint8_t* gti = P.g_ti ? P.g_ti + ((int64_t)t * P.n_tiles + tile) * 4 * TILE_BYTES : nullptr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t ar[16], az[16], ain[16], ahn[16];
+                tmem_ld_32x16(tlane + 16 * c, ar);
+                tmem_ld_32x16(tlane + 64 + 16 * c, az);
+                tmem_ld_32x16(tlane + 128 + 16 * c, ain);
+                tmem_ld_32x16(tlane + 192 + 16 * c, ahn);
+                tmem_wait_ld();
+                float fr[16], fz[16], fn[16], fhn[16], fh[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int jj = 16 * c + j;
+                    float rg = fast_sigmoid(__uint_as_float(ar[j]) + bias[jj]);
+                    float zg = fast_sigmoid(__uint_as_float(az[j]) + bias[64 + jj]);
+                    float hn = __uint_as_float(ahn[j]) + bias[192 + jj];
+                    float ng = fast_tanh(__uint_as_float(ain[j]) + bias[128 + jj] + rg * hn);
+                    float hv = ng + zg * (h[jj] - ng);
+                    h[jj] = hv;
+                    fr[j] = rg; fz[j] = zg; fn[j] = ng; fhn[j] = hn; fh[j] = hv;
+                }
+                store_row16(smem + HT, r, c, fh);
+                if (valid) {
+                    if (hti) store_row16(hti, r, c, fh);
+                    if (gti) {
+                        store_row16(gti, r, c, fr);
+                        store_row16(gti + TILE_BYTES, r, c, fz);
+                        store_row16(gti + 2 * TILE_BYTES, r, c, fn);
+                        store_row16(gti + 3 * TILE_BYTES, r, c, fhn);
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_ready);
+            if (valid && P.h_last && t == P.nt - 1) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) P.h_last[row * 64 + j] = h[j];
+            }
+            // q = fc2(h)
+            mbar_wait(q_full, t & 1);
+            tc_fence_after();
+            float* qo = P.q + ((int64_t)t * P.R + row) * P.A;
+            for (int c0 = 0; c0 < A_pad; c0 += 16) {
+                uint32_t aq[16];
+                tmem_ld_32x16(tlane + c0, aq);
+                tmem_wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < P.A) qo[c0 + j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_free);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (BPTT), two sub-tiles per CTA in ping-pong
+// ------------------------------------------------------------------------------------------
+namespace gb {
+constexpr int WIH = 0, WHH = 24576, DG = 49152;               // DG: [2 sub-tiles][4 gates][16 KB]
+constexpr int BARS = DG + 2 * 4 * TILE_BYTES;                 // 180224
+constexpr int SMEM_BYTES = 1024 + BARS + 128;
+constexpr int THREADS = 256;                                  // 2 sub-tiles x 4 warps; warp 0 of a sub-tile also issues its MMAs
+}  // namespace gb
+
+
+__device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
+    f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
+    f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+__global__ void __launch_bounds__(gb::THREADS, 1) gru_bwd_tc_kernel(GruBwdParams P) {
+    using namespace gb;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* w_full = bars;
+    uint64_t* dg_ready = bars + 1;       // [2]
+    uint64_t* mma_done = bars + 3;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&dg_ready[i], 4); mbar_init(&mma_done[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(w_full, 2 * 24576);
+        bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
+        bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
+    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);          // A K-major, B MN-major
+    {
+        const int st = warp >> 2;
+        const int tile = 2 * blockIdx.x + st;
+        if (tile < P.n_tiles) {
+            const uint32_t r = (warp & 3) * 32 + lane;
+            const int64_t row = (int64_t)tile * TILE_ROWS + r;
+            const bool valid = row < P.R;
+            const int64_t b = valid ? row / P.N : 0;
+            const int n = valid ? (int)(row - b * P.N) : 0;
+            uint8_t* dgs = smem + DG + st * 4 * TILE_BYTES;
+            const uint32_t tlane = tmem_base + st * 128 + ((uint32_t)((warp & 3) * 32) << 16);
+            float dh[64], zk[64];
+            uint64_t xmask = 0;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) dh[j] = 0.f;
+
+            for (int i = 0; i < P.T; ++i) {
+                const int t = P.T - 1 - i;
+                const int64_t toff = ((int64_t)t * P.n_tiles + tile) * TILE_BYTES;
+                uint8_t* g_t = P.g_ti + toff * 4;
+                // chosen-action gradient enters through fc2: dh += dq * fc2_w[a, :]
+                if (valid && t < P.T - 1) {
+                    const float dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
+                    if (dq != 0.f) {
+                        const int a = (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n);
+                        const float4* w2 = reinterpret_cast<const float4*>(P.fc2_w + (int64_t)a * 64);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            float4 w = __ldg(w2 + q);
+                            dh[4 * q] = fmaf(dq, w.x, dh[4 * q]); dh[4 * q + 1] = fmaf(dq, w.y, dh[4 * q + 1]);
+                            dh[4 * q + 2] = fmaf(dq, w.z, dh[4 * q + 2]); dh[4 * q + 3] = fmaf(dq, w.w, dh[4 * q + 3]);
+                        }
+                    }
+                }
+                xmask = 0;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    // issue all loads of this half (32 columns = 4 chunks) before using them
+                    uint4 vr[4], vz[4], vn[4], vhn[4], vhp[4], vx[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t off = sw128_offset(r, 4 * half + c);
+                        if (valid) {
+                            vr[c] = *reinterpret_cast<const uint4*>(g_t + off);
+                            vz[c] = *reinterpret_cast<const uint4*>(g_t + TILE_BYTES + off);
+                            vn[c] = *reinterpret_cast<const uint4*>(g_t + 2 * TILE_BYTES + off);
+                            vhn[c] = *reinterpret_cast<const uint4*>(g_t + 3 * TILE_BYTES + off);
+                            vhp[c] = __ldg(reinterpret_cast<const uint4*>(P.h_ti + toff + off));
+                            vx[c] = __ldg(reinterpret_cast<const uint4*>(P.x_ti + toff + off));
+                        } else {
+                            vr[c] = vz[c] = vn[c] = vhn[c] = vhp[c] = vx[c] = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float fr[8], fz[8], fn[8], fhn[8], fhp[8], fx[8], dr[8], dz[8], dn[8], dnr[8];
+                        unpack8(vr[c], fr); unpack8(vz[c], fz); unpack8(vn[c], fn); unpack8(vhn[c], fhn);
+                        unpack8(vhp[c], fhp); unpack8(vx[c], fx);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int jj = 32 * half + 8 * c + j;
+                            const float d = dh[jj];
+                            const float dnn = d * (1.f - fz[j]);
+                            const float dzz = d * (fhp[j] - fn[j]);
+                            const float da_n = dnn * (1.f - fn[j] * fn[j]);
+                            dr[j] = (da_n * fhn[j]) * fr[j] * (1.f - fr[j]);
+                            dz[j] = dzz * fz[j] * (1.f - fz[j]);
+                            dn[j] = da_n;
+                            dnr[j] = da_n * fr[j];
+                            zk[jj] = fz[j];
+                            xmask |= (uint64_t)(fx[j] > 0.f ? 1u : 0u) << jj;
+                        }
+                        const uint32_t off = sw128_offset(r, 4 * half + c);
+                        const uint4 pr = pack8(dr), pz = pack8(dz), pn = pack8(dn), pnr = pack8(dnr);
+                        *reinterpret_cast<uint4*>(dgs + off) = pr;
+                        *reinterpret_cast<uint4*>(dgs + TILE_BYTES + off) = pz;
+                        *reinterpret_cast<uint4*>(dgs + 2 * TILE_BYTES + off) = pn;
+                        *reinterpret_cast<uint4*>(dgs + 3 * TILE_BYTES + off) = pnr;
+                        // every row is written (padding rows of the last tile hold zeros) so that the
+                        // row reduction in gru_dw_tc sees finite values
+                        *reinterpret_cast<uint4*>(g_t + off) = pr;
+                        *reinterpret_cast<uint4*>(g_t + TILE_BYTES + off) = pz;
+                        *reinterpret_cast<uint4*>(g_t + 2 * TILE_BYTES + off) = pn;
+                        *reinterpret_cast<uint4*>(g_t + 3 * TILE_BYTES + off) = pnr;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dg_ready[st]);
+                if ((warp & 3) == 0 && lane == 0) {
+                    // this sub-tile's MMA issuer: wait for its four warps, then 24 tcgen05.mma
+                    if (i == 0) mbar_wait(w_full, 0);
+                    mbar_wait(&dg_ready[st], i & 1);
+                    tc_fence_after();
+                    const uint32_t dg = smem_u32(dgs);
+                    const uint32_t t_dx = tmem_base + st * 128, t_dh = t_dx + 64;
+                    // dx = da_r W_ir + da_z W_iz + da_n W_in
+#pragma unroll
+                    for (int g = 0; g < 3; ++g)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(t_dx, umma_desc_sw128(dg + g * TILE_BYTES + kk * 32, 16, 1024),
+                                      umma_desc_sw128(wih + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                    // dh_prev (recurrent part) = da_r W_hr + da_z W_hz + (da_n r) W_hn
+#pragma unroll
+                    for (int g = 0; g < 3; ++g)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(t_dh, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES + kk * 32, 16, 1024),
+                                      umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                    umma_commit(&mma_done[st]);
+                }
+                __syncwarp();
+
+                mbar_wait(&mma_done[st], i & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t ax[16], ah[16];
+                    tmem_ld_32x16(tlane + 16 * c, ax);
+                    tmem_ld_32x16(tlane + 64 + 16 * c, ah);
+                    tmem_wait_ld();
+                    float dp[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int jj = 16 * c + j;
+                        dp[j] = (xmask >> jj) & 1ull ? __uint_as_float(ax[j]) : 0.f;
+                        dh[jj] = dh[jj] * zk[jj] + __uint_as_float(ah[j]);
+                    }
+                    if (valid) store_row16(P.dpre1_ti + toff, r, c, dp);
+                }
+                tc_fence_before();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// rnn.weight_ih / weight_hh / bias gradients from tile images (pure bulk-copy + MMA)
+// ------------------------------------------------------------------------------------------
+namespace gd {
+constexpr int STAGE_BYTES = 6 * TILE_BYTES;                   // dg (4 tiles) | x | h_prev
+constexpr int ONES = 2 * STAGE_BYTES;                         // static all-ones block (16 KB)
+constexpr int BARS = ONES + TILE_BYTES;
+constexpr int SMEM_BYTES = 1024 + BARS + 128;
+constexpr int THREADS = 192;
+constexpr int PARTIAL_FLOATS = 2 * 192 * 64 + 2 * 192;       // dW_ih | dW_hh | db_ih | db_hh
+}  // namespace gd
+
+struct GruDwParams {
+    const uint8_t* g_ti;             // [T][n_tiles][4][16 KB]  da_r, da_z, da_n, da_n*r
+    const uint8_t* x_ti;             // [T][n_tiles][16 KB]
+    const uint8_t* h_ti;             // [(T+1)][n_tiles][16 KB]   slot t = h_{t-1}
+    float* partial;                  // [grid][PARTIAL_FLOATS]
+    int64_t n_items;                 // T * n_tiles
+    int64_t items_per_cta;
+};
+
+__global__ void __launch_bounds__(gd::THREADS, 1) gru_dw_tc_kernel(GruDwParams P) {
+    using namespace gd;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* full = bars;               // [2]
+    uint64_t* empty = bars + 2;          // [2]
+    uint64_t* done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    // the ones block: bf16 1.0 everywhere (only the first 16 columns are read)
+    for (int i = threadIdx.x; i < TILE_BYTES / 16; i += THREADS)
+        reinterpret_cast<uint4*>(smem + ONES)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t beg = (int64_t)blockIdx.x * P.items_per_cta;
+    const int64_t end = beg + P.items_per_cta < P.n_items ? beg + P.items_per_cta : P.n_items;
+    const int64_t n_my = end > beg ? end - beg : 0;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int64_t i = 0; i < n_my; ++i) {
+                const int s = (int)(i & 1);
+                const int64_t item = beg + i;                 // item = t * n_tiles + tile (same index in all buffers)
+                mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                bulk_copy_g2s(st, P.g_ti + item * 4 * TILE_BYTES, 4 * TILE_BYTES, &full[s]);
+                bulk_copy_g2s(st + 4 * TILE_BYTES, P.x_ti + item * TILE_BYTES, TILE_BYTES, &full[s]);
+                bulk_copy_g2s(st + 5 * TILE_BYTES, P.h_ti + item * TILE_BYTES, TILE_BYTES, &full[s]);
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0 && n_my > 0) {
+            const uint32_t id128 = umma_idesc_bf16(128, 128, 1, 1), id16 = umma_idesc_bf16(128, 16, 1, 1);
+            const uint32_t ones = smem_u32(smem + ONES);
+            for (int64_t i = 0; i < n_my; ++i) {
+                const int s = (int)(i & 1);
+                mbar_wait(&full[s], (i >> 1) & 1);
+                tc_fence_after();
+                const uint32_t dg = smem_u32(smem + s * STAGE_BYTES), xh = dg + 4 * TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {               // 128 rows = 8 x (K = 16)
+                    const uint32_t acc = (i | kk) != 0;
+                    const uint64_t a_rz = umma_desc_sw128(dg + kk * 2048, TILE_BYTES, 1024);
+                    const uint64_t a_nn = umma_desc_sw128(dg + 2 * TILE_BYTES + kk * 2048, TILE_BYTES, 1024);
+                    const uint64_t b_xh = umma_desc_sw128(xh + kk * 2048, TILE_BYTES, 1024);
+                    const uint64_t b_1 = umma_desc_sw128(ones + kk * 2048, TILE_BYTES, 1024);
+                    umma_bf16(tmem_base, a_rz, b_xh, id128, acc);            // [r|z]^T [x|h]
+                    umma_bf16(tmem_base + 128, a_nn, b_xh, id128, acc);      // [n|nr]^T [x|h]
+                    umma_bf16(tmem_base + 256, a_rz, b_1, id16, acc);        // column sums
+                    umma_bf16(tmem_base + 272, a_nn, b_1, id16, acc);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(done);
+        }
+    } else {
+        // epilogue: row c of the accumulators = gate column (warp*32 + lane) of the [r|z] resp. [n|nr] pair
+        float* out = P.partial + (int64_t)blockIdx.x * PARTIAL_FLOATS;
+        float* dwih = out, *dwhh = out + 192 * 64, *dbih = out + 2 * 192 * 64, *dbhh = dbih + 192;
+        const int c = warp * 32 + lane;                       // 0..127
+        if (n_my > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int g = 0; g < 128; g += 32) {
+                uint32_t v1[32], v2[32];
+                tmem_ld_32x32(tl + g, v1);
+                tmem_ld_32x32(tl + 128 + g, v2);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int k = (g + j) & 63;
+                    if (g < 64) {                                     // x columns -> weight_ih
+                        dwih[c * 64 + k] = __uint_as_float(v1[j]);                       // rows r, z
+                        if (c < 64) dwih[(128 + c) * 64 + k] = __uint_as_float(v2[j]);   // rows n
+                    } else {                                          // h columns -> weight_hh
+                        dwhh[c * 64 + k] = __uint_as_float(v1[j]);
+                        if (c >= 64) dwhh[(128 + c - 64) * 64 + k] = __uint_as_float(v2[j]);   // rows n (from da_n*r)
+                    }
+                }
+            }
+            uint32_t b1[16], b2[16];
+            tmem_ld_32x16(tl + 256, b1);
+            tmem_ld_32x16(tl + 272, b2);
+            tmem_wait_ld();
+            dbih[c] = __uint_as_float(b1[0]);
+            dbhh[c] = __uint_as_float(b1[0]);
+            if (c < 64) dbih[128 + c] = __uint_as_float(b2[0]);
+            else dbhh[128 + c - 64] = __uint_as_float(b2[0]);
+        } else {
+            for (int i = threadIdx.x; i < PARTIAL_FLOATS; i += 128) out[i] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void gru_dw_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ w_ih,
+                                     float* __restrict__ w_hh, float* __restrict__ b_ih, float* __restrict__ b_hh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= gd::PARTIAL_FLOATS) return;
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * gd::PARTIAL_FLOATS + i];
+    if (i < 192 * 64) w_ih[i] = s;
+    else if (i < 2 * 192 * 64) w_hh[i - 192 * 64] = s;
+    else if (i < 2 * 192 * 64 + 192) b_ih[i - 2 * 192 * 64] = s;
+    else b_hh[i - 2 * 192 * 64 - 192] = s;
+}
+
+// zero the padding rows (row >= R) of the last tile of every timestep of a tile-image buffer
+__global__ void ti_zero_pad_kernel(uint8_t* buf, int n_t, int n_tiles, int64_t R) {
+    const int pad0 = (int)(R - (int64_t)(n_tiles - 1) * TILE_ROWS);      // first padding row of the last tile
+    const int n_pad = TILE_ROWS - pad0;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one 16-byte chunk each
+    int64_t total = (int64_t)n_t * n_pad * 8;
+    if (i >= total) return;
+    int j = (int)(i & 7);
+    int64_t q = i >> 3;
+    int rr = pad0 + (int)(q % n_pad);
+    int64_t t = q / n_pad;
+    uint8_t* tile = buf + (t * n_tiles + (n_tiles - 1)) * TILE_BYTES;
+    *reinterpret_cast<uint4*>(tile + sw128_offset((uint32_t)rr, (uint32_t)j)) = make_uint4(0, 0, 0, 0);
+}
+
+}  // namespace tc
+
+int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
+    PMB_CUDA(cudaFuncSetAttribute(tc::gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gf::SMEM_BYTES));
+    tc::gru_fwd_tc_kernel<<<P.n_tiles, tc::gf::THREADS, tc::gf::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("gru_fwd_tc_kernel");
+    return PMB_OK;
+}
+
+int64_t tc_gru_dw_scratch_bytes() { return align_up((int64_t)148 * 2 * tc::gd::PARTIAL_FLOATS * 4, 256); }
+
+int tc_gru_dw(const uint8_t* g_ti, const uint8_t* x_ti, const uint8_t* h_ti, int T, int n_tiles, float* w_ih, float* w_hh,
+              float* b_ih, float* b_hh, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+    tc::GruDwParams P;
+    P.g_ti = g_ti; P.x_ti = x_ti; P.h_ti = h_ti;
+    P.n_items = (int64_t)T * n_tiles;
+    int grid = (int)(P.n_items < sm_count() ? P.n_items : sm_count());
+    if ((int64_t)grid * tc::gd::PARTIAL_FLOATS * 4 > scratch_bytes) { set_error("tc_gru_dw: scratch too small"); return PMB_ERR_WORKSPACE; }
+    P.items_per_cta = ceil_div(P.n_items, grid);
+    P.partial = static_cast<float*>(scratch);
+    PMB_CUDA(cudaFuncSetAttribute(tc::gru_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gd::SMEM_BYTES));
+    tc::gru_dw_tc_kernel<<<grid, tc::gd::THREADS, tc::gd::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("gru_dw_tc_kernel");
+    tc::gru_dw_reduce_kernel<<<(unsigned)ceil_div(tc::gd::PARTIAL_FLOATS, 256), 256, 0, s>>>(P.partial, grid, w_ih, w_hh, b_ih,
+                                                                                            b_hh);
+    PMB_LAUNCH_CHECK("gru_dw_reduce_kernel");
+    return PMB_OK;
+}
+
+int tc_ti_zero_pad(uint8_t* buf, int n_t, int n_tiles, int64_t R, cudaStream_t s) {
+    if (R % tc::TILE_ROWS == 0) return PMB_OK;
+    int n_pad = (int)((int64_t)n_tiles * tc::TILE_ROWS - R);
+    int64_t total = (int64_t)n_t * n_pad * 8;
+    tc::ti_zero_pad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(buf, n_t, n_tiles, R);
+    PMB_LAUNCH_CHECK("ti_zero_pad_kernel");
+    return PMB_OK;
+}
+
+int tc_gru_bwd(const tc::GruBwdParams& P, cudaStream_t s) {
+    PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gb::SMEM_BYTES));
+    tc::gru_bwd_tc_kernel<<<(P.n_tiles + 1) / 2, tc::gb::THREADS, tc::gb::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("gru_bwd_tc_kernel");
+    return PMB_OK;
+}
+
+}  // namespace pmb

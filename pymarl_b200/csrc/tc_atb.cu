@@ -36,6 +36,10 @@ struct AtbParams {
     int64_t rows_per_slice;                       // multiple of 64
     float* partial;                               // [slices][C][K + 1]
     int tile_w;                                   // columns per n-tile (multiple of 16, <= 256), balanced
+    // tile-image mode (D = bf16 [T][n_tiles][16 KB] images, C = 64): rows are m = t * R_pad + p
+    const uint8_t* d_ti;
+    int ti_T, ti_N, ti_n_tiles;
+    int64_t ti_R;
 };
 
 // load 4 consecutive floats p[0..3] with per-element validity, using the widest aligned access
@@ -94,6 +98,13 @@ __global__ void __launch_bounds__(atb::THREADS, 1) tc_atb_kernel(AtbParams P) {
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
+    if (P.d_ti) {                                               // MN block 1 of every D stage stays zero
+        for (int i = threadIdx.x; i < STAGES * (BLOCK_BYTES / 16); i += THREADS) {
+            const int s = i / (BLOCK_BYTES / 16), q = i - s * (BLOCK_BYTES / 16);
+            reinterpret_cast<uint4*>(d_stage + s * D_STAGE_BYTES + BLOCK_BYTES)[q] = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -112,7 +123,18 @@ __global__ void __launch_bounds__(atb::THREADS, 1) tc_atb_kernel(AtbParams P) {
             const float* myptr = nullptr;
             if (lane < RPW) {
                 const int64_t m = mbeg + (int64_t)ch * BR + pw + N_A_WARPS * lane;
-                if (m < mend) myptr = P.A + P.amap.offset(m);
+                if (m < mend) {
+                    if (P.d_ti) {
+                        const int64_t r_pad = (int64_t)P.ti_n_tiles * 128;
+                        const int64_t t = m / r_pad, pp = m - t * r_pad;
+                        if (pp < P.ti_R) {
+                            const int64_t bb = pp / P.ti_N, nn = pp - bb * P.ti_N;
+                            myptr = P.A + P.amap.offset((bb * P.ti_T + t) * P.ti_N + nn);
+                        }
+                    } else {
+                        myptr = P.A + P.amap.offset(m);
+                    }
+                }
             }
             float v[RPW][2][4];
             uint32_t row_ok = 0;
@@ -161,6 +183,26 @@ __global__ void __launch_bounds__(atb::THREADS, 1) tc_atb_kernel(AtbParams P) {
         const int pw = warp - FIRST_D_WARP;
         const int cc = 4 * lane;
         const int nv = P.C - (c0 + cc);
+        if (P.d_ti) {
+            // tile-image mode: the 64 rows of a chunk are one contiguous 8 KB piece of a tile image
+            // (= MN block 0); block 1 of every stage was zeroed at start.  One bulk copy per chunk.
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const int s = ch % STAGES;
+                mbar_wait(&empty[s], ((ch / STAGES) & 1) ^ 1);
+                if (lane == 0) {
+                    if (pw == 0) {
+                        const int64_t m0 = mbeg + (int64_t)ch * BR;
+                        const int64_t r_pad = (int64_t)P.ti_n_tiles * 128;
+                        const int64_t t = m0 / r_pad, p0 = m0 - t * r_pad;
+                        const uint8_t* src = P.d_ti + (t * P.ti_n_tiles + (p0 >> 7)) * 16384 + (p0 & 127) * 128;
+                        mbar_arrive_expect_tx(&full[s], BLOCK_BYTES);
+                        bulk_copy_g2s(d_stage + s * D_STAGE_BYTES, src, BLOCK_BYTES, &full[s]);
+                    } else {
+                        mbar_arrive(&full[s]);
+                    }
+                }
+            }
+        } else
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int s = ch % STAGES;
             const float* myptr = nullptr;
@@ -297,6 +339,7 @@ int tc_gemm_atb(const float* D, RowMap dmap, int C, const float* A, RowMap amap,
     P.rows_per_slice = align_up(ceil_div(M, slices), tc::atb::BR);
     P.partial = static_cast<float*>(scratch);
     P.tile_w = tc_atb_tile_w(K);
+    P.d_ti = nullptr; P.ti_T = P.ti_N = P.ti_n_tiles = 0; P.ti_R = 0;
     PMB_CUDA(cudaFuncSetAttribute(tc::tc_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::atb::SMEM_BYTES));
     dim3 grid((unsigned)ceil_div(K + 1, P.tile_w), (unsigned)ceil_div(C, tc::atb::BC), (unsigned)slices);
     tc::tc_atb_kernel<<<grid, tc::atb::THREADS, tc::atb::SMEM_BYTES, s>>>(P);
@@ -306,5 +349,29 @@ int tc_gemm_atb(const float* D, RowMap dmap, int C, const float* A, RowMap amap,
     PMB_LAUNCH_CHECK("atb_reduce_kernel");
     return PMB_OK;
 }
+
+// fc1.weight[:, :O] / fc1.bias gradient: D = dpre1 tile images (C = 64), A = obs (fp32, batch major)
+int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, const float* A, RowMap amap, int K,
+                   float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+    const int C = 64;
+    const int64_t M = (int64_t)T * n_tiles * 128;
+    const int slices = tc_atb_slices(C, K, M);
+    if (tc_atb_scratch_bytes(C, K, M) > scratch_bytes) { set_error("tc_gemm_atb_ti: scratch too small"); return PMB_ERR_WORKSPACE; }
+    tc::AtbParams P;
+    P.D = nullptr; P.dmap = dense_map(0); P.C = C; P.A = A; P.amap = amap; P.K = K; P.M = M;
+    P.rows_per_slice = align_up(ceil_div(M, slices), tc::atb::BR);
+    P.partial = static_cast<float*>(scratch);
+    P.tile_w = tc_atb_tile_w(K);
+    P.d_ti = d_ti; P.ti_T = T; P.ti_N = N; P.ti_n_tiles = n_tiles; P.ti_R = R;
+    PMB_CUDA(cudaFuncSetAttribute(tc::tc_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::atb::SMEM_BYTES));
+    dim3 grid((unsigned)ceil_div(K + 1, P.tile_w), 1, (unsigned)slices);
+    tc::tc_atb_kernel<<<grid, tc::atb::THREADS, tc::atb::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("tc_atb_kernel<ti>");
+    int64_t n = (int64_t)C * (K + 1);
+    tc::atb_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(P.partial, slices, C, K, out, ldo, bias_out);
+    PMB_LAUNCH_CHECK("atb_reduce_kernel");
+    return PMB_OK;
+}
+int64_t tc_atb_ti_scratch_bytes(int T, int n_tiles, int K) { return tc_atb_scratch_bytes(64, K, (int64_t)T * n_tiles * 128); }
 
 }  // namespace pmb

@@ -71,7 +71,7 @@ pack_w_kernel(PackSegs segs, int K, int n_chunks, int Ncols, __nv_bfloat16* __re
     const float* src = nullptr;
     int rr = col;
     for (int s = 0; s < segs.nseg; ++s) {
-        if (rr < segs.rows[s]) { src = segs.ptr[s] + (int64_t)rr * segs.ld[s]; break; }
+        if (rr < segs.rows[s]) { src = segs.ptr[s] ? segs.ptr[s] + (int64_t)rr * segs.ld[s] : nullptr; break; }
         rr -= segs.rows[s];
     }
     uint32_t w[4];
@@ -303,6 +303,55 @@ struct Fc1Epi {
     __device__ void end(Row&, int64_t, bool) const {}
 };
 
+// Same, but x is written as bf16 tile images [nt][n_tiles][16 KB] (the operand format of gru_tc.cu).
+struct Fc1TiEpi {
+    struct Row { int64_t tile_off; uint32_t r; int n; int a_prev; };
+    const float* tab_act; const float* tab_id;
+    const int64_t* actions; int64_t actions_sb;
+    const int64_t* filled;  int64_t filled_sb;
+    uint8_t* x_on; uint8_t* x_tg;
+    int t0, nt, N, A, use_act, n_tiles;
+    __device__ void begin(Row& r, int64_t m, bool valid) const {
+        r.tile_off = 0; r.r = 0; r.n = 0; r.a_prev = -1;
+        if (!valid) return;
+        const int tn = nt * N;
+        int64_t b = m / tn;
+        int rem = (int)(m - b * tn);
+        int tl = rem / N;
+        r.n = rem - tl * N;
+        int t = t0 + tl;
+        if (use_act && t > 0 && filled[b * filled_sb + (t - 1)] != 0)
+            r.a_prev = (int)actions[b * actions_sb + (int64_t)(t - 1) * N + r.n];
+        int64_t p = b * N + r.n;
+        r.tile_off = ((int64_t)tl * n_tiles + (p >> 7)) * 16384;
+        r.r = (uint32_t)(p & 127);
+    }
+    __device__ void cols(Row& r, int64_t, bool valid, int col0, const uint32_t (&v)[32]) const {
+        if (!valid) return;
+        const int net = col0 >> 6, h0 = col0 & 63;
+        uint8_t* tile = (net ? x_tg : x_on) + r.tile_off;
+        const float4* tid = reinterpret_cast<const float4*>(tab_id + ((int64_t)net * N + r.n) * 64 + h0);
+        const float4* tac = r.a_prev >= 0 ? reinterpret_cast<const float4*>(tab_act + ((int64_t)net * A + r.a_prev) * 64 + h0)
+                                          : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                 // 8 columns = one 16-byte chunk
+            float o[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float4 bi = __ldg(tid + 2 * q + hh);
+                float4 ac = tac ? __ldg(tac + 2 * q + hh) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[4 * hh + 0] = fmaxf(__uint_as_float(v[8 * q + 4 * hh + 0]) + ac.x + bi.x, 0.f);
+                o[4 * hh + 1] = fmaxf(__uint_as_float(v[8 * q + 4 * hh + 1]) + ac.y + bi.y, 0.f);
+                o[4 * hh + 2] = fmaxf(__uint_as_float(v[8 * q + 4 * hh + 2]) + ac.z + bi.z, 0.f);
+                o[4 * hh + 3] = fmaxf(__uint_as_float(v[8 * q + 4 * hh + 3]) + ac.w + bi.w, 0.f);
+            }
+            *reinterpret_cast<uint4*>(tile + sw128_offset(r.r, (uint32_t)(h0 / 8 + q))) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
+    }
+    __device__ void end(Row&, int64_t, bool) const {}
+};
+
 // QMIX mixing on the hypernet outputs, E = 32.  Packed column order: [ w1 (N*32) | b1 | w_final | v0 ].
 //   hidden = ELU(sum_n q[n] |w1[n, :]| + b1);  q_tot = hidden . |w_final| + V.2(ReLU(v0))
 // raw_out (optional, bf16 [M][(N+3)*32], packed column order) keeps the hypernet outputs for the backward.
@@ -431,7 +480,7 @@ __global__ void fc1_tables_kernel(const float* __restrict__ w_on, const float* _
 }
 
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
-                    float* x_on, float* x_tg, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+                    float* x_on, float* x_tg, int tile_images, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
     // scratch: packed W (128 x Kpad bf16) | tab_act | tab_id
     const int D_in = d_in_of(d);
     int64_t wp_bytes = align_up(tc_packed_elems(128, d->O) * 2, 256);
@@ -453,6 +502,13 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     const int64_t M = (int64_t)d->B * nt * d->N;
     RowMap map{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, nt, d->N};
     tc::GemmParams P{b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, (d->O + tc::BK - 1) / tc::BK, wp, 128};
+    if (tile_images) {
+        const int n_tiles = (int)ceil_div((int64_t)d->B * d->N, 128);
+        tc::Fc1TiEpi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb,
+                         reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
+                         d->obs_last_action, n_tiles};
+        return tc::launch_tc_gemm(P, epi, s);
+    }
     tc::Fc1Epi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb, x_on, x_tg,
                    t0, nt, d->N, d->A, d->obs_last_action, (int64_t)d->B * d->N};
     return tc::launch_tc_gemm(P, epi, s);

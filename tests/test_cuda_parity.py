@@ -383,7 +383,7 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
     # (sign flips -> hypernet tensors).  A ~0.3 % fraction of entries flips and each flip is a full-size
     # error on one term of a sum, so those tensors carry a few-percent error that is inherent to a single
     # bf16 pass (it is NOT accumulation error: fp32 accumulate).  Bounds: recurrent / fc2 tensors 1e-2
-    # norm-wise, fc1 5e-2, hypernet tensors 0.15 in the relative L2 norm.  The observed errors are printed.
+    # norm-wise, fc1 5e-2 in the relative L2 norm, hypernet tensors 0.15 in the relative L2 norm.  The observed errors are printed.
     errs = {}
     for k, v in raw_grads.items():
         kind, name = k.split(".", 1)
@@ -394,7 +394,7 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
     print({k: ("%.2e" % a, "%.2e" % b) for k, (a, b) in errs.items()})
     for k, (mx, l2) in errs.items():
         if k.startswith("agent.fc1"):
-            assert mx < 5 * TOL_BF16, (k, mx, l2)
+            assert l2 < 5 * TOL_BF16 and mx < 0.15, (k, mx, l2)
         elif k.startswith("agent."):
             assert mx < TOL_BF16, (k, mx, l2)
         else:
