@@ -1,0 +1,35 @@
+"""Data-parallel plumbing for the learner (one process per GPU, torch.distributed).
+
+Episodes are independent units: rank r trains on a contiguous slice of the sampled batch and
+contributes the UN-normalised gradient of sum((td * mask)^2) plus the five loss sums; one
+all-reduce(sum) of each per step, after which every rank applies the identical clip + RMSprop
+update (parameters / optimizer state stay replicated - no broadcast).  Replay indices are drawn
+once (rank 0's numpy stream) and sliced, so sampling stays identical to the 1-GPU run."""
+import torch as th
+import torch.distributed as dist
+
+
+def is_active():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def shard_slice(batch_size, rank, world):
+    """Contiguous episode range [lo, hi) of this rank (the first `batch_size % world` ranks get one more)."""
+    base, rem = divmod(batch_size, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_fields(fields, rank, world):
+    """Slice every batch-major field to this rank's episodes (views, no copy)."""
+    some = next(iter(fields.values()))
+    lo, hi = shard_slice(some.shape[0], rank, world)
+    return {k: v[lo:hi] for k, v in fields.items()}
+
+
+def allreduce_step(flat_grad, loss_sums):
+    """Sum the un-normalised flat gradient and the loss sums over all ranks (in place)."""
+    if not is_active():
+        return
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    dist.all_reduce(loss_sums, op=dist.ReduceOp.SUM)

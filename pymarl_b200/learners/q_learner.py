@@ -15,7 +15,7 @@ import ctypes as C
 
 import torch as th
 
-from .. import _lib, flat as _flat
+from .. import _lib, flat as _flat, data_parallel
 from ..modules.mixers.qmix import QMixer
 from ..modules.mixers.vdn import VDNMixer
 
@@ -186,8 +186,7 @@ class QLearner:
         need = self._ensure_workspace(dims, dev)
 
         do_sync = (episode_num - self.last_target_update_episode) / a.target_update_interval >= 1.0
-        dp = th.distributed.is_available() and th.distributed.is_initialized() and th.distributed.get_world_size() > 1 \
-            and getattr(a, "data_parallel", True)
+        dp = data_parallel.is_active() and getattr(a, "data_parallel", True)
         hp = _lib.HParams(a.gamma, a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip, int(do_sync), int(dp), 0)
         L = _lib.lib()
         s = _lib.stream_ptr(dev)
@@ -197,8 +196,7 @@ class QLearner:
                    "pmb_qlearner_train_step")
         if dp:
             # one exchange per step: gradients of sum((td*mask)^2) and the five loss sums
-            th.distributed.all_reduce(f["g"])
-            th.distributed.all_reduce(self._stats[:5])
+            data_parallel.allreduce_step(f["g"], self._stats[:5])
             scratch = self._workspace[:4096 * 4].view(th.float32)
             _lib.check(L.pmb_clip_rmsprop_update(f["layout"].n_total, _lib.ptr(f["p"]), _lib.ptr(f["g"]),
                                                  _lib.ptr(f["sq"]), _lib.ptr(f["target"]), int(do_sync),
