@@ -236,6 +236,7 @@ typedef struct pmb_ws_views {
     float *x_on, *x_tg, *h_stash, *gates, *q_on, *q_tg, *chosen, *tmax, *raw_on, *raw_tg,
           *q_tot, *t_tot, *g, *d_chosen, *scratch;
     int64_t scratch_bytes;
+    float* obs_img;            /* bf16 tier: obs tile images written by the fc1 GEMM */
 } pmb_ws_views;
 int pmb_learner_workspace_views(const pmb_dims* d, void* workspace, int64_t workspace_bytes, pmb_ws_views* out);
 

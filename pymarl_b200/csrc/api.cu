@@ -41,7 +41,8 @@ int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nse
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
                   const float* bias, float* C, int64_t ldc, cudaStream_t s);
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
-                    float* x_on, float* x_tg, int tile_images, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+                    float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, void* scratch,
+                    int64_t scratch_bytes, cudaStream_t s);
 // tc_atb.cu (tile-image D operand)
 int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, const float* A, RowMap amap, int K,
                    float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
@@ -170,7 +171,8 @@ WsPlan plan_workspace(const pmb_dims* d) {
         M * N,                     // 6 chosen
         M * N,                     // 7 tmax
         qmix ? M * C : 0,          // 8 raw (target pass first, then online: one buffer)
-        0,                         // 9 (raw_tg aliases raw)
+        // 9 obs tile images [T][n_tiles][ceil(O/64)][16 KB] written by the fc1 GEMM, read by agent_dw_tc
+        (d->precision == PMB_PREC_BF16 && d->H == 64) ? T * n_tiles * ((d->O + 63) / 64) * ti : 0,
         iql ? 0 : M,               // 10 q_tot
         iql ? 0 : M,               // 11 t_tot
         M * W,                     // 12 g
@@ -193,6 +195,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
         if (g > sc) sc = g;
         int64_t a2 = tc_atb_ti_scratch_bytes(d->T, (int)ceil_div((int64_t)d->B * d->N, 128), d->O);
         if (a2 > sc) sc = a2;
+        if (tc_agent_dw_scratch_bytes() > sc) sc = tc_agent_dw_scratch_bytes();
         if (d->mixer == PMB_MIXER_QMIX) { int64_t m2 = tc_mixer_scratch_bytes(d); if (m2 > sc) sc = m2; }
     }
     if (sc < 4096 * 4) sc = 4096 * 4;
@@ -214,6 +217,7 @@ void fill_views(const pmb_dims* d, void* ws, const WsPlan& p, pmb_ws_views* v) {
     v->d_chosen = iql ? v->g : f(13);
     v->scratch = f(14);
     v->scratch_bytes = p.scratch_bytes;
+    v->obs_img = f(9);
 }
 
 int fc1_fwd(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& ap, float* x_out,
@@ -542,12 +546,16 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         return tc_pack_w(p3, r3, l3, 2, 64, reinterpret_cast<__nv_bfloat16*>(base + 49152), s);
     };
     char* gru_img = reinterpret_cast<char*>(v.scratch);
+    // fc1/fc2 weight gradients as one image-fed GEMM kernel (needs the obs tile images written by fc1)
+    const bool fused_dw = tc_agent && d->O <= 320 && d->N <= 64;
+    uint8_t* obs_ti = reinterpret_cast<uint8_t*>(v.obs_img);
     if (tc_agent) {
         if ((rc = tc_ti_zero_pad(x_on_ti, d->T, n_tiles, R, s))) return rc;
         if ((rc = tc_ti_zero_pad(x_tg_ti, d->T, n_tiles, R, s))) return rc;
         if ((rc = tc_ti_zero_pad(h_ti, d->T + 1, n_tiles, R, s))) return rc;
         PHASE(s, "fc1_fwd_both_tc");
-        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, v.scratch, v.scratch_bytes, s))) return rc;
+        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, fused_dw ? obs_ti : nullptr, v.scratch,
+                                  v.scratch_bytes, s))) return rc;
         PHASE(s, "gru_unroll_fwd_online_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
         if ((rc = pack_gru(tg, gru_img + 57344))) return rc;
@@ -620,13 +628,19 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         char* sc2 = reinterpret_cast<char*>(v.scratch) + 131072;
         if ((rc = tc_gru_dw(g_ti, x_on_ti, h_ti, d->T, n_tiles, gr.w_ih, gr.w_hh, gr.b_ih, gr.b_hh, sc2,
                             v.scratch_bytes - 131072, s))) return rc;
-        PHASE(s, "dW_fc1_tc");
-        RowMap omap{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, d->T, d->N};
-        if ((rc = tc_gemm_atb_ti(x_tg_ti, d->T, d->N, R, n_tiles, b->obs, omap, d->O, gr.fc1_w, d_in_of(d), gr.fc1_b,
-                                 v.scratch, v.scratch_bytes, s))) return rc;
-        PHASE(s, "agent_scatter_grads");
-        if ((rc = scatter_grads_dispatch(d, b, v.h_stash, v.x_tg, v.d_chosen, gr, v.scratch, v.scratch_bytes, s,
-                                         n_tiles))) return rc;
+        if (fused_dw) {
+            PHASE(s, "dW_fc1_fc2_tc");
+            if ((rc = tc_agent_dw(d, b, x_tg_ti, h_ti, obs_ti, v.d_chosen, n_tiles, gr.fc1_w, gr.fc1_b, gr.fc2_w, gr.fc2_b,
+                                  v.scratch, v.scratch_bytes, s))) return rc;
+        } else {
+            PHASE(s, "dW_fc1_tc");
+            RowMap omap{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, d->T, d->N};
+            if ((rc = tc_gemm_atb_ti(x_tg_ti, d->T, d->N, R, n_tiles, b->obs, omap, d->O, gr.fc1_w, d_in_of(d), gr.fc1_b,
+                                     v.scratch, v.scratch_bytes, s))) return rc;
+            PHASE(s, "agent_scatter_grads");
+            if ((rc = scatter_grads_dispatch(d, b, v.h_stash, v.x_tg, v.d_chosen, gr, v.scratch, v.scratch_bytes, s,
+                                             n_tiles))) return rc;
+        }
     } else if ((rc = agent_bwd(d, b, flat_p, v.x_on, v.h_stash, v.gates, v.d_chosen, v.x_tg, flat_g, v.scratch,
                                v.scratch_bytes, s))) return rc;
     // :102-107

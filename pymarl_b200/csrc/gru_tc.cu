@@ -605,6 +605,220 @@ __global__ void gru_dw_reduce_kernel(const float* __restrict__ partial, int n_ct
     else b_hh[i - 2 * 192 * 64 - 192] = s;
 }
 
+// ------------------------------------------------------------------------------------------
+// fc1 / fc2 weight gradients from tile images, one-hot operands generated on the fly.
+//   item = (t, tile, half): 64 rows.  A1 = [dpre1 | Q1], A2 = [P1 | ID] (MN-major, M = 128), where
+//     Q1[row, a]  = dq[row]        if a == action[row]          (-> fc2.weight / fc2.bias)
+//     P1[row, a]  = 1              if a == action[row at t-1] and that step was filled (-> fc1 last-action columns)
+//     ID[row, n]  = 1              if n == agent(row)                                  (-> fc1 agent-id columns)
+//   D_obs = A1 x obs (fc1.weight[:, :O] in rows 0..63), D_h = A1 x h_t (fc2.weight in rows 64..),
+//   D_one = A1 x 1 (fc1.bias | fc2.bias), D_a2 = A2 x dpre1 (last-action | agent-id columns).
+// ------------------------------------------------------------------------------------------
+namespace ad {
+constexpr int HALF = 8192;                                   // 64 rows x 128 B
+constexpr int MAX_CHUNKS = 5;                                // obs width <= 320
+constexpr int STAGE_BYTES = (5 + MAX_CHUNKS) * HALF;         // dpre1 | Q1 | P1 | ID | h_t | obs chunks
+constexpr int ONES = 2 * STAGE_BYTES;
+constexpr int BARS = ONES + HALF;
+constexpr int SMEM_BYTES = 1024 + BARS + 128;
+constexpr int THREADS = 192;
+constexpr int OBS_LD = MAX_CHUNKS * 64;                      // 320
+constexpr int PARTIAL_FLOATS = 64 * OBS_LD + 64 * 64 + 128 + 128 * 64;   // dW1obs | dW2 | (db1|db2) | (dW1act|dW1id)
+}  // namespace ad
+
+struct AgentDwParams {
+    const uint8_t* dpre1_ti; const uint8_t* h_ti; const uint8_t* obs_ti;
+    const float* d_chosen; const int64_t* actions; int64_t actions_sb; const int64_t* filled; int64_t filled_sb;
+    float* partial;
+    int64_t R, n_items, items_per_cta;
+    int T, N, A, n_tiles, n_chunks, use_act, use_id;
+};
+
+__global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwParams P) {
+    using namespace ad;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* full = bars;               // [2]: loader bytes + 2 generator warps
+    uint64_t* empty = bars + 2;          // [2]
+    uint64_t* done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 3); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < HALF / 16; i += THREADS)
+        reinterpret_cast<uint4*>(smem + ONES)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t beg = (int64_t)blockIdx.x * P.items_per_cta;
+    const int64_t end = beg + P.items_per_cta < P.n_items ? beg + P.items_per_cta : P.n_items;
+    const int64_t n_my = end > beg ? end - beg : 0;
+    const int n_obs_cols = P.n_chunks * 64;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int64_t i = 0; i < n_my; ++i) {
+                const int s = (int)(i & 1);
+                const int64_t item = beg + i;
+                const int64_t tt = item >> 1;                  // t * n_tiles + tile
+                const int half = (int)(item & 1);
+                const int64_t t = tt / P.n_tiles, tile = tt - t * P.n_tiles;
+                mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[s], (2 + P.n_chunks) * HALF);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                bulk_copy_g2s(st, P.dpre1_ti + tt * TILE_BYTES + half * HALF, HALF, &full[s]);
+                bulk_copy_g2s(st + 4 * HALF, P.h_ti + ((t + 1) * P.n_tiles + tile) * TILE_BYTES + half * HALF, HALF, &full[s]);
+                for (int c = 0; c < P.n_chunks; ++c)
+                    bulk_copy_g2s(st + (5 + c) * HALF, P.obs_ti + (tt * P.n_chunks + c) * TILE_BYTES + half * HALF, HALF,
+                                  &full[s]);
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0 && n_my > 0) {
+            const int n1 = n_obs_cols > 256 ? 256 : n_obs_cols, n2 = n_obs_cols - n1;
+            const uint32_t id_o1 = umma_idesc_bf16(128, n1, 1, 1), id_o2 = umma_idesc_bf16(128, n2 > 0 ? n2 : 16, 1, 1);
+            const uint32_t id64 = umma_idesc_bf16(128, 64, 1, 1), id16 = umma_idesc_bf16(128, 16, 1, 1);
+            const uint32_t ones = smem_u32(smem + ONES);
+            for (int64_t i = 0; i < n_my; ++i) {
+                const int s = (int)(i & 1);
+                mbar_wait(&full[s], (i >> 1) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {               // 64 rows = 4 x (K = 16)
+                    const uint32_t acc = (i | kk) != 0;
+                    const uint64_t a1 = umma_desc_sw128(st + kk * 2048, HALF, 1024);              // [dpre1 | Q1]
+                    const uint64_t a2 = umma_desc_sw128(st + 2 * HALF + kk * 2048, HALF, 1024);   // [P1 | ID]
+                    umma_bf16(tmem_base, a1, umma_desc_sw128(st + 5 * HALF + kk * 2048, HALF, 1024), id_o1, acc);
+                    if (n2 > 0)
+                        umma_bf16(tmem_base + 256, a1, umma_desc_sw128(st + 9 * HALF + kk * 2048, HALF, 1024), id_o2, acc);
+                    umma_bf16(tmem_base + 320, a1, umma_desc_sw128(st + 4 * HALF + kk * 2048, HALF, 1024), id64, acc);
+                    umma_bf16(tmem_base + 384, a1, umma_desc_sw128(ones + kk * 2048, HALF, 1024), id16, acc);
+                    umma_bf16(tmem_base + 400, a2, umma_desc_sw128(st + kk * 2048, HALF, 1024), id64, acc);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(done);
+        }
+    } else {
+        // ===== warps 0-1: one-hot generators (one row per thread); all four warps: final epilogue =====
+        if (warp < 2) {
+            const int rr = warp * 32 + lane;                   // row within the half tile
+            for (int64_t i = 0; i < n_my; ++i) {
+                const int s = (int)(i & 1);
+                const int64_t item = beg + i;
+                const int64_t tt = item >> 1;
+                const int half = (int)(item & 1);
+                const int64_t t = tt / P.n_tiles, tile = tt - t * P.n_tiles;
+                const int64_t p = tile * TILE_ROWS + half * 64 + rr;
+                int a = -1, ap = -1, n = -1;
+                float dq = 0.f;
+                if (p < P.R) {
+                    const int64_t b = p / P.N;
+                    n = (int)(p - b * P.N);
+                    if (t < P.T - 1) {
+                        dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
+                        a = (int)__ldg(P.actions + b * P.actions_sb + t * P.N + n);
+                    }
+                    if (P.use_act && t > 0 && __ldg(P.filled + b * P.filled_sb + (t - 1)) != 0)
+                        ap = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + n);
+                    if (!P.use_id) n = -1;
+                }
+                const uint32_t dqb = pack_bf16x2(dq, 0.f) & 0xffffu;      // bf16 bits of dq
+                mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = sw128_offset((uint32_t)rr, (uint32_t)j);
+                    uint32_t q[4] = {0, 0, 0, 0}, pp[4] = {0, 0, 0, 0}, id[4] = {0, 0, 0, 0};
+                    if ((a >> 3) == j) q[(a & 7) >> 1] = dqb << (16 * (a & 1));
+                    if ((ap >> 3) == j) pp[(ap & 7) >> 1] = 0x3f80u << (16 * (ap & 1));
+                    if ((n >> 3) == j) id[(n & 7) >> 1] = 0x3f80u << (16 * (n & 1));
+                    *reinterpret_cast<uint4*>(st + 1 * HALF + off) = make_uint4(q[0], q[1], q[2], q[3]);
+                    *reinterpret_cast<uint4*>(st + 2 * HALF + off) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+                    *reinterpret_cast<uint4*>(st + 3 * HALF + off) = make_uint4(id[0], id[1], id[2], id[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        }
+        float* out = P.partial + (int64_t)blockIdx.x * PARTIAL_FLOATS;
+        float* p_obs = out, *p_w2 = out + 64 * OBS_LD, *p_b = p_w2 + 64 * 64, *p_a2 = p_b + 128;
+        const int c = warp * 32 + lane;                        // accumulator row 0..127
+        if (n_my > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int g = 0; g < n_obs_cols; g += 32) {          // D_obs: rows 0..63 = fc1.weight[:, :O]
+                uint32_t v[32];
+                tmem_ld_32x32(tl + g, v);
+                tmem_wait_ld();
+                if (c < 64) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) p_obs[c * OBS_LD + g + j] = __uint_as_float(v[j]);
+                }
+            }
+            for (int g = 0; g < 64; g += 32) {
+                uint32_t v[32], w[32];
+                tmem_ld_32x32(tl + 320 + g, v);                 // D_h: rows 64.. = fc2.weight[a, :]
+                tmem_ld_32x32(tl + 400 + g, w);                 // D_a2: rows 0..63 last-action, 64.. agent-id
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (c >= 64) p_w2[(c - 64) * 64 + g + j] = __uint_as_float(v[j]);
+                    p_a2[c * 64 + g + j] = __uint_as_float(w[j]);
+                }
+            }
+            uint32_t b1[16];
+            tmem_ld_32x16(tl + 384, b1);
+            tmem_wait_ld();
+            p_b[c] = __uint_as_float(b1[0]);
+        } else {
+            for (int i = threadIdx.x; i < PARTIAL_FLOATS; i += 128) out[i] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void agent_dw_reduce_kernel(const float* __restrict__ partial, int n_cta, int O, int A, int N, int D_in,
+                                       int use_act, int use_id, float* __restrict__ fc1_w, float* __restrict__ fc1_b,
+                                       float* __restrict__ fc2_w, float* __restrict__ fc2_b) {
+    using namespace ad;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PARTIAL_FLOATS) return;
+    float s = 0.f;
+    for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * PARTIAL_FLOATS + i];
+    if (i < 64 * OBS_LD) {
+        int j = i / OBS_LD, k = i - j * OBS_LD;
+        if (k < O) fc1_w[(int64_t)j * D_in + k] = s;
+    } else if (i < 64 * OBS_LD + 64 * 64) {
+        int q = i - 64 * OBS_LD, a = q / 64, j = q - a * 64;
+        if (a < A) fc2_w[a * 64 + j] = s;
+    } else if (i < 64 * OBS_LD + 64 * 64 + 128) {
+        int q = i - (64 * OBS_LD + 64 * 64);
+        if (q < 64) fc1_b[q] = s;
+        else if (q - 64 < A) fc2_b[q - 64] = s;
+    } else {
+        int q = i - (64 * OBS_LD + 64 * 64 + 128), r = q / 64, j = q - r * 64;
+        if (r < 64) { if (use_act && r < A) fc1_w[(int64_t)j * D_in + O + r] = s; }
+        else if (use_id && r - 64 < N) fc1_w[(int64_t)j * D_in + O + (use_act ? A : 0) + (r - 64)] = s;
+    }
+}
+
 // zero the padding rows (row >= R) of the last tile of every timestep of a tile-image buffer
 __global__ void ti_zero_pad_kernel(uint8_t* buf, int n_t, int n_tiles, int64_t R) {
     const int pad0 = (int)(R - (int64_t)(n_tiles - 1) * TILE_ROWS);      // first padding row of the last tile
@@ -646,6 +860,30 @@ int tc_gru_dw(const uint8_t* g_ti, const uint8_t* x_ti, const uint8_t* h_ti, int
     tc::gru_dw_reduce_kernel<<<(unsigned)ceil_div(tc::gd::PARTIAL_FLOATS, 256), 256, 0, s>>>(P.partial, grid, w_ih, w_hh, b_ih,
                                                                                             b_hh);
     PMB_LAUNCH_CHECK("gru_dw_reduce_kernel");
+    return PMB_OK;
+}
+
+int64_t tc_agent_dw_scratch_bytes() { return align_up((int64_t)148 * 2 * tc::ad::PARTIAL_FLOATS * 4, 256); }
+
+int tc_agent_dw(const pmb_dims* d, const pmb_batch* b, const uint8_t* dpre1_ti, const uint8_t* h_ti, const uint8_t* obs_ti,
+                const float* d_chosen, int n_tiles, float* fc1_w, float* fc1_b, float* fc2_w, float* fc2_b, void* scratch,
+                int64_t scratch_bytes, cudaStream_t s) {
+    tc::AgentDwParams P;
+    P.dpre1_ti = dpre1_ti; P.h_ti = h_ti; P.obs_ti = obs_ti; P.d_chosen = d_chosen;
+    P.actions = b->actions; P.actions_sb = b->actions_sb; P.filled = b->filled; P.filled_sb = b->filled_sb;
+    P.R = (int64_t)d->B * d->N; P.T = d->T; P.N = d->N; P.A = d->A; P.n_tiles = n_tiles;
+    P.n_chunks = (d->O + 63) / 64; P.use_act = d->obs_last_action; P.use_id = d->obs_agent_id;
+    P.n_items = (int64_t)d->T * n_tiles * 2;
+    int grid = (int)(P.n_items < sm_count() ? P.n_items : sm_count());
+    if ((int64_t)grid * tc::ad::PARTIAL_FLOATS * 4 > scratch_bytes) { set_error("tc_agent_dw: scratch too small"); return PMB_ERR_WORKSPACE; }
+    P.items_per_cta = ceil_div(P.n_items, grid);
+    P.partial = static_cast<float*>(scratch);
+    PMB_CUDA(cudaFuncSetAttribute(tc::agent_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ad::SMEM_BYTES));
+    tc::agent_dw_tc_kernel<<<grid, tc::ad::THREADS, tc::ad::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("agent_dw_tc_kernel");
+    tc::agent_dw_reduce_kernel<<<(unsigned)ceil_div(tc::ad::PARTIAL_FLOATS, 256), 256, 0, s>>>(
+        P.partial, grid, d->O, d->A, d->N, d_in_of(d), d->obs_last_action, d->obs_agent_id, fc1_w, fc1_b, fc2_w, fc2_b);
+    PMB_LAUNCH_CHECK("agent_dw_reduce_kernel");
     return PMB_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/pymarl_b200.h"
 
 namespace pmb {
 namespace tc {
@@ -43,6 +44,10 @@ int tc_gru_bwd(const tc::GruBwdParams& P, cudaStream_t s);
 int64_t tc_gru_dw_scratch_bytes();
 int tc_gru_dw(const uint8_t* g_ti, const uint8_t* x_ti, const uint8_t* h_ti, int T, int n_tiles, float* w_ih, float* w_hh,
               float* b_ih, float* b_hh, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+int64_t tc_agent_dw_scratch_bytes();
+int tc_agent_dw(const pmb_dims* d, const pmb_batch* b, const uint8_t* dpre1_ti, const uint8_t* h_ti, const uint8_t* obs_ti,
+                const float* d_chosen, int n_tiles, float* fc1_w, float* fc1_b, float* fc2_w, float* fc2_b, void* scratch,
+                int64_t scratch_bytes, cudaStream_t s);
 int tc_ti_zero_pad(uint8_t* buf, int n_t, int n_tiles, int64_t R, cudaStream_t s);
 
 }  // namespace pmb

@@ -37,6 +37,12 @@ struct GemmParams {
     int n_chunks;          // ceil(K / 64)
     const __nv_bfloat16* Wp;   // packed tiles: pass-major, then k-chunk; each tile ncols_p rows x 128 B
     int Ncols;             // multiple of 32
+    // time-major tiled row order (tm_R > 0): logical row m = t * tm_Rpad + p, p = b*N + n < tm_R is valid and
+    // maps to batch row (b*tm_T + t)*tm_N + n of amap; rows p >= tm_R are padding.  A 128-row tile then is
+    // exactly one (t, tile) tile image of the bf16 tier.
+    int64_t tm_R, tm_Rpad;
+    int tm_N, tm_T;
+    uint8_t* a_img_out;    // optional: the converted A tiles are also written to global, [tile][k-chunk][16 KB]
 };
 
 __host__ __device__ inline int pass_cols(int Ncols, int p) {
@@ -126,7 +132,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
             const float* myptr = nullptr;
             if (lane < BM / N_PROD_WARPS) {
                 int64_t row = tile * BM + pw + N_PROD_WARPS * lane;
-                if (row < P.M) myptr = P.A + P.amap.offset(row);
+                if (row < P.M) {
+                    if (P.tm_R > 0) {
+                        const int64_t t = row / P.tm_Rpad, pp = row - t * P.tm_Rpad;
+                        if (pp < P.tm_R) {
+                            const int64_t bb = pp / P.tm_N, nn = pp - bb * P.tm_N;
+                            myptr = P.A + P.amap.offset((bb * P.tm_T + t) * P.tm_N + nn);
+                        }
+                    } else {
+                        myptr = P.A + P.amap.offset(row);
+                    }
+                }
             }
             for (int p = 0; p < n_pass; ++p) {
                 for (int c = 0; c < P.n_chunks; ++c, ++it) {
@@ -151,11 +167,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
                         }
                         v0[l] = a; v1[l] = b;
                     }
+                    uint8_t* gimg = (P.a_img_out && p == 0)
+                                        ? P.a_img_out + ((int64_t)tile * P.n_chunks + c) * A_STAGE_BYTES : nullptr;
 #pragma unroll
                     for (int l = 0; l < BM / N_PROD_WARPS; ++l) {
                         const uint32_t r = pw + N_PROD_WARPS * l;
-                        *reinterpret_cast<uint32_t*>(dst + sw128_offset(r, lane >> 2) + (lane & 3) * 4) =
-                            pack_bf16x2(v0[l], v1[l]);
+                        const uint32_t off = sw128_offset(r, lane >> 2) + (lane & 3) * 4;
+                        const uint32_t w = pack_bf16x2(v0[l], v1[l]);
+                        *reinterpret_cast<uint32_t*>(dst + off) = w;
+                        if (gimg) *reinterpret_cast<uint32_t*>(gimg + off) = w;
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -311,23 +331,25 @@ struct Fc1TiEpi {
     const int64_t* filled;  int64_t filled_sb;
     uint8_t* x_on; uint8_t* x_tg;
     int t0, nt, N, A, use_act, n_tiles;
+    int64_t R;
+    // rows arrive in time-major tiled order: m = tl * (n_tiles*128) + p
     __device__ void begin(Row& r, int64_t m, bool valid) const {
-        r.tile_off = 0; r.r = 0; r.n = 0; r.a_prev = -1;
+        r.tile_off = 0; r.r = 0; r.n = 0; r.a_prev = -2;          // -2: padding row (nothing is written)
         if (!valid) return;
-        const int tn = nt * N;
-        int64_t b = m / tn;
-        int rem = (int)(m - b * tn);
-        int tl = rem / N;
-        r.n = rem - tl * N;
-        int t = t0 + tl;
+        const int64_t r_pad = (int64_t)n_tiles * 128;
+        const int64_t tl = m / r_pad, p = m - tl * r_pad;
+        if (p >= R) return;
+        const int64_t b = p / N;
+        r.n = (int)(p - b * N);
+        r.a_prev = -1;
+        const int t = t0 + (int)tl;
         if (use_act && t > 0 && filled[b * filled_sb + (t - 1)] != 0)
             r.a_prev = (int)actions[b * actions_sb + (int64_t)(t - 1) * N + r.n];
-        int64_t p = b * N + r.n;
-        r.tile_off = ((int64_t)tl * n_tiles + (p >> 7)) * 16384;
+        r.tile_off = (tl * n_tiles + (p >> 7)) * 16384;
         r.r = (uint32_t)(p & 127);
     }
     __device__ void cols(Row& r, int64_t, bool valid, int col0, const uint32_t (&v)[32]) const {
-        if (!valid) return;
+        if (!valid || r.a_prev == -2) return;
         const int net = col0 >> 6, h0 = col0 & 63;
         uint8_t* tile = (net ? x_tg : x_on) + r.tile_off;
         const float4* tid = reinterpret_cast<const float4*>(tab_id + ((int64_t)net * N + r.n) * 64 + h0);
@@ -454,7 +476,7 @@ int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nse
 // plain C = A . W^T + bias  (diagnostics / unit test of the tcgen05 pipeline)
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
                   const float* bias, float* C, int64_t ldc, cudaStream_t s) {
-    tc::GemmParams P{A, amap, M, K, (K + tc::BK - 1) / tc::BK, Wp, Ncols_padded};
+    tc::GemmParams P{A, amap, M, K, (K + tc::BK - 1) / tc::BK, Wp, Ncols_padded, 0, 0, 0, 0, nullptr};
     tc::PlainEpi epi{C, ldc, bias, Nreal};
     return tc::launch_tc_gemm(P, epi, s);
 }
@@ -480,7 +502,8 @@ __global__ void fc1_tables_kernel(const float* __restrict__ w_on, const float* _
 }
 
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
-                    float* x_on, float* x_tg, int tile_images, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+                    float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, void* scratch,
+                    int64_t scratch_bytes, cudaStream_t s) {
     // scratch: packed W (128 x Kpad bf16) | tab_act | tab_id
     const int D_in = d_in_of(d);
     int64_t wp_bytes = align_up(tc_packed_elems(128, d->O) * 2, 256);
@@ -501,12 +524,18 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     PMB_LAUNCH_CHECK("fc1_tables_kernel");
     const int64_t M = (int64_t)d->B * nt * d->N;
     RowMap map{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, nt, d->N};
-    tc::GemmParams P{b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, (d->O + tc::BK - 1) / tc::BK, wp, 128};
+    tc::GemmParams P{b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, (d->O + tc::BK - 1) / tc::BK, wp, 128,
+                     0, 0, 0, 0, nullptr};
     if (tile_images) {
-        const int n_tiles = (int)ceil_div((int64_t)d->B * d->N, 128);
+        // rows in time-major tiled order so that GEMM tiles coincide with the (t, tile) tile images
+        const int64_t R = (int64_t)d->B * d->N;
+        const int n_tiles = (int)ceil_div(R, 128);
+        P.M = (int64_t)nt * n_tiles * 128;
+        P.tm_R = R; P.tm_Rpad = (int64_t)n_tiles * 128; P.tm_N = d->N; P.tm_T = nt;
+        P.a_img_out = obs_img_out;
         tc::Fc1TiEpi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb,
                          reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
-                         d->obs_last_action, n_tiles};
+                         d->obs_last_action, n_tiles, R};
         return tc::launch_tc_gemm(P, epi, s);
     }
     tc::Fc1Epi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb, x_on, x_tg,
@@ -550,7 +579,7 @@ int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, c
     PMB_LAUNCH_CHECK("mix_bias_perm_kernel");
     const int64_t M = (int64_t)d->B * (d->T - 1);
     RowMap smap{b->state_sb, (int64_t)S, 0, d->T - 1, 1};
-    tc::GemmParams P{b->state + (int64_t)t_off * S, smap, M, S, (S + tc::BK - 1) / tc::BK, wp, C};
+    tc::GemmParams P{b->state + (int64_t)t_off * S, smap, M, S, (S + tc::BK - 1) / tc::BK, wp, C, 0, 0, 0, 0, nullptr};
     tc::MixEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_out, raw_f32, N};
     return tc::launch_tc_gemm(P, epi, s);
 }

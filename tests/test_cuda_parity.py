@@ -376,6 +376,7 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
     for sq in list(olr.sq_agent.values()) + list(olr.sq_mixer.values()):
         sq[...] = 1e-2
     learner._flat["sq"].fill_(1e-2)
+    p_init = {"agent": {k: v.copy() for k, v in olr.agent.items()}, "mixer": {k: v.copy() for k, v in olr.mixer_p.items()}}
     stats, raw_grads, fw = olr.train(fields, 0, 0)
     learner.train(to_batch(shape, fields), 0, 0)
     # Gradients.  bf16 operand rounding moves near-zero pre-activations across zero, and the step has two
@@ -406,7 +407,17 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
         assert rel_err(ws["q_tot"].cpu().numpy(), fw["q_tot"]) < TOL_BF16
     for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
         assert abs(st[key] - stats[key]) <= 2 * TOL_BF16 * max(1.0, abs(stats[key])), (key, st[key], stats[key])
-    for k, v in olr.agent.items():
-        assert rel_err(state_np(learner.mac.agent)[k], v) < TOL_BF16, k
-    for k, v in olr.mixer_p.items():
-        assert rel_err(state_np(learner.mixer)[k], v) < TOL_BF16, k
+    # Post-update parameters.  RMSprop divides by sqrt(v): an element whose gradient is at the noise level gets a
+    # +-lr/sqrt(1-alpha)-sized step whose SIGN is noise, so comparing parameters against the oracle measures the
+    # optimiser's noise amplification, not the kernels (it fails the same way between the reference's own fp32 and
+    # bf16 autocast runs).  The check is therefore split: gradients vs the oracle (above), and the update arithmetic
+    # exactly, from the kernel's own gradients: p' = p - lr g / (sqrt(alpha v + (1-alpha) g^2) + eps).
+    def expect(p0, gg):
+        v = np.float32(args.optim_alpha) * np.float32(1e-2) + (np.float32(1) - np.float32(args.optim_alpha)) * gg * gg
+        return p0 - np.float32(args.lr) * gg / (np.sqrt(v) + np.float32(args.optim_eps))
+    for kind, mod, init in (("agent", learner.mac.agent, p_init["agent"]), ("mixer", learner.mixer, p_init["mixer"])):
+        if mod is None:
+            continue
+        for name, prm in mod.named_parameters():
+            gg = prm.grad.cpu().numpy()
+            assert rel_err(prm.detach().cpu().numpy(), expect(init[name], gg)) < 1e-5, (kind, name)
