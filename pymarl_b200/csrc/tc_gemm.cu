@@ -43,6 +43,7 @@ struct GemmParams {
     int64_t tm_R, tm_Rpad;
     int tm_N, tm_T;
     uint8_t* a_img_out;    // optional: the converted A tiles are also written to global, [tile][k-chunk][16 KB]
+    const uint8_t* a_img;  // optional: A is already bf16 tile images [tile][k-chunk][16 KB] -> bulk copied, no producers
 };
 
 __host__ __device__ inline int pass_cols(int Ncols, int p) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], N_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], P.a_img ? 1 : N_PROD_WARPS + 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], N_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -124,9 +125,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
     const int n_pass = (P.Ncols + BN_MAX - 1) / BN_MAX;
 
     if (warp >= FIRST_PROD_WARP) {
-        // ===== A producers: fp32 global -> bf16 swizzled smem =====
+        // ===== A producers: fp32 global -> bf16 swizzled smem (idle when A comes as tile images) =====
         const int pw = warp - FIRST_PROD_WARP;
         uint32_t it = 0;
+        if (P.a_img == nullptr)
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // lane l (< 16) keeps the pointer of tile row (pw + 8 l)
             const float* myptr = nullptr;
@@ -193,9 +195,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
                     for (int c = 0; c < P.n_chunks; ++c, ++it) {
                         const int s = it % STAGES;
                         mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&full[s], bytes);
+                        mbar_arrive_expect_tx(&full[s], bytes + (P.a_img ? A_STAGE_BYTES : 0));
                         bulk_copy_g2s(w_stage + s * W_STAGE_BYTES, P.Wp + packed_tile_offset(P.Ncols, P.n_chunks, p, c),
                                       bytes, &full[s]);
+                        if (P.a_img)
+                            bulk_copy_g2s(a_stage + s * A_STAGE_BYTES, P.a_img + ((int64_t)tile * P.n_chunks + c) * A_STAGE_BYTES,
+                                          A_STAGE_BYTES, &full[s]);
                     }
                 }
         }
@@ -432,6 +437,65 @@ struct MixEpi {
     }
 };
 
+// Mixer epilogue for the image-fed path: GEMM rows are ALL (b, t) pairs, m' = b*T + t.  The online mixer
+// (t_off = 0) uses rows t < T-1, the target mixer (t_off = 1) rows t >= 1; agent_qs / q_tot are indexed by
+// mq = b*(T-1) + t - t_off.  raw_img (online only): hypernet outputs as bf16 tile images
+// [row tile][(N+3)/2 column blocks of 64][16 KB], packed column order, kept for the backward.
+struct MixImgEpi {
+    struct Row { float hidden[32]; float y; int64_t mq; uint8_t* img; uint32_t r; };
+    const float* bias; const float* agent_qs; const float* v2_w; const float* v2_b;
+    float* q_tot; uint8_t* raw_img;
+    int N, T, t_off, n_cblk;
+    int64_t BT;
+    __device__ void begin(Row& r, int64_t m, bool) const {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r.hidden[e] = 0.f;
+        r.y = 0.f; r.mq = -1;
+        r.img = raw_img ? raw_img + (m >> 7) * (int64_t)n_cblk * 16384 : nullptr;
+        r.r = (uint32_t)(m & 127);
+        if (m < BT) {
+            const int64_t b = m / T;
+            const int t = (int)(m - b * T);
+            if (t_off == 0 ? (t < T - 1) : (t >= 1)) r.mq = b * (T - 1) + t - t_off;
+        }
+    }
+    __device__ void cols(Row& r, int64_t, bool, int col0, const uint32_t (&v)[32]) const {
+        const int grp = col0 >> 5;
+        float raw[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) raw[e] = __uint_as_float(v[e]) + __ldg(bias + col0 + e);
+        if (r.img) {                                   // every row is written (finite values; the backward zeroes unused rows)
+            uint8_t* blk = r.img + (int64_t)(col0 >> 6) * 16384;
+            const uint32_t ch0 = (uint32_t)((col0 & 63) >> 3);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(blk + sw128_offset(r.r, ch0 + q)) =
+                    make_uint4(pack_bf16x2(raw[8 * q], raw[8 * q + 1]), pack_bf16x2(raw[8 * q + 2], raw[8 * q + 3]),
+                               pack_bf16x2(raw[8 * q + 4], raw[8 * q + 5]), pack_bf16x2(raw[8 * q + 6], raw[8 * q + 7]));
+        }
+        if (grp < N) {
+            const float qn = r.mq >= 0 ? __ldg(agent_qs + r.mq * N + grp) : 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r.hidden[e] = fmaf(qn, fabsf(raw[e]), r.hidden[e]);
+        } else if (grp == N) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                float pre = r.hidden[e] + raw[e];
+                r.hidden[e] = pre > 0.f ? pre : expm1f(pre);
+            }
+        } else if (grp == N + 1) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r.y = fmaf(r.hidden[e], fabsf(raw[e]), r.y);
+        } else if (grp == N + 2) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r.y = fmaf(fmaxf(raw[e], 0.f), __ldg(v2_w + e), r.y);
+        }
+    }
+    __device__ void end(Row& r, int64_t, bool) const {
+        if (r.mq >= 0) q_tot[r.mq] = r.y + __ldg(v2_b);
+    }
+};
+
 template <class Epi>
 int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
     if (P.M <= 0) return PMB_OK;
@@ -476,7 +540,7 @@ int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nse
 // plain C = A . W^T + bias  (diagnostics / unit test of the tcgen05 pipeline)
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
                   const float* bias, float* C, int64_t ldc, cudaStream_t s) {
-    tc::GemmParams P{A, amap, M, K, (K + tc::BK - 1) / tc::BK, Wp, Ncols_padded, 0, 0, 0, 0, nullptr};
+    tc::GemmParams P{A, amap, M, K, (K + tc::BK - 1) / tc::BK, Wp, Ncols_padded, 0, 0, 0, 0, nullptr, nullptr};
     tc::PlainEpi epi{C, ldc, bias, Nreal};
     return tc::launch_tc_gemm(P, epi, s);
 }
@@ -525,7 +589,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     const int64_t M = (int64_t)d->B * nt * d->N;
     RowMap map{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, nt, d->N};
     tc::GemmParams P{b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, (d->O + tc::BK - 1) / tc::BK, wp, 128,
-                     0, 0, 0, 0, nullptr};
+                     0, 0, 0, 0, nullptr, nullptr};
     if (tile_images) {
         // rows in time-major tiled order so that GEMM tiles coincide with the (t, tile) tile images
         const int64_t R = (int64_t)d->B * d->N;
@@ -579,8 +643,69 @@ int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, c
     PMB_LAUNCH_CHECK("mix_bias_perm_kernel");
     const int64_t M = (int64_t)d->B * (d->T - 1);
     RowMap smap{b->state_sb, (int64_t)S, 0, d->T - 1, 1};
-    tc::GemmParams P{b->state + (int64_t)t_off * S, smap, M, S, (S + tc::BK - 1) / tc::BK, wp, C, 0, 0, 0, 0, nullptr};
+    tc::GemmParams P{b->state + (int64_t)t_off * S, smap, M, S, (S + tc::BK - 1) / tc::BK, wp, C, 0, 0, 0, 0, nullptr, nullptr};
     tc::MixEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_out, raw_f32, N};
+    return tc::launch_tc_gemm(P, epi, s);
+}
+
+// ---- image-fed mixer path -------------------------------------------------------------------------
+// state [B, T, S] fp32 -> bf16 tile images [ceil(B*T/128)][ceil(S/64)][16 KB] over ALL (b, t) rows (zero padded)
+__global__ void __launch_bounds__(256)
+state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, int64_t BT, int T, int S, int n_chunks,
+                       uint8_t* __restrict__ img) {
+    // one thread per 16-byte chunk
+    const int64_t total = ((BT + 127) / 128) * 128 * (int64_t)n_chunks * 8;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = (int)(i & 7);
+    int64_t q = i >> 3;
+    const int r = (int)(q & 127);
+    q >>= 7;
+    const int c = (int)(q % n_chunks);
+    const int64_t tile = q / n_chunks;
+    const int64_t m = tile * 128 + r;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (m < BT) {
+        const int64_t b = m / T;
+        const int t = (int)(m - b * T);
+        const float* src = state + b * state_sb + (int64_t)t * S + c * 64 + j * 8;
+        const int nv = S - (c * 64 + j * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (e < nv) f[e] = __ldg(src + e);
+    }
+    *reinterpret_cast<uint4*>(img + (tile * n_chunks + c) * 16384 + tc::sw128_offset((uint32_t)r, (uint32_t)j)) =
+        make_uint4(tc::pack_bf16x2(f[0], f[1]), tc::pack_bf16x2(f[2], f[3]), tc::pack_bf16x2(f[4], f[5]),
+                   tc::pack_bf16x2(f[6], f[7]));
+}
+
+int tc_state_to_images(const pmb_dims* d, const pmb_batch* b, uint8_t* img, cudaStream_t s) {
+    const int64_t BT = (int64_t)d->B * d->T;
+    const int n_chunks = (d->S + 63) / 64;
+    const int64_t total = ((BT + 127) / 128) * 128 * (int64_t)n_chunks * 8;
+    state_to_images_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(b->state, b->state_sb, BT, d->T, d->S, n_chunks, img);
+    PMB_LAUNCH_CHECK("state_to_images_kernel");
+    return PMB_OK;
+}
+
+// QMIX forward from state images; raw_img != null keeps the hypernet outputs (online mixer)
+int tc_mixer_fwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* state_img, const float* agent_qs, int t_off,
+                     uint8_t* raw_img, float* q_tot, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+    const int N = d->N, S = d->S, C = (N + 3) * 32;
+    if (scratch_bytes < tc_mixer_scratch_bytes(d)) { set_error("tc_mixer: scratch too small"); return PMB_ERR_WORKSPACE; }
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
+    float* bias = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(tc_packed_elems(C, S) * 2, 256));
+    const float* ptrs[4] = {mp.w_cat, mp.w_cat + (int64_t)(N + 1) * 32 * S, mp.w_cat + (int64_t)N * 32 * S,
+                            mp.w_cat + (int64_t)(N + 2) * 32 * S};
+    int rows[4] = {N * 32, 32, 32, 32}, lds[4] = {S, S, S, S};
+    int rc = tc_pack_w(ptrs, rows, lds, 4, S, wp, s);
+    if (rc) return rc;
+    mix_bias_perm_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, s>>>(mp.b_cat, N, bias);
+    PMB_LAUNCH_CHECK("mix_bias_perm_kernel");
+    const int64_t BT = (int64_t)d->B * d->T;
+    tc::GemmParams P{nullptr, dense_map(0), ((BT + 127) / 128) * 128, S, (S + tc::BK - 1) / tc::BK, wp, C,
+                     0, 0, 0, 0, nullptr, state_img};
+    tc::MixImgEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_img, N, d->T, t_off, (N + 4) / 2, BT};
     return tc::launch_tc_gemm(P, epi, s);
 }
 

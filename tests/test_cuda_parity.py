@@ -409,8 +409,7 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
         assert abs(st[key] - stats[key]) <= 2 * TOL_BF16 * max(1.0, abs(stats[key])), (key, st[key], stats[key])
     # Post-update parameters.  RMSprop divides by sqrt(v): an element whose gradient is at the noise level gets a
     # +-lr/sqrt(1-alpha)-sized step whose SIGN is noise, so comparing parameters against the oracle measures the
-    # optimiser's noise amplification, not the kernels (it fails the same way between the reference's own fp32 and
-    # bf16 autocast runs).  The check is therefore split: gradients vs the oracle (above), and the update arithmetic
+    # optimiser's noise amplification, not the kernels.  The check is therefore split: gradients vs the oracle (above), and the update arithmetic
     # exactly, from the kernel's own gradients: p' = p - lr g / (sqrt(alpha v + (1-alpha) g^2) + eps).
     def expect(p0, gg):
         v = np.float32(args.optim_alpha) * np.float32(1e-2) + (np.float32(1) - np.float32(args.optim_alpha)) * gg * gg
