@@ -237,6 +237,7 @@ typedef struct pmb_ws_views {
           *q_tot, *t_tot, *g, *d_chosen, *scratch;
     int64_t scratch_bytes;
     float* obs_img;            /* bf16 tier: obs tile images written by the fc1 GEMM */
+    float* state_img;          /* bf16 tier: state tile images shared by both mixers and the hypernet weight gradients */
 } pmb_ws_views;
 int pmb_learner_workspace_views(const pmb_dims* d, void* workspace, int64_t workspace_bytes, pmb_ws_views* out);
 

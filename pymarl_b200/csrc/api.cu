@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "gru_tc.cuh"
+#include "mixer_tc.cuh"
 
 namespace pmb {
 
@@ -35,9 +36,6 @@ int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target,
                         float alpha, float eps, float clip, float* scratch, cudaStream_t s);
 
 // tc_gemm.cu (bf16 tcgen05 tier)
-int64_t tc_packed_elems(int Ncols, int K);
-int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nseg, int K, __nv_bfloat16* out,
-              cudaStream_t s);
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
                   const float* bias, float* C, int64_t ldc, cudaStream_t s);
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
@@ -48,7 +46,6 @@ int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, co
                    float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
 int64_t tc_atb_ti_scratch_bytes(int T, int n_tiles, int K);
 int64_t tc_fc1_scratch_bytes(const pmb_dims* d);
-int64_t tc_mixer_scratch_bytes(const pmb_dims* d);
 int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
                  __nv_bfloat16* raw_out, float* raw_f32, float* q_tot, void* scratch, int64_t scratch_bytes,
                  cudaStream_t s);
@@ -138,7 +135,7 @@ void compute_layout(const pmb_dims* d, pmb_layout* L) {
 namespace {
 
 struct WsPlan {
-    int64_t off[15];
+    int64_t off[16];
     int64_t scratch_bytes;
     int64_t total;
 };
@@ -161,7 +158,8 @@ WsPlan plan_workspace(const pmb_dims* d) {
     // the bf16 tier stores x / h / gates as bf16 tile images (128-row tiles, 16 KB each); take the larger size
     const int64_t n_tiles = ceil_div(R, 128), ti = d->precision == PMB_PREC_BF16 ? 4096 : 0;   // floats per tile
     auto mx = [](int64_t a, int64_t b) { return a > b ? a : b; };
-    int64_t sizes[15] = {
+    const bool tc_mix = qmix && d->precision == PMB_PREC_BF16 && d->E == 32;
+    int64_t sizes[16] = {
         mx(T * R * H, T * n_tiles * ti),               // 0 x_on
         mx(T * R * H, T * n_tiles * ti),               // 1 x_tg (reused as dpre1 in the backward)
         mx((T + 1) * R * H, (T + 1) * n_tiles * ti),   // 2 h_stash
@@ -170,18 +168,20 @@ WsPlan plan_workspace(const pmb_dims* d) {
         T * R * A,                 // 5 q_tg
         M * N,                     // 6 chosen
         M * N,                     // 7 tmax
-        qmix ? M * C : 0,          // 8 raw (target pass first, then online: one buffer)
+        // 8 raw: hypernet outputs of the online mixer (bf16 tier: tile images, see mixer_tc.cuh)
+        qmix ? (tc_mix ? tc_raw_img_bytes(d) / 4 : M * C) : 0,
         // 9 obs tile images [T][n_tiles][ceil(O/64)][16 KB] written by the fc1 GEMM, read by agent_dw_tc
         (d->precision == PMB_PREC_BF16 && d->H == 64) ? T * n_tiles * ((d->O + 63) / 64) * ti : 0,
         iql ? 0 : M,               // 10 q_tot
         iql ? 0 : M,               // 11 t_tot
         M * W,                     // 12 g
         iql ? 0 : M * N,           // 13 d_chosen
-        0                          // 14 scratch (bytes, below)
+        tc_mix ? tc_state_img_bytes(d) / 4 : 0,   // 14 state tile images (bf16 tier)
+        0                          // 15 scratch (bytes, below)
     };
     WsPlan p;
     int64_t off = 0;
-    for (int i = 0; i < 14; ++i) {
+    for (int i = 0; i < 15; ++i) {
         p.off[i] = off;
         off += align_up(sizes[i] * 4, 256);
     }
@@ -196,10 +196,13 @@ WsPlan plan_workspace(const pmb_dims* d) {
         int64_t a2 = tc_atb_ti_scratch_bytes(d->T, (int)ceil_div((int64_t)d->B * d->N, 128), d->O);
         if (a2 > sc) sc = a2;
         if (tc_agent_dw_scratch_bytes() > sc) sc = tc_agent_dw_scratch_bytes();
-        if (d->mixer == PMB_MIXER_QMIX) { int64_t m2 = tc_mixer_scratch_bytes(d); if (m2 > sc) sc = m2; }
+        if (tc_mix) {
+            int64_t m2 = tc_mixer_scratch_bytes(d); if (m2 > sc) sc = m2;
+            int64_t m3 = tc_mixer_bwd_img_scratch_bytes(d); if (m3 > sc) sc = m3;
+        }
     }
     if (sc < 4096 * 4) sc = 4096 * 4;
-    p.off[14] = off;
+    p.off[15] = off;
     p.scratch_bytes = align_up(sc, 256);
     p.total = off + p.scratch_bytes;
     return p;
@@ -215,7 +218,8 @@ void fill_views(const pmb_dims* d, void* ws, const WsPlan& p, pmb_ws_views* v) {
     v->t_tot = iql ? v->tmax : f(11);
     v->g = f(12);
     v->d_chosen = iql ? v->g : f(13);
-    v->scratch = f(14);
+    v->scratch = f(15);
+    v->state_img = f(14);
     v->scratch_bytes = p.scratch_bytes;
     v->obs_img = f(9);
 }
@@ -590,13 +594,17 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     PHASE(s, "target_select");
     if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
     // :81-83 (target mixer first: both passes share the raw buffer, the online one must survive)
+    uint8_t* state_img = reinterpret_cast<uint8_t*>(v.state_img);
+    uint8_t* raw_img = reinterpret_cast<uint8_t*>(v.raw_on);
     if (tc_mixer) {
+        PHASE(s, "state_to_images");
+        if ((rc = tc_state_to_images(d, b, state_img, s))) return rc;
         PHASE(s, "mixer_fwd_target_tc");
-        if ((rc = tc_mixer_fwd(d, b, mixer_params(d, flat_target + L.n_agent), v.tmax, 1, nullptr, nullptr, v.t_tot,
-                               v.scratch, v.scratch_bytes, s))) return rc;
+        if ((rc = tc_mixer_fwd_img(d, mixer_params(d, flat_target + L.n_agent), state_img, v.tmax, 1, nullptr, v.t_tot,
+                                   v.scratch, v.scratch_bytes, s))) return rc;
         PHASE(s, "mixer_fwd_online_tc");
-        if ((rc = tc_mixer_fwd(d, b, mixer_params(d, flat_p + L.n_agent), v.chosen, 0, nullptr, v.raw_on, v.q_tot,
-                               v.scratch, v.scratch_bytes, s))) return rc;
+        if ((rc = tc_mixer_fwd_img(d, mixer_params(d, flat_p + L.n_agent), state_img, v.chosen, 0, raw_img, v.q_tot,
+                                   v.scratch, v.scratch_bytes, s))) return rc;
     } else if (d->mixer != PMB_MIXER_NONE) {
         PHASE(s, "mixer_fwd_target");
         if ((rc = launch_mixer_fwd(d, b, flat_target + L.n_agent, v.tmax, 1, v.raw_tg, v.t_tot, s))) return rc;
@@ -608,7 +616,12 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     if ((rc = launch_td_loss(d, b, v.q_tot, v.t_tot, hp->gamma, v.g, stats, s))) return rc;
     // :100-101 backward
     PHASE(s, "mixer_bwd");
-    if (d->mixer != PMB_MIXER_NONE) {
+    if (tc_mixer) {
+        if ((rc = tc_mixer_bwd_img(d, mixer_params(d, flat_p + L.n_agent), state_img, raw_img, v.chosen, v.g, v.d_chosen,
+                                   flat_g + L.offset[PMB_P_HW1_W], flat_g + L.offset[PMB_P_HW1_B],
+                                   flat_g + L.offset[PMB_P_V2_W], flat_g + L.offset[PMB_P_V2_B], v.scratch, v.scratch_bytes,
+                                   s))) return rc;
+    } else if (d->mixer != PMB_MIXER_NONE) {
         if ((rc = launch_mixer_bwd(d, b, flat_p + L.n_agent, v.chosen, v.raw_on, v.g, v.d_chosen, flat_g + L.n_agent,
                                    v.scratch, v.scratch_bytes, s))) return rc;
     }

@@ -15,6 +15,7 @@
 // Persistent over 128-row tiles: grid = min(#tiles, #SMs).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "mixer_tc.cuh"
 
 namespace pmb {
 namespace tc {
@@ -519,7 +520,7 @@ int64_t tc_packed_elems(int Ncols, int K) {
 }
 
 int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nseg, int K, __nv_bfloat16* out,
-              cudaStream_t s) {
+              cudaStream_t s, int n_chunks_min) {
     tc::PackSegs segs;
     int Ncols = 0;
     segs.nseg = nseg;
@@ -531,6 +532,7 @@ int tc_pack_w(const float* const* ptrs, const int* rows, const int* lds, int nse
     }
     Ncols = (int)align_up(Ncols, 32);
     int n_chunks = (K + tc::BK - 1) / tc::BK;
+    if (n_chunks < n_chunks_min) n_chunks = n_chunks_min;      // extra all-zero k-chunks (A images may be wider than K)
     int64_t total = (int64_t)Ncols * n_chunks * 8;
     tc::pack_w_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(segs, K, n_chunks, Ncols, out);
     PMB_LAUNCH_CHECK("pack_w_kernel");
@@ -623,7 +625,7 @@ __global__ void mix_bias_perm_kernel(const float* __restrict__ b_cat, int N, flo
 
 int64_t tc_mixer_scratch_bytes(const pmb_dims* d) {
     const int C = (d->N + 3) * 32;
-    return align_up(tc_packed_elems((int)align_up(C, 32), d->S) * 2, 256) + align_up((int64_t)C * 4, 256);
+    return align_up(tc_packed_elems((int)align_up(C, 32), d->S + 1) * 2, 256) + align_up((int64_t)C * 4, 256);
 }
 
 int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
@@ -649,7 +651,9 @@ int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, c
 }
 
 // ---- image-fed mixer path -------------------------------------------------------------------------
-// state [B, T, S] fp32 -> bf16 tile images [ceil(B*T/128)][ceil(S/64)][16 KB] over ALL (b, t) rows (zero padded)
+// state [B, T, S] fp32 -> bf16 tile images [ceil(B*T/128)][ceil((S+1)/64)][16 KB] over ALL (b, t) rows, m' = b*T + t.
+// Column S of every real row holds 1.0 (the bias-gradient column of the hypernet weight-gradient GEMM; the packed
+// forward weights are zero there), everything else beyond S and all padding rows are zero.
 __global__ void __launch_bounds__(256)
 state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, int64_t BT, int T, int S, int n_chunks,
                        uint8_t* __restrict__ img) {
@@ -671,8 +675,10 @@ state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, int64_
         const float* src = state + b * state_sb + (int64_t)t * S + c * 64 + j * 8;
         const int nv = S - (c * 64 + j * 8);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < 8; ++e) {
             if (e < nv) f[e] = __ldg(src + e);
+            else if (e == nv) f[e] = 1.0f;
+        }
     }
     *reinterpret_cast<uint4*>(img + (tile * n_chunks + c) * 16384 + tc::sw128_offset((uint32_t)r, (uint32_t)j)) =
         make_uint4(tc::pack_bf16x2(f[0], f[1]), tc::pack_bf16x2(f[2], f[3]), tc::pack_bf16x2(f[4], f[5]),
@@ -681,7 +687,7 @@ state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, int64_
 
 int tc_state_to_images(const pmb_dims* d, const pmb_batch* b, uint8_t* img, cudaStream_t s) {
     const int64_t BT = (int64_t)d->B * d->T;
-    const int n_chunks = (d->S + 63) / 64;
+    const int n_chunks = tc_state_chunks(d);
     const int64_t total = ((BT + 127) / 128) * 128 * (int64_t)n_chunks * 8;
     state_to_images_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(b->state, b->state_sb, BT, d->T, d->S, n_chunks, img);
     PMB_LAUNCH_CHECK("state_to_images_kernel");
@@ -692,20 +698,21 @@ int tc_state_to_images(const pmb_dims* d, const pmb_batch* b, uint8_t* img, cuda
 int tc_mixer_fwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* state_img, const float* agent_qs, int t_off,
                      uint8_t* raw_img, float* q_tot, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
     const int N = d->N, S = d->S, C = (N + 3) * 32;
+    const int n_chunks = tc_state_chunks(d);
     if (scratch_bytes < tc_mixer_scratch_bytes(d)) { set_error("tc_mixer: scratch too small"); return PMB_ERR_WORKSPACE; }
     __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
-    float* bias = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(tc_packed_elems(C, S) * 2, 256));
+    float* bias = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(tc_packed_elems(C, S + 1) * 2, 256));
     const float* ptrs[4] = {mp.w_cat, mp.w_cat + (int64_t)(N + 1) * 32 * S, mp.w_cat + (int64_t)N * 32 * S,
                             mp.w_cat + (int64_t)(N + 2) * 32 * S};
     int rows[4] = {N * 32, 32, 32, 32}, lds[4] = {S, S, S, S};
-    int rc = tc_pack_w(ptrs, rows, lds, 4, S, wp, s);
+    int rc = tc_pack_w(ptrs, rows, lds, 4, S, wp, s, n_chunks);
     if (rc) return rc;
     mix_bias_perm_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, s>>>(mp.b_cat, N, bias);
     PMB_LAUNCH_CHECK("mix_bias_perm_kernel");
     const int64_t BT = (int64_t)d->B * d->T;
-    tc::GemmParams P{nullptr, dense_map(0), ((BT + 127) / 128) * 128, S, (S + tc::BK - 1) / tc::BK, wp, C,
+    tc::GemmParams P{nullptr, dense_map(0), ((BT + 127) / 128) * 128, n_chunks * 64, n_chunks, wp, C,
                      0, 0, 0, 0, nullptr, state_img};
-    tc::MixImgEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_img, N, d->T, t_off, (N + 4) / 2, BT};
+    tc::MixImgEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_img, N, d->T, t_off, tc_mix_cblks(d), BT};
     return tc::launch_tc_gemm(P, epi, s);
 }
 
