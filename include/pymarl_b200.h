@@ -96,7 +96,7 @@ typedef struct pmb_hparams {
     float gamma, lr, alpha, eps, grad_norm_clip;
     int32_t do_target_sync;          /* host decides: (episode_num - last)/interval >= 1  */
     int32_t skip_update;             /* 1: stop after the gradients (multi-GPU: all-reduce, then pmb_clip_rmsprop_update) */
-    int32_t reserved;
+    int32_t keep_q;                  /* bf16 tier: 1 = also write the Q tensors (mac_out) into the workspace (tests) */
 } pmb_hparams;
 
 /* stats buffer: 16 doubles on the device, written by the step */
@@ -238,6 +238,7 @@ typedef struct pmb_ws_views {
     int64_t scratch_bytes;
     float* obs_img;            /* bf16 tier: obs tile images written by the fc1 GEMM */
     float* state_img;          /* bf16 tier: state tile images shared by both mixers and the hypernet weight gradients */
+    float* h_tg;               /* bf16 tier: h tile images of the target net */
 } pmb_ws_views;
 int pmb_learner_workspace_views(const pmb_dims* d, void* workspace, int64_t workspace_bytes, pmb_ws_views* out);
 

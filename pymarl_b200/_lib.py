@@ -49,14 +49,14 @@ class Layout(C.Structure):
 class HParams(C.Structure):
     _fields_ = [("gamma", C.c_float), ("lr", C.c_float), ("alpha", C.c_float), ("eps", C.c_float),
                 ("grad_norm_clip", C.c_float), ("do_target_sync", C.c_int32), ("skip_update", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("keep_q", C.c_int32)]
 
 
 class WsViews(C.Structure):
     _names = ("x_on", "x_tg", "h_stash", "gates", "q_on", "q_tg", "chosen", "tmax", "raw_on", "raw_tg",
               "q_tot", "t_tot", "g", "d_chosen", "scratch")
     _fields_ = [(k, C.c_void_p) for k in _names] + [("scratch_bytes", C.c_int64), ("obs_img", C.c_void_p),
-                                                        ("state_img", C.c_void_p)]
+                                                        ("state_img", C.c_void_p), ("h_tg", C.c_void_p)]
 
 
 class PmbError(RuntimeError):

@@ -135,7 +135,7 @@ void compute_layout(const pmb_dims* d, pmb_layout* L) {
 namespace {
 
 struct WsPlan {
-    int64_t off[16];
+    int64_t off[17];
     int64_t scratch_bytes;
     int64_t total;
 };
@@ -159,7 +159,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
     const int64_t n_tiles = ceil_div(R, 128), ti = d->precision == PMB_PREC_BF16 ? 4096 : 0;   // floats per tile
     auto mx = [](int64_t a, int64_t b) { return a > b ? a : b; };
     const bool tc_mix = qmix && d->precision == PMB_PREC_BF16 && d->E == 32;
-    int64_t sizes[16] = {
+    int64_t sizes[17] = {
         mx(T * R * H, T * n_tiles * ti),               // 0 x_on
         mx(T * R * H, T * n_tiles * ti),               // 1 x_tg (reused as dpre1 in the backward)
         mx((T + 1) * R * H, (T + 1) * n_tiles * ti),   // 2 h_stash
@@ -177,11 +177,13 @@ WsPlan plan_workspace(const pmb_dims* d) {
         M * W,                     // 12 g
         iql ? 0 : M * N,           // 13 d_chosen
         tc_mix ? tc_state_img_bytes(d) / 4 : 0,   // 14 state tile images (bf16 tier)
-        0                          // 15 scratch (bytes, below)
+        // 15 h images of the TARGET net (bf16 tier: q = fc2(h) is computed from the images by q_select)
+        (d->precision == PMB_PREC_BF16 && d->H == 64) ? (T + 1) * n_tiles * ti : 0,
+        0                          // 16 scratch (bytes, below)
     };
     WsPlan p;
     int64_t off = 0;
-    for (int i = 0; i < 15; ++i) {
+    for (int i = 0; i < 16; ++i) {
         p.off[i] = off;
         off += align_up(sizes[i] * 4, 256);
     }
@@ -202,7 +204,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
         }
     }
     if (sc < 4096 * 4) sc = 4096 * 4;
-    p.off[15] = off;
+    p.off[16] = off;
     p.scratch_bytes = align_up(sc, 256);
     p.total = off + p.scratch_bytes;
     return p;
@@ -218,8 +220,9 @@ void fill_views(const pmb_dims* d, void* ws, const WsPlan& p, pmb_ws_views* v) {
     v->t_tot = iql ? v->tmax : f(11);
     v->g = f(12);
     v->d_chosen = iql ? v->g : f(13);
-    v->scratch = f(15);
+    v->scratch = f(16);
     v->state_img = f(14);
+    v->h_tg = f(15);
     v->scratch_bytes = p.scratch_bytes;
     v->obs_img = f(9);
 }
@@ -540,6 +543,7 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     const int n_tiles = (int)ceil_div(R, 128);
     uint8_t *x_on_ti = reinterpret_cast<uint8_t*>(v.x_on), *x_tg_ti = reinterpret_cast<uint8_t*>(v.x_tg);
     uint8_t *h_ti = reinterpret_cast<uint8_t*>(v.h_stash), *g_ti = reinterpret_cast<uint8_t*>(v.gates);
+    uint8_t* hg_ti = reinterpret_cast<uint8_t*>(v.h_tg);
     // GRU weight images live at the start of the scratch area: [online: w_ih | w_hh | w2][target: same]
     auto pack_gru = [&](const AgentParams& ap, char* base) -> int {
         const float* p1[1] = {ap.w_ih}; const float* p2[1] = {ap.w_hh}; const float* p3[2] = {ap.fc2_w, nullptr};
@@ -556,28 +560,21 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     if (tc_agent) {
         if ((rc = tc_ti_zero_pad(x_on_ti, d->T, n_tiles, R, s))) return rc;
         if ((rc = tc_ti_zero_pad(x_tg_ti, d->T, n_tiles, R, s))) return rc;
-        if ((rc = tc_ti_zero_pad(h_ti, d->T + 1, n_tiles, R, s))) return rc;
         PHASE(s, "fc1_fwd_both_tc");
         if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, fused_dw ? obs_ti : nullptr, v.scratch,
                                   v.scratch_bytes, s))) return rc;
         PHASE(s, "gru_unroll_fwd_online_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
         if ((rc = pack_gru(tg, gru_img + 57344))) return rc;
-        tc::GruFwdParams fp;
-        fp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img);
-        fp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576);
-        fp.w2_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 49152);
-        fp.b_ih = on.b_ih; fp.b_hh = on.b_hh; fp.b2 = on.fc2_b;
-        fp.x_ti = x_on_ti; fp.h0 = nullptr; fp.h_ti = h_ti; fp.g_ti = g_ti; fp.q = v.q_on; fp.h_last = nullptr;
-        fp.R = R; fp.nt = d->T; fp.A = d->A; fp.n_tiles = n_tiles;
-        if ((rc = tc_gru_fwd(fp, s))) return rc;
+        auto img = [&](int64_t off) { return reinterpret_cast<const __nv_bfloat16*>(gru_img + off); };
+        if ((rc = tc_gru_fwd2(img(0), img(24576), on.b_ih, on.b_hh, x_on_ti, h_ti, g_ti, R, d->T, n_tiles, s))) return rc;
         PHASE(s, "gru_unroll_fwd_target_tc");
-        fp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 57344);
-        fp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 57344 + 24576);
-        fp.w2_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 57344 + 49152);
-        fp.b_ih = tg.b_ih; fp.b_hh = tg.b_hh; fp.b2 = tg.fc2_b;
-        fp.x_ti = x_tg_ti; fp.h_ti = nullptr; fp.g_ti = nullptr; fp.q = v.q_tg;
-        if ((rc = tc_gru_fwd(fp, s))) return rc;
+        if ((rc = tc_gru_fwd2(img(57344), img(57344 + 24576), tg.b_ih, tg.b_hh, x_tg_ti, hg_ti, nullptr, R, d->T, n_tiles,
+                              s))) return rc;
+        // :55-78 fused with fc2 of both nets
+        PHASE(s, "q_select_tc");
+        if ((rc = tc_q_select(d, b, img(49152), img(57344 + 49152), on.fc2_b, tg.fc2_b, h_ti, hg_ti, n_tiles, v.chosen,
+                              v.tmax, hp->keep_q ? v.q_on : nullptr, hp->keep_q ? v.q_tg : nullptr, s))) return rc;
     } else {
         PHASE(s, "fc1_fwd_online");
         if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
@@ -591,8 +588,10 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         if ((rc = gru_fwd_dispatch(d, tg, R, d->T, v.x_tg, nullptr, nullptr, nullptr, v.q_tg, nullptr, s))) return rc;
     }
     // :55-78
-    PHASE(s, "target_select");
-    if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
+    if (!tc_agent) {
+        PHASE(s, "target_select");
+        if ((rc = launch_target_select(d, b, v.q_on, v.q_tg, v.chosen, v.tmax, nullptr, s))) return rc;
+    }
     // :81-83 (target mixer first: both passes share the raw buffer, the online one must survive)
     uint8_t* state_img = reinterpret_cast<uint8_t*>(v.state_img);
     uint8_t* raw_img = reinterpret_cast<uint8_t*>(v.raw_on);

@@ -709,30 +709,42 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
             umma_commit(done);
         }
     } else {
-        // ===== warps 0-1: one-hot generators (one row per thread); all four warps: final epilogue =====
-        if (warp < 2) {
-            const int rr = warp * 32 + lane;                   // row within the half tile
-            for (int64_t i = 0; i < n_my; ++i) {
-                const int s = (int)(i & 1);
+        // ===== one-hot generators (one row per thread): warps 0-1 take the even items of this CTA, warps 2-3 the odd
+        // ones; the index loads of a warp's next item are issued before the current item is written (software
+        // pipeline: the generators, not the copies or the MMAs, were the critical path).  All four warps: final epilogue.
+        {
+            const int rr = (warp & 1) * 32 + lane;             // row within the half tile
+            struct Idx { int a, ap, n; float dq; };
+            auto fetch = [&](int64_t i) {
+                Idx x{-1, -1, -1, 0.f};
+                if (i >= n_my) return x;
                 const int64_t item = beg + i;
                 const int64_t tt = item >> 1;
                 const int half = (int)(item & 1);
                 const int64_t t = tt / P.n_tiles, tile = tt - t * P.n_tiles;
                 const int64_t p = tile * TILE_ROWS + half * 64 + rr;
-                int a = -1, ap = -1, n = -1;
-                float dq = 0.f;
                 if (p < P.R) {
                     const int64_t b = p / P.N;
-                    n = (int)(p - b * P.N);
+                    x.n = (int)(p - b * P.N);
                     if (t < P.T - 1) {
-                        dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
-                        a = (int)__ldg(P.actions + b * P.actions_sb + t * P.N + n);
+                        x.dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + x.n);
+                        x.a = (int)__ldg(P.actions + b * P.actions_sb + t * P.N + x.n);
                     }
-                    if (P.use_act && t > 0 && __ldg(P.filled + b * P.filled_sb + (t - 1)) != 0)
-                        ap = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + n);
-                    if (!P.use_id) n = -1;
+                    if (P.use_act && t > 0) {                  // both loads issued unconditionally, then selected
+                        const int64_t f = __ldg(P.filled + b * P.filled_sb + (t - 1));
+                        const int apv = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + x.n);
+                        x.ap = f != 0 ? apv : -1;
+                    }
+                    if (!P.use_id) x.n = -1;
                 }
-                const uint32_t dqb = pack_bf16x2(dq, 0.f) & 0xffffu;      // bf16 bits of dq
+                return x;
+            };
+            Idx cur = fetch(warp >> 1);
+            for (int64_t i = warp >> 1; i < n_my; i += 2) {
+                const int s = (int)(i & 1);
+                const Idx nxt = fetch(i + 2);
+                const int a = cur.a, ap = cur.ap, n = cur.n;
+                const uint32_t dqb = pack_bf16x2(cur.dq, 0.f) & 0xffffu;      // bf16 bits of dq
                 mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
@@ -749,6 +761,7 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
+                cur = nxt;
             }
         }
         float* out = P.partial + (int64_t)blockIdx.x * PARTIAL_FLOATS;

@@ -1,0 +1,474 @@
+// bf16 tensor-core tier, second-generation recurrence kernels (learner step only).
+//
+//   gru_fwd2_kernel   : GRUCell unrolled over T for TWO 128-row tiles per CTA in ping-pong (one CTA per SM): while the
+//                       eight epilogue warps do the gate math of one tile, the tensor core runs the 16 tcgen05.mma of
+//                       the other.  No fc2 inside the recurrence (q is produced by q_select_kernel from the h images),
+//                       so a step's dependency chain is MMA -> gate math -> MMA.  Everything that goes to HBM leaves
+//                       through shared memory: the new h tile is the MMA operand tile itself, the four gate tiles are
+//                       staged in the exact image layout, and ONE thread issues cp.async.bulk shared->global copies of
+//                       16 KB each (the first version stored 16 bytes per thread at a 128-byte stride: 32 cache lines
+//                       per warp instruction, which made the LSU the bottleneck - ncu, profiles/r01_*).
+//   q_select_kernel   : q = fc2(h) for the online and the target net out of the h images (two tcgen05.mma groups per
+//                       128-row tile) fused with learners/q_learner.py:55-78: chosen-action gather, avail masking
+//                       (-9999999), double-Q arg-max (ties -> lowest index), target gather.  Q never goes to HBM
+//                       unless a debug/test output pointer is given.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "gru_tc.cuh"
+
+namespace pmb {
+namespace tc {
+
+namespace {
+constexpr int TILE_ROWS2 = 128;
+constexpr int TILE_BYTES2 = 16384;
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 : one MUFU op instead of ex2 + rcp
+__device__ __forceinline__ float sigmoid_tanh(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ void ld_tmem_16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 16 fp32 values (columns 16*c16 .. +15 of row r) -> two 16-byte chunks of a tile image
+__device__ __forceinline__ void st_row16(uint8_t* tile, uint32_t r, int c16, const float (&f)[16]) {
+    uint4 a = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    uint4 b = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                         pack_bf16x2(f[14], f[15]));
+    *reinterpret_cast<uint4*>(tile + sw128_offset(r, 2 * c16)) = a;
+    *reinterpret_cast<uint4*>(tile + sw128_offset(r, 2 * c16 + 1)) = b;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// forward recurrence, two tiles per CTA
+// ------------------------------------------------------------------------------------------
+namespace g2 {
+constexpr int WIH = 0, WHH = 24576;
+constexpr int XB = 49152;                          // [tile 2][buf 2][16 KB]
+constexpr int HT = XB + 4 * TILE_BYTES2;           // [tile 2][16 KB]   h operand tile = h image
+constexpr int ST = HT + 2 * TILE_BYTES2;           // [4][16 KB]        gate staging (r, z, n, hn), shared by both tiles
+constexpr int BIAS = ST + 4 * TILE_BYTES2;         // brz[128] | bin[64] | bhn[64]
+constexpr int BARS = BIAS + 1024;
+constexpr int SMEM_BYTES = 1024 + BARS + 256;
+constexpr int N_EPI_WARPS = 8, MMA_WARP = 8, IO_WARP = 9;
+constexpr int THREADS = 320;
+}  // namespace g2
+
+struct GruFwd2Params {
+    const __nv_bfloat16* w_ih_img;   // 192 rows x 128 B
+    const __nv_bfloat16* w_hh_img;
+    const float *b_ih, *b_hh;
+    const uint8_t* x_ti;             // [nt][n_tiles][16 KB]
+    uint8_t* h_ti;                   // [(nt+1)][n_tiles][16 KB]   slot 0 = h_0 = 0 (written here), slot t+1 = h_t
+    uint8_t* g_ti;                   // [nt][n_tiles][4][16 KB] (r, z, n, hn) or null
+    int64_t R;
+    int nt, n_tiles;
+};
+
+__global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params P) {
+    using namespace g2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* bias = reinterpret_cast<float*>(smem + BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* w_full = bars;                 // weights landed
+    uint64_t* x_full = bars + 1;             // [tile][buf]
+    uint64_t* x_empty = bars + 5;            // [tile][buf]
+    uint64_t* gates_full = bars + 9;         // [tile]
+    uint64_t* h_ready = bars + 11;           // [tile]  epilogue wrote h (and the gate staging)
+    uint64_t* st_free = bars + 13;           // bulk stores of the previous use finished reading shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile0 = 2 * blockIdx.x;
+    const int n_my = P.n_tiles - tile0 >= 2 ? 2 : 1;
+    const bool stash = P.g_ti != nullptr;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&gates_full[i], 1); mbar_init(&h_ready[i], N_EPI_WARPS); }
+        mbar_init(st_free, 1);
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < 128; i += THREADS) bias[i] = P.b_ih[i] + P.b_hh[i];
+    for (int i = threadIdx.x; i < 64; i += THREADS) {
+        bias[128 + i] = P.b_ih[128 + i];
+        bias[192 + i] = P.b_hh[128 + i];
+    }
+    // h_0 = 0 in both operand tiles
+    for (int i = threadIdx.x; i < 2 * TILE_BYTES2 / 16; i += THREADS)
+        reinterpret_cast<uint4*>(smem + HT)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == IO_WARP) {
+        // ===== loads (weights, x tiles) and bulk stores (h, gates) : one thread =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, 2 * 24576);
+            bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
+            bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
+            auto load_x = [&](int i, int t) {
+                const int b = t & 1;
+                mbar_wait(&x_empty[2 * i + b], (uint32_t)(((t >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&x_full[2 * i + b], TILE_BYTES2);
+                bulk_copy_g2s(smem + XB + (2 * i + b) * TILE_BYTES2,
+                              P.x_ti + ((int64_t)t * P.n_tiles + tile0 + i) * TILE_BYTES2, TILE_BYTES2, &x_full[2 * i + b]);
+            };
+            for (int t = 0; t < 2 && t < P.nt; ++t)
+                for (int i = 0; i < n_my; ++i) load_x(i, t);
+            // h_0 image (zeros) from the operand tiles
+            for (int i = 0; i < n_my; ++i)
+                bulk_copy_s2g(P.h_ti + (int64_t)(tile0 + i) * TILE_BYTES2, smem + HT + i * TILE_BYTES2, TILE_BYTES2);
+            bulk_commit_group();
+            bulk_wait_group_read<0>();
+            mbar_arrive(st_free);                              // arrival #0: the h_0 stores no longer read the operand tiles
+            for (int t = 0; t < P.nt; ++t)
+                for (int i = 0; i < n_my; ++i) {
+                    mbar_wait(&h_ready[i], (uint32_t)(t & 1));
+                    const int64_t tt = (int64_t)t * P.n_tiles + tile0 + i;
+                    bulk_copy_s2g(P.h_ti + (tt + P.n_tiles) * TILE_BYTES2, smem + HT + i * TILE_BYTES2, TILE_BYTES2);
+                    if (stash) bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, smem + ST, 4 * TILE_BYTES2);
+                    bulk_commit_group();
+                    if (t + 2 < P.nt) load_x(i, t + 2);
+                    bulk_wait_group_read<0>();
+                    mbar_arrive(st_free);
+                }
+            bulk_wait_group<0>();
+        }
+    } else if (warp == MMA_WARP) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
+            const uint32_t id128 = umma_idesc_bf16(128, 128, 0, 0), id64 = umma_idesc_bf16(128, 64, 0, 0);
+            mbar_wait(w_full, 0);
+            for (int t = 0; t < P.nt; ++t)
+                for (int i = 0; i < n_my; ++i) {
+                    const int b = t & 1;
+                    const uint32_t xt = smem_u32(smem + XB + (2 * i + b) * TILE_BYTES2);
+                    const uint32_t ht = smem_u32(smem + HT + i * TILE_BYTES2);
+                    const uint32_t tm = tmem_base + 256 * i;
+                    mbar_wait(&x_full[2 * i + b], (uint32_t)((t >> 1) & 1));
+                    if (t > 0) mbar_wait(&h_ready[i], (uint32_t)((t - 1) & 1));     // h_{t-1} written, gates(t-1) drained
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)                 // r|z : x . W_i{r,z}^T
+                        umma_bf16(tm, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024),
+                                  id128, kk != 0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)                 // n, input part
+                        umma_bf16(tm + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
+                                  umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)                 // r|z += h . W_h{r,z}^T
+                        umma_bf16(tm, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024),
+                                  id128, 1);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)                 // n, hidden part
+                        umma_bf16(tm + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
+                                  umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+                    umma_commit(&x_empty[2 * i + b]);
+                    umma_commit(&gates_full[i]);
+                }
+        }
+    } else {
+        // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 (w & 3) .. +31 and hidden columns 32 (w >> 2) .. +31 =====
+        const int q4 = warp & 3, ch = warp >> 2;
+        const uint32_t r = (uint32_t)(q4 * 32 + lane);
+        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 32 * ch;
+        float h[2][32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[i][j] = 0.f;
+        bool valid[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) valid[i] = (int64_t)(tile0 + i) * TILE_ROWS2 + r < P.R;
+        uint32_t use = 0;                                      // staging-buffer use counter (all tiles, all steps)
+        for (int t = 0; t < P.nt; ++t) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i < n_my) {
+                    mbar_wait(&gates_full[i], (uint32_t)(t & 1));
+                    // the previous use's bulk stores must have finished reading HT / the staging tiles (use k needs
+                    // arrival #k of the IO thread; #0 covers the h_0 stores)
+                    mbar_wait(st_free, use & 1);
+                    ++use;
+                    tc_fence_after();
+                    uint8_t* hti = smem + HT + i * TILE_BYTES2;
+#pragma unroll
+                    for (int sc = 0; sc < 2; ++sc) {
+                        uint32_t ar[16], az[16], ain[16], ahn[16];
+                        const uint32_t ta = tlane + 256 * i + 16 * sc;
+                        ld_tmem_16(ta, ar);
+                        ld_tmem_16(ta + 64, az);
+                        ld_tmem_16(ta + 128, ain);
+                        ld_tmem_16(ta + 192, ahn);
+                        tmem_wait_ld();
+                        float fr[16], fz[16], fn[16], fhn[16], fh[16];
+                        const int c0 = 32 * ch + 16 * sc;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 b_r = *reinterpret_cast<const float4*>(bias + c0 + 4 * j4);
+                            const float4 b_z = *reinterpret_cast<const float4*>(bias + 64 + c0 + 4 * j4);
+                            const float4 b_n = *reinterpret_cast<const float4*>(bias + 128 + c0 + 4 * j4);
+                            const float4 b_h = *reinterpret_cast<const float4*>(bias + 192 + c0 + 4 * j4);
+                            const float br[4] = {b_r.x, b_r.y, b_r.z, b_r.w}, bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w};
+                            const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w}, bh[4] = {b_h.x, b_h.y, b_h.z, b_h.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * j4 + jj;
+                                const float rg = sigmoid_tanh(__uint_as_float(ar[j]) + br[jj]);
+                                const float zg = sigmoid_tanh(__uint_as_float(az[j]) + bz[jj]);
+                                const float hn = __uint_as_float(ahn[j]) + bh[jj];
+                                const float ng = tanh_approx(fmaf(rg, hn, __uint_as_float(ain[j]) + bn[jj]));
+                                float hv = fmaf(zg, h[i][16 * sc + j] - ng, ng);
+                                if (!valid[i]) hv = 0.f;
+                                h[i][16 * sc + j] = hv;
+                                fr[j] = rg; fz[j] = zg; fn[j] = ng; fhn[j] = hn; fh[j] = hv;
+                            }
+                        }
+                        const int c16 = 2 * ch + sc;
+                        st_row16(hti, r, c16, fh);
+                        if (stash) {
+                            if (!valid[i]) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { fr[j] = 0.f; fz[j] = 0.f; fn[j] = 0.f; fhn[j] = 0.f; }
+                            }
+                            st_row16(smem + ST, r, c16, fr);
+                            st_row16(smem + ST + TILE_BYTES2, r, c16, fz);
+                            st_row16(smem + ST + 2 * TILE_BYTES2, r, c16, fn);
+                            st_row16(smem + ST + 3 * TILE_BYTES2, r, c16, fhn);
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&h_ready[i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// q = fc2(h) for both nets + chosen-action gather + double-Q target (q_learner.py:55-78)
+// ------------------------------------------------------------------------------------------
+namespace qs {
+constexpr int STAGES = 2;                                  // x 2 CTAs per SM = 4 tiles in flight
+constexpr int W2ON = 0, W2TG = 8192, STG = 16384;          // stage: h_on tile | h_tg tile
+constexpr int STAGE_BYTES = 2 * TILE_BYTES2;
+constexpr int BIAS = STG + STAGES * STAGE_BYTES;           // b2_on[64] | b2_tg[64]
+constexpr int BARS = BIAS + 512;
+constexpr int SMEM_BYTES = 1024 + BARS + 256;
+constexpr int THREADS = 192;                               // warps 0-3 epilogue, 4 MMA, 5 loader
+}  // namespace qs
+
+struct QSelectParams {
+    const __nv_bfloat16* w2_on_img;  // 64 rows x 128 B (rows >= A zero)
+    const __nv_bfloat16* w2_tg_img;
+    const float *b2_on, *b2_tg;
+    const uint8_t* h_on_ti;          // [(T+1)][n_tiles][16 KB]
+    const uint8_t* h_tg_ti;
+    const int32_t* avail; int64_t avail_sb;
+    const int64_t* actions; int64_t actions_sb;
+    float* chosen;                   // [B][T-1][N]
+    float* tmax;                     // [B][T-1][N]
+    float* q_on_out;                 // optional fp32 [T][R][A] (tests / diagnostics)
+    float* q_tg_out;
+    int64_t R;
+    int T, N, A, n_tiles, double_q;
+};
+
+__global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams P) {
+    using namespace qs;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* bias = reinterpret_cast<float*>(smem + BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* w_full = bars;
+    uint64_t* full = bars + 1;               // [STAGES]
+    uint64_t* empty = bars + 1 + STAGES;     // [STAGES]
+    uint64_t* tfull = bars + 1 + 2 * STAGES; // [2]
+    uint64_t* tempty = tfull + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A_pad = (P.A + 15) & ~15;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    for (int i = threadIdx.x; i < 128; i += THREADS) {
+        const int a = i & 63;
+        bias[i] = a < P.A ? (i < 64 ? P.b2_on[a] : P.b2_tg[a]) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_items = (int64_t)P.T * P.n_tiles;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, 2 * 8192);
+            bulk_copy_g2s(smem + W2ON, P.w2_on_img, 8192, w_full);
+            bulk_copy_g2s(smem + W2TG, P.w2_tg_img, 8192, w_full);
+            uint32_t it = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                uint8_t* st = smem + STG + s * STAGE_BYTES;
+                // item = t * n_tiles + tile ; h_t lives in slot t + 1
+                bulk_copy_g2s(st, P.h_on_ti + (item + P.n_tiles) * TILE_BYTES2, TILE_BYTES2, &full[s]);
+                bulk_copy_g2s(st + TILE_BYTES2, P.h_tg_ti + (item + P.n_tiles) * TILE_BYTES2, TILE_BYTES2, &full[s]);
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t w_on = smem_u32(smem + W2ON), w_tg = smem_u32(smem + W2TG);
+            const uint32_t idq = umma_idesc_bf16(128, A_pad, 0, 0);
+            mbar_wait(w_full, 0);
+            uint32_t it = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int s = it % STAGES, b = it & 1;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                mbar_wait(&tempty[b], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + STG + s * STAGE_BYTES);
+                const uint32_t tm = tmem_base + 128 * b;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tm, umma_desc_sw128(st + kk * 32, 16, 1024), umma_desc_sw128(w_on + kk * 32, 16, 1024), idq,
+                              kk != 0);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tm + 64, umma_desc_sw128(st + TILE_BYTES2 + kk * 32, 16, 1024),
+                              umma_desc_sw128(w_tg + kk * 32, 16, 1024), idq, kk != 0);
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[b]);
+            }
+        }
+    } else {
+        // ===== epilogue: one row per thread =====
+        const uint32_t r = (uint32_t)(warp * 32 + lane);
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t it = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int b2 = it & 1;
+            const int t = (int)(item / P.n_tiles);
+            const int64_t tile = item - (int64_t)t * P.n_tiles;
+            const int64_t p = tile * TILE_ROWS2 + r;
+            const bool valid = p < P.R;
+            const int64_t b = valid ? p / P.N : 0;
+            const int n = valid ? (int)(p - b * P.N) : 0;
+            // issue the index / avail loads before waiting for the accumulator
+            int a_taken = -1;
+            if (valid && t < P.T - 1) a_taken = (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n);
+            const int32_t* av = P.avail + b * P.avail_sb + ((int64_t)t * P.N + n) * P.A;
+            mbar_wait(&tfull[b2], (it >> 1) & 1);
+            tc_fence_after();
+            float best = -INFINITY, chosen = 0.f, tsel = 0.f, mt0 = 0.f;
+            int bidx = 0x7fffffff;
+            const bool want_t = valid && t >= 1;
+            float* qo = P.q_on_out ? P.q_on_out + ((int64_t)t * P.R + p) * P.A : nullptr;
+            float* qt = P.q_tg_out ? P.q_tg_out + ((int64_t)t * P.R + p) * P.A : nullptr;
+            for (int c0 = 0; c0 < A_pad; c0 += 16) {
+                uint32_t von[16], vtg[16];
+                ld_tmem_16(tl + 128 * b2 + c0, von);
+                ld_tmem_16(tl + 128 * b2 + 64 + c0, vtg);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int a = c0 + j;
+                    if (a < P.A) {
+                        const float q_on = __uint_as_float(von[j]) + bias[a];
+                        const float q_tg = __uint_as_float(vtg[j]) + bias[64 + a];
+                        if (a == a_taken) chosen = q_on;
+                        if (want_t) {
+                            const bool ok = __ldg(av + a) != 0;
+                            const float mt = ok ? q_tg : kMaskValue;
+                            const float v = P.double_q ? (ok ? q_on : kMaskValue) : mt;
+                            if (a == 0) mt0 = mt;
+                            if (v > best) { best = v; bidx = a; tsel = mt; }      // ascending a, strict >: lowest index wins
+                        }
+                        if (valid && qo) qo[a] = q_on;
+                        if (valid && qt) qt[a] = q_tg;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[b2]);
+            if (valid && t < P.T - 1) P.chosen[(b * (P.T - 1) + t) * P.N + n] = chosen;
+            if (want_t) {
+                if (bidx == 0x7fffffff) tsel = mt0;             // all-NaN row: index 0, as target_select_kernel
+                P.tmax[(b * (P.T - 1) + (t - 1)) * P.N + n] = P.double_q ? tsel : best;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace tc
+
+int tc_gru_fwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* b_ih, const float* b_hh,
+                const uint8_t* x_ti, uint8_t* h_ti, uint8_t* g_ti, int64_t R, int nt, int n_tiles, cudaStream_t s) {
+    tc::GruFwd2Params P;
+    P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.b_ih = b_ih; P.b_hh = b_hh;
+    P.x_ti = x_ti; P.h_ti = h_ti; P.g_ti = g_ti; P.R = R; P.nt = nt; P.n_tiles = n_tiles;
+    PMB_CUDA(cudaFuncSetAttribute(tc::gru_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g2::SMEM_BYTES));
+    tc::gru_fwd2_kernel<<<(n_tiles + 1) / 2, tc::g2::THREADS, tc::g2::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("gru_fwd2_kernel");
+    return PMB_OK;
+}
+
+int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_on_img, const __nv_bfloat16* w2_tg_img,
+                const float* b2_on, const float* b2_tg, const uint8_t* h_on_ti, const uint8_t* h_tg_ti, int n_tiles,
+                float* chosen, float* tmax, float* q_on_out, float* q_tg_out, cudaStream_t s) {
+    tc::QSelectParams P;
+    P.w2_on_img = w2_on_img; P.w2_tg_img = w2_tg_img; P.b2_on = b2_on; P.b2_tg = b2_tg;
+    P.h_on_ti = h_on_ti; P.h_tg_ti = h_tg_ti;
+    P.avail = b->avail; P.avail_sb = b->avail_sb; P.actions = b->actions; P.actions_sb = b->actions_sb;
+    P.chosen = chosen; P.tmax = tmax; P.q_on_out = q_on_out; P.q_tg_out = q_tg_out;
+    P.R = (int64_t)d->B * d->N; P.T = d->T; P.N = d->N; P.A = d->A; P.n_tiles = n_tiles; P.double_q = d->double_q;
+    const int64_t n_items = (int64_t)d->T * n_tiles;
+    int grid = 2 * sm_count();
+    if (grid > n_items) grid = (int)n_items;
+    PMB_CUDA(cudaFuncSetAttribute(tc::q_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::qs::SMEM_BYTES));
+    tc::q_select_kernel<<<grid, tc::qs::THREADS, tc::qs::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("q_select_kernel");
+    return PMB_OK;
+}
+
+}  // namespace pmb

@@ -187,7 +187,8 @@ class QLearner:
 
         do_sync = (episode_num - self.last_target_update_episode) / a.target_update_interval >= 1.0
         dp = data_parallel.is_active() and getattr(a, "data_parallel", True)
-        hp = _lib.HParams(a.gamma, a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip, int(do_sync), int(dp), 0)
+        hp = _lib.HParams(a.gamma, a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip, int(do_sync), int(dp),
+                          int(bool(getattr(a, "keep_q", False))))
         L = _lib.lib()
         s = _lib.stream_ptr(dev)
         _lib.check(L.pmb_qlearner_train_step(C.byref(dims), C.byref(pb), C.byref(hp), _lib.ptr(f["p"]),

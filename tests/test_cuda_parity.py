@@ -369,7 +369,7 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
     # constant on both sides: from a zero state the first update is +-lr/sqrt(1-alpha) * sign(g) for
     # every element, which turns bf16-level noise on near-zero gradients into full-size sign flips
     # and says nothing about the kernels ("RMSprop amplifies tiny-gradient noise").
-    args = default_args(shape, mixer=mixer, learner_log_interval=0, precision="bf16", grad_norm_clip=1e30)
+    args = default_args(shape, mixer=mixer, learner_log_interval=0, precision="bf16", grad_norm_clip=1e30, keep_q=True)
     fields = numpy_episode_fields(shape, B, T, seed=21, ragged=True)
     olr = _oracle_learner(shape, copy.copy(args), seed=8)
     learner, _ = build_learner(shape, args, olr.agent, olr.target_agent, olr.mixer_p, olr.target_mixer_p)
