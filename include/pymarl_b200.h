@@ -239,6 +239,7 @@ typedef struct pmb_ws_views {
     float* obs_img;            /* bf16 tier: obs tile images written by the fc1 GEMM */
     float* state_img;          /* bf16 tier: state tile images shared by both mixers and the hypernet weight gradients */
     float* h_tg;               /* bf16 tier: h tile images of the target net */
+    float* relu_mask;          /* bf16 tier: bit mask (x > 0) of the online fc1 output */
 } pmb_ws_views;
 int pmb_learner_workspace_views(const pmb_dims* d, void* workspace, int64_t workspace_bytes, pmb_ws_views* out);
 

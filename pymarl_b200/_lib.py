@@ -56,7 +56,8 @@ class WsViews(C.Structure):
     _names = ("x_on", "x_tg", "h_stash", "gates", "q_on", "q_tg", "chosen", "tmax", "raw_on", "raw_tg",
               "q_tot", "t_tot", "g", "d_chosen", "scratch")
     _fields_ = [(k, C.c_void_p) for k in _names] + [("scratch_bytes", C.c_int64), ("obs_img", C.c_void_p),
-                                                        ("state_img", C.c_void_p), ("h_tg", C.c_void_p)]
+                                                        ("state_img", C.c_void_p), ("h_tg", C.c_void_p),
+                                                        ("relu_mask", C.c_void_p)]
 
 
 class PmbError(RuntimeError):

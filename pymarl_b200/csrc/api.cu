@@ -39,7 +39,7 @@ int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target,
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
                   const float* bias, float* C, int64_t ldc, cudaStream_t s);
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
-                    float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, void* scratch,
+                    float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, uint32_t* relu_mask, void* scratch,
                     int64_t scratch_bytes, cudaStream_t s);
 // tc_atb.cu (tile-image D operand)
 int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, const float* A, RowMap amap, int K,
@@ -135,7 +135,7 @@ void compute_layout(const pmb_dims* d, pmb_layout* L) {
 namespace {
 
 struct WsPlan {
-    int64_t off[17];
+    int64_t off[18];
     int64_t scratch_bytes;
     int64_t total;
 };
@@ -159,7 +159,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
     const int64_t n_tiles = ceil_div(R, 128), ti = d->precision == PMB_PREC_BF16 ? 4096 : 0;   // floats per tile
     auto mx = [](int64_t a, int64_t b) { return a > b ? a : b; };
     const bool tc_mix = qmix && d->precision == PMB_PREC_BF16 && d->E == 32;
-    int64_t sizes[17] = {
+    int64_t sizes[18] = {
         mx(T * R * H, T * n_tiles * ti),               // 0 x_on
         mx(T * R * H, T * n_tiles * ti),               // 1 x_tg (reused as dpre1 in the backward)
         mx((T + 1) * R * H, (T + 1) * n_tiles * ti),   // 2 h_stash
@@ -179,11 +179,13 @@ WsPlan plan_workspace(const pmb_dims* d) {
         tc_mix ? tc_state_img_bytes(d) / 4 : 0,   // 14 state tile images (bf16 tier)
         // 15 h images of the TARGET net (bf16 tier: q = fc2(h) is computed from the images by q_select)
         (d->precision == PMB_PREC_BF16 && d->H == 64) ? (T + 1) * n_tiles * ti : 0,
-        0                          // 16 scratch (bytes, below)
+        // 16 ReLU mask of the online fc1 output, one bit per element: [T][n_tiles][2][128] words
+        (d->precision == PMB_PREC_BF16 && d->H == 64) ? T * n_tiles * 256 : 0,
+        0                          // 17 scratch (bytes, below)
     };
     WsPlan p;
     int64_t off = 0;
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 17; ++i) {
         p.off[i] = off;
         off += align_up(sizes[i] * 4, 256);
     }
@@ -204,7 +206,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
         }
     }
     if (sc < 4096 * 4) sc = 4096 * 4;
-    p.off[16] = off;
+    p.off[17] = off;
     p.scratch_bytes = align_up(sc, 256);
     p.total = off + p.scratch_bytes;
     return p;
@@ -220,7 +222,8 @@ void fill_views(const pmb_dims* d, void* ws, const WsPlan& p, pmb_ws_views* v) {
     v->t_tot = iql ? v->tmax : f(11);
     v->g = f(12);
     v->d_chosen = iql ? v->g : f(13);
-    v->scratch = f(16);
+    v->scratch = f(17);
+    v->relu_mask = f(16);
     v->state_img = f(14);
     v->h_tg = f(15);
     v->scratch_bytes = p.scratch_bytes;
@@ -561,8 +564,8 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         if ((rc = tc_ti_zero_pad(x_on_ti, d->T, n_tiles, R, s))) return rc;
         if ((rc = tc_ti_zero_pad(x_tg_ti, d->T, n_tiles, R, s))) return rc;
         PHASE(s, "fc1_fwd_both_tc");
-        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, fused_dw ? obs_ti : nullptr, v.scratch,
-                                  v.scratch_bytes, s))) return rc;
+        if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, fused_dw ? obs_ti : nullptr,
+                                  reinterpret_cast<uint32_t*>(v.relu_mask), v.scratch, v.scratch_bytes, s))) return rc;
         PHASE(s, "gru_unroll_fwd_online_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
         if ((rc = pack_gru(tg, gru_img + 57344))) return rc;
@@ -628,14 +631,10 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         AgentGrads gr = agent_grads(d, flat_g);
         PHASE(s, "gru_unroll_bwd_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
-        tc::GruBwdParams bp;
-        bp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img);
-        bp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576);
-        bp.fc2_w = on.fc2_w;
-        bp.x_ti = x_on_ti; bp.h_ti = h_ti; bp.g_ti = g_ti; bp.dpre1_ti = x_tg_ti;
-        bp.d_chosen = v.d_chosen; bp.actions = b->actions; bp.actions_sb = b->actions_sb;
-        bp.R = R; bp.T = d->T; bp.N = d->N; bp.n_tiles = n_tiles;
-        if ((rc = tc_gru_bwd(bp, s))) return rc;
+        if ((rc = tc_gru_bwd2(reinterpret_cast<const __nv_bfloat16*>(gru_img),
+                              reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576), on.fc2_w, h_ti, g_ti, x_tg_ti,
+                              reinterpret_cast<const uint32_t*>(v.relu_mask), v.d_chosen, b->actions, b->actions_sb, R,
+                              d->T, d->N, d->A, n_tiles, s))) return rc;
         PHASE(s, "dW_rnn_tc");
         char* sc2 = reinterpret_cast<char*>(v.scratch) + 131072;
         if ((rc = tc_gru_dw(g_ti, x_on_ti, h_ti, d->T, n_tiles, gr.w_ih, gr.w_hh, gr.b_ih, gr.b_hh, sc2,

@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
         // ===== epilogue: one row per thread =====
         const uint32_t r = (uint32_t)(warp * 32 + lane);
         const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const bool vec_ok = (P.A & 3) == 0 && (P.avail_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
         uint32_t it = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b2 = it & 1;
@@ -391,34 +392,55 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
             int a_taken = -1;
             if (valid && t < P.T - 1) a_taken = (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n);
             const int32_t* av = P.avail + b * P.avail_sb + ((int64_t)t * P.N + n) * P.A;
+            const bool want_t = valid && t >= 1;
+            // the whole avail row goes to registers before the accumulator wait (16-byte loads when the layout allows)
+            int4 avv[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                avv[q] = make_int4(0, 0, 0, 0);
+                if (want_t && 4 * q < P.A) {
+                    if (vec_ok) avv[q] = __ldg(reinterpret_cast<const int4*>(av) + q);
+                    else {
+                        avv[q].x = __ldg(av + 4 * q);
+                        if (4 * q + 1 < P.A) avv[q].y = __ldg(av + 4 * q + 1);
+                        if (4 * q + 2 < P.A) avv[q].z = __ldg(av + 4 * q + 2);
+                        if (4 * q + 3 < P.A) avv[q].w = __ldg(av + 4 * q + 3);
+                    }
+                }
+            }
             mbar_wait(&tfull[b2], (it >> 1) & 1);
             tc_fence_after();
             float best = -INFINITY, chosen = 0.f, tsel = 0.f, mt0 = 0.f;
             int bidx = 0x7fffffff;
-            const bool want_t = valid && t >= 1;
             float* qo = P.q_on_out ? P.q_on_out + ((int64_t)t * P.R + p) * P.A : nullptr;
             float* qt = P.q_tg_out ? P.q_tg_out + ((int64_t)t * P.R + p) * P.A : nullptr;
-            for (int c0 = 0; c0 < A_pad; c0 += 16) {
-                uint32_t von[16], vtg[16];
-                ld_tmem_16(tl + 128 * b2 + c0, von);
-                ld_tmem_16(tl + 128 * b2 + 64 + c0, vtg);
-                tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int a = c0 + j;
-                    if (a < P.A) {
-                        const float q_on = __uint_as_float(von[j]) + bias[a];
-                        const float q_tg = __uint_as_float(vtg[j]) + bias[64 + a];
-                        if (a == a_taken) chosen = q_on;
-                        if (want_t) {
-                            const bool ok = __ldg(av + a) != 0;
-                            const float mt = ok ? q_tg : kMaskValue;
-                            const float v = P.double_q ? (ok ? q_on : kMaskValue) : mt;
-                            if (a == 0) mt0 = mt;
-                            if (v > best) { best = v; bidx = a; tsel = mt; }      // ascending a, strict >: lowest index wins
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c0 = 16 * cc;
+                if (c0 < A_pad) {
+                    uint32_t von[16], vtg[16];
+                    ld_tmem_16(tl + 128 * b2 + c0, von);
+                    ld_tmem_16(tl + 128 * b2 + 64 + c0, vtg);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int a = c0 + j;
+                        if (a < P.A) {
+                            const float q_on = __uint_as_float(von[j]) + bias[a];
+                            const float q_tg = __uint_as_float(vtg[j]) + bias[64 + a];
+                            if (a == a_taken) chosen = q_on;
+                            if (want_t) {
+                                const int4 w = avv[4 * cc + (j >> 2)];
+                                const int avj = (j & 3) == 0 ? w.x : ((j & 3) == 1 ? w.y : ((j & 3) == 2 ? w.z : w.w));
+                                const bool ok = avj != 0;
+                                const float mt = ok ? q_tg : kMaskValue;
+                                const float v = P.double_q ? (ok ? q_on : kMaskValue) : mt;
+                                if (a == 0) mt0 = mt;
+                                if (v > best) { best = v; bidx = a; tsel = mt; }      // ascending a, strict >: lowest index wins
+                            }
+                            if (valid && qo) qo[a] = q_on;
+                            if (valid && qt) qt[a] = q_tg;
                         }
-                        if (valid && qo) qo[a] = q_on;
-                        if (valid && qt) qt[a] = q_tg;
                     }
                 }
             }
@@ -437,6 +459,245 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
     if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// backward recurrence (BPTT), one tile per CTA, double-buffered bulk-copied inputs
+// ------------------------------------------------------------------------------------------
+//   stage buffer (80 KB): [r | z | n | hn | h_prev] tile images of step t, brought in by two bulk copies.  The gate
+//   gradients are written IN PLACE (dr -> r, dz -> z, dn -> n, dn*r -> hn: every thread overwrites exactly the
+//   elements it has just read), are the K-major A operands of the 24 tcgen05.mma (dx = dg . W_ih, dh_rec = dg' . W_hh;
+//   B = the weight images read MN-major) and leave as ONE 64 KB bulk store into the gate stash (gru_dw reads them);
+//   the h_prev slot is reused as the staging tile of dpre1 = relu'(x) dx.  dh stays in fp32 registers.
+namespace b2 {
+constexpr int WIH = 0, WHH = 24576;
+constexpr int BUF = 49152;                         // [2][5][16 KB]
+constexpr int BUF_BYTES = 5 * TILE_BYTES2;
+constexpr int W2T = BUF + 2 * BUF_BYTES;           // fc2.weight as bf16 [A][72] (row stride 144 B)
+constexpr int W2T_STRIDE = 144;
+constexpr int W2T_BYTES = 64 * W2T_STRIDE;         // A <= 64
+constexpr int BARS = W2T + W2T_BYTES;
+constexpr int SMEM_BYTES = 1024 + BARS + 256;
+constexpr int N_EPI_WARPS = 8, MMA_WARP = 8, IO_WARP = 9;
+constexpr int THREADS = 320;
+}  // namespace b2
+
+struct GruBwd2Params {
+    const __nv_bfloat16* w_ih_img;
+    const __nv_bfloat16* w_hh_img;
+    const float* fc2_w;              // fp32 [A][64]
+    const uint8_t* h_ti;             // [(T+1)][n_tiles][16 KB]   slot t = h_{t-1}
+    uint8_t* g_ti;                   // [T][n_tiles][4][16 KB]: in (r, z, n, hn) -> out (da_r, da_z, da_n, da_n*r)
+    uint8_t* dpre1_ti;               // [T][n_tiles][16 KB]
+    const uint32_t* relu_mask;       // [T][n_tiles][2][128]: bit j of word (half, row) = fc1 output column 32*half + j > 0
+    const float* d_chosen;           // [B][T-1][N]
+    const int64_t* actions; int64_t actions_sb;
+    int64_t R;
+    int T, N, A, n_tiles;
+};
+
+__global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params P) {
+    using namespace b2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
+    uint64_t* w_full = bars;
+    uint64_t* in_full = bars + 1;            // [2]  stage buffer landed
+    uint64_t* dg_ready = bars + 3;           // gate gradients written (8 warps)
+    uint64_t* mma_done = bars + 4;
+    uint64_t* dp_ready = bars + 5;           // dpre1 staged (8 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        mbar_init(&in_full[0], 1); mbar_init(&in_full[1], 1);
+        mbar_init(dg_ready, N_EPI_WARPS); mbar_init(mma_done, 1); mbar_init(dp_ready, N_EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 128);
+    // fc2.weight table (bf16, padded rows)
+    for (int i = threadIdx.x; i < P.A * 32; i += THREADS) {
+        const int a = i >> 5, c = (i & 31) * 2;
+        *reinterpret_cast<uint32_t*>(smem + W2T + a * W2T_STRIDE + c * 2) =
+            pack_bf16x2(P.fc2_w[a * 64 + c], P.fc2_w[a * 64 + c + 1]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == IO_WARP) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, 2 * 24576);
+            bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
+            bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
+            auto load = [&](int i) {                            // step index i <-> t = T-1-i, buffer i & 1
+                const int t = P.T - 1 - i;
+                const int64_t tt = (int64_t)t * P.n_tiles + tile;
+                uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
+                mbar_arrive_expect_tx(&in_full[i & 1], BUF_BYTES);
+                bulk_copy_g2s(buf, P.g_ti + tt * 4 * TILE_BYTES2, 4 * TILE_BYTES2, &in_full[i & 1]);
+                bulk_copy_g2s(buf + 4 * TILE_BYTES2, P.h_ti + tt * TILE_BYTES2, TILE_BYTES2, &in_full[i & 1]);
+            };
+            load(0);
+            if (P.T > 1) load(1);
+            for (int i = 0; i < P.T; ++i) {
+                const int t = P.T - 1 - i;
+                const int64_t tt = (int64_t)t * P.n_tiles + tile;
+                uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
+                mbar_wait(dg_ready, (uint32_t)(i & 1));
+                bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, buf, 4 * TILE_BYTES2);
+                bulk_commit_group();
+                mbar_wait(dp_ready, (uint32_t)(i & 1));        // implies the MMAs of this step have completed
+                bulk_copy_s2g(P.dpre1_ti + tt * TILE_BYTES2, buf + 4 * TILE_BYTES2, TILE_BYTES2);
+                bulk_commit_group();
+                bulk_wait_group_read<0>();                     // buffer i & 1 is free again
+                if (i + 2 < P.T) load(i + 2);
+            }
+            bulk_wait_group<0>();
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
+            const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);          // A K-major, B MN-major
+            mbar_wait(w_full, 0);
+            for (int i = 0; i < P.T; ++i) {
+                const uint32_t dg = smem_u32(smem + BUF + (i & 1) * BUF_BYTES);
+                mbar_wait(dg_ready, (uint32_t)(i & 1));
+                tc_fence_after();
+                // dx = da_r W_ir + da_z W_iz + da_n W_in
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base, umma_desc_sw128(dg + g * TILE_BYTES2 + kk * 32, 16, 1024),
+                                  umma_desc_sw128(wih + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                // dh_prev (recurrent part) = da_r W_hr + da_z W_hz + (da_n r) W_hn
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + 64, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES2 + kk * 32, 16, 1024),
+                                  umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                umma_commit(mma_done);
+            }
+        }
+    } else {
+        // ===== 8 warps: warp w owns rows 32 (w & 3) .. +31 and hidden columns 32 (w >> 2) .. +31 =====
+        const int q4 = warp & 3, ch = warp >> 2;
+        const uint32_t r = (uint32_t)(q4 * 32 + lane);
+        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 32 * ch;
+        const int64_t row = (int64_t)tile * TILE_ROWS2 + r;
+        const bool valid = row < P.R;
+        const int64_t b = valid ? row / P.N : 0;
+        const int n = valid ? (int)(row - b * P.N) : 0;
+        float dh[32], zk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dh[j] = 0.f;
+        // per-step scalars, fetched one step ahead
+        auto fetch_dq = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n) : 0.f; };
+        auto fetch_a = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n) : 0; };
+        auto fetch_m = [&](int t) { return t >= 0 ? __ldg(P.relu_mask + (((int64_t)t * P.n_tiles + tile) * 2 + ch) * 128 + r) : 0u; };
+        float dq = fetch_dq(P.T - 1);
+        int act = fetch_a(P.T - 1);
+        uint32_t xm = fetch_m(P.T - 1);
+        for (int i = 0; i < P.T; ++i) {
+            const int t = P.T - 1 - i;
+            uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
+            const float dq_n = fetch_dq(t - 1);
+            const int act_n = fetch_a(t - 1);
+            const uint32_t xm_n = fetch_m(t - 1);
+            // chosen-action gradient enters through fc2: dh += dq * fc2_w[a, :]
+            if (dq != 0.f) {
+                const uint8_t* wr = smem + W2T + act * W2T_STRIDE + 64 * ch;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(wr + 16 * c);
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        dh[8 * c + 2 * k] = fmaf(dq, __uint_as_float(ww[k] << 16), dh[8 * c + 2 * k]);
+                        dh[8 * c + 2 * k + 1] = fmaf(dq, __uint_as_float(ww[k] & 0xffff0000u), dh[8 * c + 2 * k + 1]);
+                    }
+                }
+            }
+            mbar_wait(&in_full[i & 1], (uint32_t)((i >> 1) & 1));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                       // 4 chunks of 8 columns
+                const uint32_t off = sw128_offset(r, (uint32_t)(4 * ch + c));
+                const uint4 vr = *reinterpret_cast<const uint4*>(buf + off);
+                const uint4 vz = *reinterpret_cast<const uint4*>(buf + TILE_BYTES2 + off);
+                const uint4 vn = *reinterpret_cast<const uint4*>(buf + 2 * TILE_BYTES2 + off);
+                const uint4 vh = *reinterpret_cast<const uint4*>(buf + 3 * TILE_BYTES2 + off);
+                const uint4 vp = *reinterpret_cast<const uint4*>(buf + 4 * TILE_BYTES2 + off);
+                const uint32_t wr_[4] = {vr.x, vr.y, vr.z, vr.w}, wz_[4] = {vz.x, vz.y, vz.z, vz.w};
+                const uint32_t wn_[4] = {vn.x, vn.y, vn.z, vn.w}, wh_[4] = {vh.x, vh.y, vh.z, vh.w};
+                const uint32_t wp_[4] = {vp.x, vp.y, vp.z, vp.w};
+                uint32_t o_r[4], o_z[4], o_n[4], o_nr[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float dr2[2], dz2[2], dn2[2], dnr2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int jj = 8 * c + 2 * k + e;
+                        const float fr = e ? __uint_as_float(wr_[k] & 0xffff0000u) : __uint_as_float(wr_[k] << 16);
+                        const float fz = e ? __uint_as_float(wz_[k] & 0xffff0000u) : __uint_as_float(wz_[k] << 16);
+                        const float fn = e ? __uint_as_float(wn_[k] & 0xffff0000u) : __uint_as_float(wn_[k] << 16);
+                        const float fhn = e ? __uint_as_float(wh_[k] & 0xffff0000u) : __uint_as_float(wh_[k] << 16);
+                        const float fhp = e ? __uint_as_float(wp_[k] & 0xffff0000u) : __uint_as_float(wp_[k] << 16);
+                        const float d = dh[jj];
+                        const float da_n = d * (1.f - fz) * (1.f - fn * fn);
+                        dr2[e] = (da_n * fhn) * fr * (1.f - fr);
+                        dz2[e] = d * (fhp - fn) * fz * (1.f - fz);
+                        dn2[e] = da_n;
+                        dnr2[e] = da_n * fr;
+                        zk[jj] = fz;
+                    }
+                    o_r[k] = pack_bf16x2(dr2[0], dr2[1]); o_z[k] = pack_bf16x2(dz2[0], dz2[1]);
+                    o_n[k] = pack_bf16x2(dn2[0], dn2[1]); o_nr[k] = pack_bf16x2(dnr2[0], dnr2[1]);
+                }
+                *reinterpret_cast<uint4*>(buf + off) = make_uint4(o_r[0], o_r[1], o_r[2], o_r[3]);
+                *reinterpret_cast<uint4*>(buf + TILE_BYTES2 + off) = make_uint4(o_z[0], o_z[1], o_z[2], o_z[3]);
+                *reinterpret_cast<uint4*>(buf + 2 * TILE_BYTES2 + off) = make_uint4(o_n[0], o_n[1], o_n[2], o_n[3]);
+                *reinterpret_cast<uint4*>(buf + 3 * TILE_BYTES2 + off) = make_uint4(o_nr[0], o_nr[1], o_nr[2], o_nr[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dg_ready);
+
+            mbar_wait(mma_done, (uint32_t)(i & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int sc = 0; sc < 2; ++sc) {
+                uint32_t ax[16], ah[16];
+                ld_tmem_16(tlane + 16 * sc, ax);
+                ld_tmem_16(tlane + 64 + 16 * sc, ah);
+                tmem_wait_ld();
+                float dp[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int jj = 16 * sc + j;
+                    dp[j] = (xm >> jj) & 1u ? __uint_as_float(ax[j]) : 0.f;
+                    dh[jj] = fmaf(dh[jj], zk[jj], __uint_as_float(ah[j]));
+                }
+                st_row16(buf + 4 * TILE_BYTES2, r, 2 * ch + sc, dp);     // the h_prev slot is free: dpre1 staging
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dp_ready);
+            dq = dq_n; act = act_n; xm = xm_n;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
     }
 }
 
@@ -468,6 +729,19 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
     PMB_CUDA(cudaFuncSetAttribute(tc::q_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::qs::SMEM_BYTES));
     tc::q_select_kernel<<<grid, tc::qs::THREADS, tc::qs::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("q_select_kernel");
+    return PMB_OK;
+}
+
+int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* fc2_w, const uint8_t* h_ti,
+                uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask, const float* d_chosen, const int64_t* actions,
+                int64_t actions_sb, int64_t R, int T, int N, int A, int n_tiles, cudaStream_t s) {
+    tc::GruBwd2Params P;
+    P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.fc2_w = fc2_w; P.h_ti = h_ti; P.g_ti = g_ti; P.dpre1_ti = dpre1_ti;
+    P.relu_mask = relu_mask; P.d_chosen = d_chosen; P.actions = actions; P.actions_sb = actions_sb;
+    P.R = R; P.T = T; P.N = N; P.A = A; P.n_tiles = n_tiles;
+    PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::b2::SMEM_BYTES));
+    tc::gru_bwd2_kernel<<<n_tiles, tc::b2::THREADS, tc::b2::SMEM_BYTES, s>>>(P);
+    PMB_LAUNCH_CHECK("gru_bwd2_kernel");
     return PMB_OK;
 }
 

@@ -338,6 +338,7 @@ struct Fc1TiEpi {
     uint8_t* x_on; uint8_t* x_tg;
     int t0, nt, N, A, use_act, n_tiles;
     int64_t R;
+    uint32_t* relu_mask;        // optional [nt][n_tiles][2][128]: bit j of word (half, row) = online x[32*half + j] > 0
     // rows arrive in time-major tiled order: m = tl * (n_tiles*128) + p
     __device__ void begin(Row& r, int64_t m, bool valid) const {
         r.tile_off = 0; r.r = 0; r.n = 0; r.a_prev = -2;          // -2: padding row (nothing is written)
@@ -361,6 +362,7 @@ struct Fc1TiEpi {
         const float4* tid = reinterpret_cast<const float4*>(tab_id + ((int64_t)net * N + r.n) * 64 + h0);
         const float4* tac = r.a_prev >= 0 ? reinterpret_cast<const float4*>(tab_act + ((int64_t)net * A + r.a_prev) * 64 + h0)
                                           : nullptr;
+        uint32_t mbits = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                 // 8 columns = one 16-byte chunk
             float o[8];
@@ -373,9 +375,12 @@ struct Fc1TiEpi {
                 o[4 * hh + 2] = fmaxf(__uint_as_float(v[8 * q + 4 * hh + 2]) + ac.z + bi.z, 0.f);
                 o[4 * hh + 3] = fmaxf(__uint_as_float(v[8 * q + 4 * hh + 3]) + ac.w + bi.w, 0.f);
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mbits |= (o[k] > 0.f ? 1u : 0u) << (8 * q + k);
             *reinterpret_cast<uint4*>(tile + sw128_offset(r.r, (uint32_t)(h0 / 8 + q))) =
                 make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
+        if (relu_mask && net == 0) relu_mask[((r.tile_off >> 14) * 2 + (h0 >> 5)) * 128 + r.r] = mbits;
     }
     __device__ void end(Row&, int64_t, bool) const {}
 };
@@ -568,7 +573,7 @@ __global__ void fc1_tables_kernel(const float* __restrict__ w_on, const float* _
 }
 
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
-                    float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, void* scratch,
+                    float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, uint32_t* relu_mask, void* scratch,
                     int64_t scratch_bytes, cudaStream_t s) {
     // scratch: packed W (128 x Kpad bf16) | tab_act | tab_id
     const int D_in = d_in_of(d);
@@ -601,7 +606,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
         P.a_img_out = obs_img_out;
         tc::Fc1TiEpi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb,
                          reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
-                         d->obs_last_action, n_tiles, R};
+                         d->obs_last_action, n_tiles, R, relu_mask};
         return tc::launch_tc_gemm(P, epi, s);
     }
     tc::Fc1Epi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb, x_on, x_tg,
