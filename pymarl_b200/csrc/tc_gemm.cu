@@ -514,6 +514,235 @@ int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
     return PMB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fc1 for both nets as a STREAMING kernel (obs is 70 % of the learner step's HBM bytes)
+// ------------------------------------------------------------------------------------------
+// The generic kernel above feeds A through eight producer warps that load 8 bytes per lane (obs rows are 4-byte
+// aligned only: 285 floats) and convert synchronously, chunk by chunk: ~28 % of the HBM ceiling (ncu, profiles/).
+// Here the copy engine does the streaming:
+//   producer warp : walks the rows of a 16-row group (time-major tile order: a group is 1-2 contiguous runs of
+//                   [B,T,N,O] memory, one per episode), issues ONE cp.async.bulk per run for its 16-byte-aligned
+//                   interior and 4-byte cp.async for the <= 3 floats of head and tail, into a ring of fp32 staging
+//                   slots (never reads outside the run).  3 slots x 18 KB in flight per SM.
+//   8 converter warps : fp32 staging -> bf16 K-major/128B-swizzle A tile (all k-chunks of the tile, 80 KB).
+//   MMA thread    : W (both nets, 128 columns, all chunks) stays resident; 4 tcgen05.mma per chunk, 2 TMEM buffers.
+//   store thread  : the finished A tile IS the obs tile image the weight-gradient kernel wants: one 80 KB bulk store.
+//   4 epilogue warps : Fc1TiEpi (one-hot gathers, bias, ReLU, bf16 x tile images of both nets, ReLU bit mask).
+namespace fs {
+constexpr int MAX_CHUNKS = 5;
+constexpr int GROUP_ROWS = 16, GROUPS = BM / GROUP_ROWS;
+constexpr int N_SLOTS = 3;
+constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, STORE_W = 6, FIRST_CONV_W = 7, N_CONV = 8;
+constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);       // 480
+constexpr int N_FIX_LANES = 6;                              // lanes 1-3 head floats, 4-6 tail floats
+}  // namespace fs
+
+struct Fc1StreamParams {
+    const float* obs; int64_t obs_sb;
+    const __nv_bfloat16* Wp;       // packed [chunk][128 x 128 B]
+    uint8_t* obs_img;              // optional [T*n_tiles][n_chunks][16 KB]
+    int64_t R;
+    int T, N, O, n_tiles, n_chunks, slot_bytes;
+};
+
+__global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamParams P, Fc1TiEpi epi) {
+    using namespace fs;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tile_bytes = P.n_chunks * A_STAGE_BYTES;
+    uint8_t* w_s = smem;                                    // [n_chunks][16 KB]
+    uint8_t* a_s = smem + tile_bytes;                       // [n_chunks][16 KB]
+    uint8_t* stage = a_s + tile_bytes;                      // [N_SLOTS][slot_bytes]
+    int* rowoff = reinterpret_cast<int*>(stage + N_SLOTS * P.slot_bytes);   // [N_SLOTS][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rowoff + N_SLOTS * GROUP_ROWS);
+    uint64_t* w_full = bars;
+    uint64_t* st_full = bars + 1;            // [N_SLOTS]
+    uint64_t* st_empty = st_full + N_SLOTS;  // [N_SLOTS]
+    uint64_t* a_full = st_empty + N_SLOTS;
+    uint64_t* a_free = a_full + 1;
+    uint64_t* tfull = a_free + 1;            // [2]
+    uint64_t* tempty = tfull + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < N_SLOTS; ++i) { mbar_init(&st_full[i], 1 + N_FIX_LANES); mbar_init(&st_empty[i], N_CONV); }
+        mbar_init(a_full, N_CONV); mbar_init(a_free, 2);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], N_EPI); }
+        fence_barrier_init();
+    }
+    if (warp == MMA_W) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_items = (int64_t)P.T * P.n_tiles;
+
+    if (warp == PROD_W) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, (uint32_t)tile_bytes);
+            bulk_copy_g2s(w_s, P.Wp, (uint32_t)tile_bytes, w_full);
+        }
+        uint32_t git = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
+            for (int g = 0; g < GROUPS; ++g, ++git) {
+                const int slot = git % N_SLOTS;
+                mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
+                uint8_t* sl = stage + slot * P.slot_bytes;
+                int* ro = rowoff + slot * GROUP_ROWS;
+                const int64_t p0 = tile * BM + g * GROUP_ROWS;
+                uint32_t cur = 0, tx = 0;
+                int lr = 0;
+                while (lr < GROUP_ROWS) {                    // uniform across the warp
+                    const int64_t p = p0 + lr;
+                    if (p >= P.R) break;
+                    const int64_t b = p / P.N;
+                    const int n0 = (int)(p - b * P.N);
+                    int cnt = P.N - n0;
+                    if (cnt > GROUP_ROWS - lr) cnt = GROUP_ROWS - lr;
+                    if ((int64_t)cnt > P.R - p) cnt = (int)(P.R - p);
+                    const char* ga = reinterpret_cast<const char*>(P.obs + b * P.obs_sb + (t * P.N + n0) * (int64_t)P.O);
+                    const uint32_t bytes = (uint32_t)cnt * P.O * 4u;
+                    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
+                    cur = ((cur + 15u) & ~15u) + phase;
+                    if (lane < cnt) ro[lr + lane] = (int)(cur + (uint32_t)lane * P.O * 4u);
+                    // [ga, ga+bytes) = head (< 16 B) | 16-byte aligned interior | tail (< 16 B)
+                    uint32_t h_end = (16u - phase) & 15u;                      // bytes before the first aligned address
+                    if (h_end > bytes) h_end = bytes;
+                    uint32_t t_beg = (phase + bytes) & ~15u;                   // offset (from ga - phase) of the last aligned address
+                    t_beg = t_beg > phase ? t_beg - phase : 0u;
+                    if (t_beg < h_end) t_beg = h_end;
+                    if (t_beg > h_end) {
+                        if (lane == 0) bulk_copy_g2s(sl + cur + h_end, ga + h_end, t_beg - h_end, &st_full[slot]);
+                        tx += t_beg - h_end;
+                    }
+                    if (lane >= 1 && lane <= 3) {
+                        const uint32_t o = (uint32_t)(lane - 1) * 4u;
+                        if (o < h_end)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
+                    } else if (lane >= 4 && lane <= 6) {
+                        const uint32_t o = t_beg + (uint32_t)(lane - 4) * 4u;
+                        if (o < bytes)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
+                    }
+                    cur += bytes;
+                    lr += cnt;
+                }
+                if (lane >= lr && lane < GROUP_ROWS) ro[lane] = -1;           // rows beyond R: zeros
+                __syncwarp();
+                if (lane == 0) {
+                    if (tx) mbar_arrive_expect_tx(&st_full[slot], tx); else mbar_arrive(&st_full[slot]);
+                } else if (lane <= N_FIX_LANES) {
+                    // arrives when all earlier cp.async of this lane have landed (does not change the expected count)
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&st_full[slot])) : "memory");
+                }
+            }
+        }
+    } else if (warp >= FIRST_CONV_W) {
+        // ===== converters: warp cw owns rows 2cw, 2cw+1 of every group =====
+        const int cw = warp - FIRST_CONV_W;
+        uint32_t git = 0, ti = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+            mbar_wait(a_free, (ti & 1) ^ 1);                 // MMAs and the image store of the previous tile are done with A
+            for (int g = 0; g < GROUPS; ++g, ++git) {
+                const int slot = git % N_SLOTS;
+                mbar_wait(&st_full[slot], (git / N_SLOTS) & 1);
+                const uint8_t* sl = stage + slot * P.slot_bytes;
+                const int* ro = rowoff + slot * GROUP_ROWS;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int lr = 2 * cw + rr;
+                    const int off = ro[lr];
+                    const float* src = reinterpret_cast<const float*>(sl + (off < 0 ? 0 : off));
+                    const uint32_t rt = (uint32_t)(g * GROUP_ROWS + lr);
+                    for (int c = 0; c < P.n_chunks; ++c) {
+                        const int k = c * BK + 2 * lane;
+                        float v0 = 0.f, v1 = 0.f;
+                        if (off >= 0) {
+                            if (k < P.O) v0 = src[k];
+                            if (k + 1 < P.O) v1 = src[k + 1];
+                        }
+                        *reinterpret_cast<uint32_t*>(a_s + c * A_STAGE_BYTES + sw128_offset(rt, (uint32_t)(lane >> 2)) +
+                                                     (lane & 3) * 4) = pack_bf16x2(v0, v1);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&st_empty[slot]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    } else if (warp == MMA_W) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(BM, 128, 0, 0);
+            mbar_wait(w_full, 0);
+            uint32_t ti = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+                const int b = ti & 1;
+                mbar_wait(a_full, ti & 1);
+                mbar_wait(&tempty[b], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tm = tmem_base + 128u * b;
+                for (int c = 0; c < P.n_chunks; ++c) {
+                    const uint32_t a_addr = smem_u32(a_s + c * A_STAGE_BYTES), w_addr = smem_u32(w_s + c * A_STAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk)
+                        umma_bf16(tm, umma_desc_sw128(a_addr + kk * 32, 16, 1024), umma_desc_sw128(w_addr + kk * 32, 16, 1024),
+                                  idesc, (c | kk) != 0);
+                }
+                umma_commit(a_free);
+                umma_commit(&tfull[b]);
+            }
+        }
+    } else if (warp == STORE_W) {
+        if (lane == 0) {
+            uint32_t ti = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+                mbar_wait(a_full, ti & 1);
+                if (P.obs_img) {
+                    bulk_copy_s2g(P.obs_img + item * tile_bytes, a_s, (uint32_t)tile_bytes);
+                    bulk_commit_group();
+                    bulk_wait_group_read<0>();
+                }
+                mbar_arrive(a_free);
+            }
+            bulk_wait_group<0>();
+        }
+    } else {
+        // ===== epilogue =====
+        uint32_t ti = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
+            const int b = ti & 1;
+            const int64_t m = item * BM + warp * 32 + lane;
+            Fc1TiEpi::Row row;
+            epi.begin(row, m, true);
+            mbar_wait(&tfull[b], (ti >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + 128u * b + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int g = 0; g < 128; g += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + g, v);
+                tmem_wait_ld();
+                epi.cols(row, m, true, g, v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[b]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_W) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------
@@ -607,6 +836,21 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
         tc::Fc1TiEpi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb,
                          reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
                          d->obs_last_action, n_tiles, R, relu_mask};
+        const int n_chunks = (d->O + tc::BK - 1) / tc::BK;
+        const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 512, 128);
+        const int64_t smem_need = 1024 + 2 * (int64_t)n_chunks * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes +
+                                  tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
+        if (t0 == 0 && n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
+            tc::Fc1StreamParams Q;
+            Q.obs = b->obs; Q.obs_sb = b->obs_sb; Q.Wp = wp; Q.obs_img = obs_img_out; Q.R = R;
+            Q.T = nt; Q.N = d->N; Q.O = d->O; Q.n_tiles = n_tiles; Q.n_chunks = n_chunks; Q.slot_bytes = slot_bytes;
+            PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+            const int64_t n_items = (int64_t)nt * n_tiles;
+            const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
+            tc::fc1_stream_kernel<<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q, epi);
+            PMB_LAUNCH_CHECK("fc1_stream_kernel");
+            return PMB_OK;
+        }
         return tc::launch_tc_gemm(P, epi, s);
     }
     tc::Fc1Epi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb, x_on, x_tg,
