@@ -13,6 +13,7 @@
 // 4 TMEM allocator + single-thread tcgen05.mma issuer, 5 W bulk-copy issuer, 6-13 A producers.
 // Pipelines: 4 shared-memory stages (full/empty mbarriers), 2 accumulator buffers (tmem_full/tmem_empty).
 // Persistent over 128-row tiles: grid = min(#tiles, #SMs).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mixer_tc.cuh"
@@ -533,8 +534,8 @@ namespace fs {
 constexpr int MAX_CHUNKS = 5;
 constexpr int GROUP_ROWS = 16, GROUPS = BM / GROUP_ROWS;
 constexpr int N_SLOTS = 3;
-constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, STORE_W = 6, FIRST_CONV_W = 7, N_CONV = 8;
-constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);       // 480
+constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_PROD = 2, STORE_W = 7, FIRST_CONV_W = 8, N_CONV = 8;
+constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);       // 512
 constexpr int N_FIX_LANES = 6;                              // lanes 1-3 head floats, 4-6 tail floats
 }  // namespace fs
 
@@ -544,9 +545,30 @@ struct Fc1StreamParams {
     uint8_t* obs_img;              // optional [T*n_tiles][n_chunks][16 KB]
     int64_t R;
     int T, N, O, n_tiles, n_chunks, slot_bytes;
+    // fold_id: the K padding of the last chunk carries one-hot(agent id) in columns O .. O+N-1 and 1.0 in column O+N;
+    // the packed W holds the agent-id columns of fc1.weight and fc1.bias there, so the tensor core adds them.
+    int fold_id;
+    // epilogue
+    const uint4* tab_act16;        // bf16 [A][net 2][64]: fc1.weight[:, O + a] of both nets
+    const float* tab_id;           // fp32 [net 2][N][64] (used when !fold_id): W_id[:, n] + b1
+    const int64_t* actions; int64_t actions_sb;
+    const int64_t* filled;  int64_t filled_sb;
+    uint8_t* x_on; uint8_t* x_tg;  // tile images [T][n_tiles][16 KB]
+    uint32_t* relu_mask;           // [T][n_tiles][2][128]
+    int use_act;
+    int dbg;                       // timing experiments only (PMB_FC1_DBG): 2 = skip epilogue work, 4 = skip conversion
 };
 
-__global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamParams P, Fc1TiEpi epi) {
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamParams P) {
     using namespace fs;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -554,8 +576,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
     uint8_t* w_s = smem;                                    // [n_chunks][16 KB]
     uint8_t* a_s = smem + tile_bytes;                       // [n_chunks][16 KB]
     uint8_t* stage = a_s + tile_bytes;                      // [N_SLOTS][slot_bytes]
-    int* rowoff = reinterpret_cast<int*>(stage + N_SLOTS * P.slot_bytes);   // [N_SLOTS][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rowoff + N_SLOTS * GROUP_ROWS);
+    int* rowoff = reinterpret_cast<int*>(stage + N_SLOTS * P.slot_bytes);   // [N_SLOTS][16] byte offset of a row in its slot
+    int* rown = rowoff + N_SLOTS * GROUP_ROWS;                              // [N_SLOTS][16] agent index of the row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rown + N_SLOTS * GROUP_ROWS);
     uint64_t* w_full = bars;
     uint64_t* st_full = bars + 1;            // [N_SLOTS]
     uint64_t* st_empty = st_full + N_SLOTS;  // [N_SLOTS]
@@ -580,26 +603,54 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_items = (int64_t)P.T * P.n_tiles;
 
-    if (warp == PROD_W) {
-        if (lane == 0) {
+    if (warp >= PROD_W && warp < PROD_W + N_PROD) {
+        // two producer warps take alternate groups: the address walk of ONE warp (dependent integer code) capped the
+        // stream at 2.9 TB/s
+        const int pw = warp - PROD_W;
+        if (pw == 0 && lane == 0) {
             mbar_arrive_expect_tx(w_full, (uint32_t)tile_bytes);
             bulk_copy_g2s(w_s, P.Wp, (uint32_t)tile_bytes, w_full);
         }
+        // L2 prefetch of the runs of a whole tile (lane l takes the l-th episode of the tile): issued PF_AHEAD tiles ahead
+        // so that the staging ring (3 x 18 KB, all the shared memory that is left) sees L2 latency, not HBM latency.
+        auto prefetch_tile = [&](int64_t item) {
+            if (item >= n_items) return;
+            const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
+            const int64_t p0 = tile * BM;
+            int64_t p1 = p0 + BM;
+            if (p1 > P.R) p1 = P.R;
+            const int64_t b0 = p0 / P.N;
+            for (int64_t b = b0 + lane; b * P.N < p1; b += 32) {
+                const int64_t ps = b * P.N > p0 ? b * P.N : p0;
+                const int64_t pe = (b + 1) * P.N < p1 ? (b + 1) * P.N : p1;
+                const char* ga = reinterpret_cast<const char*>(P.obs + b * P.obs_sb + (t * P.N + (ps - b * P.N)) * (int64_t)P.O);
+                const uintptr_t a0 = (reinterpret_cast<uintptr_t>(ga) + 15) & ~(uintptr_t)15;
+                const uintptr_t a1 = (reinterpret_cast<uintptr_t>(ga) + (uint64_t)(pe - ps) * P.O * 4) & ~(uintptr_t)15;
+                if (a1 > a0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+            }
+        };
+        constexpr int PF_AHEAD = 2;
+        if (pw == 0 && (P.dbg & 8))
+            for (int k = 0; k < PF_AHEAD; ++k) prefetch_tile((int64_t)blockIdx.x + (int64_t)k * gridDim.x);
         uint32_t git = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
+            if (pw == 0 && (P.dbg & 8)) prefetch_tile(item + (int64_t)PF_AHEAD * gridDim.x);
             for (int g = 0; g < GROUPS; ++g, ++git) {
+                if ((g & (N_PROD - 1)) != pw) continue;
                 const int slot = git % N_SLOTS;
                 mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
                 uint8_t* sl = stage + slot * P.slot_bytes;
                 int* ro = rowoff + slot * GROUP_ROWS;
+                int* rn = rown + slot * GROUP_ROWS;
                 const int64_t p0 = tile * BM + g * GROUP_ROWS;
                 uint32_t cur = 0, tx = 0;
                 int lr = 0;
                 while (lr < GROUP_ROWS) {                    // uniform across the warp
                     const int64_t p = p0 + lr;
                     if (p >= P.R) break;
-                    const int64_t b = p / P.N;
+                    const int64_t b = (int64_t)((uint32_t)p / (uint32_t)P.N);     // B*N < 2^31 (validated on the host)
                     const int n0 = (int)(p - b * P.N);
                     int cnt = P.N - n0;
                     if (cnt > GROUP_ROWS - lr) cnt = GROUP_ROWS - lr;
@@ -608,7 +659,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     const uint32_t bytes = (uint32_t)cnt * P.O * 4u;
                     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
                     cur = ((cur + 15u) & ~15u) + phase;
-                    if (lane < cnt) ro[lr + lane] = (int)(cur + (uint32_t)lane * P.O * 4u);
+                    if (lane < cnt) { ro[lr + lane] = (int)(cur + (uint32_t)lane * P.O * 4u); rn[lr + lane] = n0 + lane; }
                     // [ga, ga+bytes) = head (< 16 B) | 16-byte aligned interior | tail (< 16 B)
                     uint32_t h_end = (16u - phase) & 15u;                      // bytes before the first aligned address
                     if (h_end > bytes) h_end = bytes;
@@ -642,31 +693,59 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             }
         }
     } else if (warp >= FIRST_CONV_W) {
-        // ===== converters: warp cw owns rows 2cw, 2cw+1 of every group =====
+        // ===== converters: warp cw owns rows 2cw, 2cw+1 of every group.  Everything that does not depend on the row
+        // (which of a lane's two columns per chunk exist, where the one-hot padding columns are) is hoisted: the
+        // first version spent ~2400 cycles per group in a serial chain of predicate / address arithmetic. =====
         const int cw = warp - FIRST_CONV_W;
+        uint32_t ok0 = 0, ok1 = 0;                            // bit c: column 64c + 2 lane (+1) < O
+#pragma unroll
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+            if (c < P.n_chunks && c * BK + 2 * lane < P.O) ok0 |= 1u << c;
+            if (c < P.n_chunks && c * BK + 2 * lane + 1 < P.O) ok1 |= 1u << c;
+        }
+        const int c_last = P.n_chunks - 1;
+        const int j_pad = c_last * BK + 2 * lane - P.O;       // index of this lane's first column in the K padding
+        const uint32_t a_base = smem_u32(a_s) + ((uint32_t)(lane >> 2) << 4) + (lane & 3) * 4;   // + row*128, ^ swizzle
         uint32_t git = 0, ti = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
             mbar_wait(a_free, (ti & 1) ^ 1);                 // MMAs and the image store of the previous tile are done with A
             for (int g = 0; g < GROUPS; ++g, ++git) {
                 const int slot = git % N_SLOTS;
                 mbar_wait(&st_full[slot], (git / N_SLOTS) & 1);
-                const uint8_t* sl = stage + slot * P.slot_bytes;
-                const int* ro = rowoff + slot * GROUP_ROWS;
+                const uint32_t sl = smem_u32(stage + slot * P.slot_bytes) + 8u * lane;
+                const int2 off2 = *reinterpret_cast<const int2*>(rowoff + slot * GROUP_ROWS + 2 * cw);
+                const int2 nn2 = *reinterpret_cast<const int2*>(rown + slot * GROUP_ROWS + 2 * cw);
+                float v0[2][MAX_CHUNKS], v1[2][MAX_CHUNKS];
+                if (!(P.dbg & 4)) {
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int lr = 2 * cw + rr;
-                    const int off = ro[lr];
-                    const float* src = reinterpret_cast<const float*>(sl + (off < 0 ? 0 : off));
-                    const uint32_t rt = (uint32_t)(g * GROUP_ROWS + lr);
-                    for (int c = 0; c < P.n_chunks; ++c) {
-                        const int k = c * BK + 2 * lane;
-                        float v0 = 0.f, v1 = 0.f;
-                        if (off >= 0) {
-                            if (k < P.O) v0 = src[k];
-                            if (k + 1 < P.O) v1 = src[k + 1];
+                    for (int rr = 0; rr < 2; ++rr) {             // all 20 loads first
+                        const int off = rr ? off2.y : off2.x;
+                        const uint32_t src = sl + (uint32_t)(off < 0 ? 0 : off);
+                        const uint32_t m0 = off < 0 ? 0u : ok0, m1 = off < 0 ? 0u : ok1;
+#pragma unroll
+                        for (int c = 0; c < MAX_CHUNKS; ++c) {
+                            v0[rr][c] = 0.f; v1[rr][c] = 0.f;
+                            if ((m0 >> c) & 1u) v0[rr][c] = lds_f32(src + c * 256);
+                            if ((m1 >> c) & 1u) v1[rr][c] = lds_f32(src + c * 256 + 4);
                         }
-                        *reinterpret_cast<uint32_t*>(a_s + c * A_STAGE_BYTES + sw128_offset(rt, (uint32_t)(lane >> 2)) +
-                                                     (lane & 3) * 4) = pack_bf16x2(v0, v1);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int off = rr ? off2.y : off2.x;
+                        const int nn = rr ? nn2.y : nn2.x;
+                        const uint32_t rt = (uint32_t)(g * GROUP_ROWS + 2 * cw + rr);
+                        const uint32_t dst = (a_base + rt * 128u) ^ ((rt & 7u) << 4);
+                        // one-hot(agent) and the bias column live in the K padding of the last chunk
+                        const bool fold = P.fold_id && off >= 0;
+                        const bool hit0 = fold && j_pad >= 0 && (j_pad == nn || j_pad == P.N);
+                        const bool hit1 = fold && j_pad + 1 >= 0 && (j_pad + 1 == nn || j_pad + 1 == P.N);
+#pragma unroll
+                        for (int c = 0; c < MAX_CHUNKS; ++c)
+                            if (c < P.n_chunks) {
+                                float a = v0[rr][c], b = v1[rr][c];
+                                if (c == c_last) { a = hit0 ? 1.0f : a; b = hit1 ? 1.0f : b; }
+                                sts_b32(dst + c * A_STAGE_BYTES, pack_bf16x2(a, b));
+                            }
                     }
                 }
                 __syncwarp();
@@ -713,26 +792,76 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             bulk_wait_group<0>();
         }
     } else {
-        // ===== epilogue =====
+        // ===== epilogue: one row per thread; x = relu(acc [+ id/bias table] + act table) -> bf16 tile images + mask =====
+        const uint32_t r = (uint32_t)(warp * 32 + lane);
+        // the previous action of a row, fetched one item ahead (-1: none / step not filled, -2: padding row)
+        auto fetch_prev = [&](int64_t item, int& n_out) {
+            n_out = 0;
+            if (item >= n_items) return -2;
+            const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
+            const int64_t p = tile * BM + r;
+            if (p >= P.R) return -2;
+            const int64_t b = p / P.N;
+            n_out = (int)(p - b * P.N);
+            if (!P.use_act || t == 0) return -1;
+            const int64_t f = __ldg(P.filled + b * P.filled_sb + (t - 1));
+            const int a = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + n_out);
+            return f != 0 ? a : -1;
+        };
+        int n_cur, n_nxt;
+        int a_prev = fetch_prev(blockIdx.x, n_cur);
         uint32_t ti = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
             const int b = ti & 1;
-            const int64_t m = item * BM + warp * 32 + lane;
-            Fc1TiEpi::Row row;
-            epi.begin(row, m, true);
+            const int a_next = fetch_prev(item + gridDim.x, n_nxt);
             mbar_wait(&tfull[b], (ti >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + 128u * b + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-            for (int g = 0; g < 128; g += 32) {
+            for (int g = 0; g < 4; ++g) {                      // 32 accumulator columns: net = g / 2, h0 = 32 (g & 1)
                 uint32_t v[32];
-                tmem_ld_32x32(taddr + g, v);
+                tmem_ld_32x32(taddr + 32 * g, v);
                 tmem_wait_ld();
-                epi.cols(row, m, true, g, v);
+                if (a_prev != -2 && !(P.dbg & 2)) {
+                    const int net = g >> 1, h0 = (g & 1) * 32;
+                    uint8_t* tile_img = (net ? P.x_tg : P.x_on) + item * A_STAGE_BYTES;
+                    const uint4* tac = a_prev >= 0 ? P.tab_act16 + ((int64_t)a_prev * 2 + net) * 8 + (h0 >> 3) : nullptr;
+                    const float4* tid = P.fold_id ? nullptr
+                                                  : reinterpret_cast<const float4*>(P.tab_id + ((int64_t)net * P.N + n_cur) * 64 + h0);
+                    uint32_t mbits = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {              // 8 columns = one 16-byte chunk
+                        float o[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(v[8 * q + k]);
+                        if (tac) {
+                            const uint4 w = __ldg(tac + q);
+                            o[0] += __uint_as_float(w.x << 16); o[1] += __uint_as_float(w.x & 0xffff0000u);
+                            o[2] += __uint_as_float(w.y << 16); o[3] += __uint_as_float(w.y & 0xffff0000u);
+                            o[4] += __uint_as_float(w.z << 16); o[5] += __uint_as_float(w.z & 0xffff0000u);
+                            o[6] += __uint_as_float(w.w << 16); o[7] += __uint_as_float(w.w & 0xffff0000u);
+                        }
+                        if (tid) {
+                            const float4 b0 = __ldg(tid + 2 * q), b1 = __ldg(tid + 2 * q + 1);
+                            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+                            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            o[k] = fmaxf(o[k], 0.f);
+                            mbits |= (o[k] > 0.f ? 1u : 0u) << (8 * q + k);
+                        }
+                        *reinterpret_cast<uint4*>(tile_img + sw128_offset(r, (uint32_t)(h0 / 8 + q))) =
+                            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                       pack_bf16x2(o[6], o[7]));
+                    }
+                    if (P.relu_mask && net == 0) P.relu_mask[(item * 2 + (h0 >> 5)) * 128 + r] = mbits;
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);
+            a_prev = a_next; n_cur = n_nxt;
         }
     }
     tc_fence_before();
@@ -801,6 +930,50 @@ __global__ void fc1_tables_kernel(const float* __restrict__ w_on, const float* _
     }
 }
 
+int64_t tc_fc1_scratch_bytes(const pmb_dims* d);
+
+// streaming fc1: packed W with the agent-id columns and the bias folded into the K padding (fold_id), and the
+// last-action table of both nets as bf16 [A][net][64]
+__global__ void fc1_stream_pack_kernel(const float* __restrict__ w_on, const float* __restrict__ b_on,
+                                       const float* __restrict__ w_tg, const float* __restrict__ b_tg, int O, int A, int N,
+                                       int D_in, int use_act, int use_id, int fold_id, int n_chunks,
+                                       __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ tab_act16) {
+    const int64_t n_w = (int64_t)128 * n_chunks * 8;          // one thread per 16-byte chunk of the packed image
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_w) {
+        const int j = (int)(i & 7);
+        const int col = (int)((i >> 3) & 127);
+        const int c = (int)(i >> 10);
+        const int net = col >> 6, h = col & 63;
+        const float* w = (net ? w_tg : w_on) + (int64_t)h * D_in;
+        const float bias = (net ? b_tg : b_on)[h];
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = c * 64 + j * 8 + e;
+            float v = 0.f;
+            if (k < O) v = w[k];
+            else if (fold_id) {
+                const int q = k - O;
+                if (q < N) v = use_id ? w[O + (use_act ? A : 0) + q] : 0.f;
+                else if (q == N) v = bias;
+            }
+            f[e] = v;
+        }
+        char* tile = reinterpret_cast<char*>(wp) + (int64_t)c * 16384;
+        *reinterpret_cast<uint4*>(tile + tc::sw128_offset((uint32_t)col, (uint32_t)j)) =
+            make_uint4(tc::pack_bf16x2(f[0], f[1]), tc::pack_bf16x2(f[2], f[3]), tc::pack_bf16x2(f[4], f[5]),
+                       tc::pack_bf16x2(f[6], f[7]));
+        return;
+    }
+    i -= n_w;
+    if (i < (int64_t)A * 128) {
+        const int a = (int)(i >> 7), net = (int)((i >> 6) & 1), h = (int)(i & 63);
+        const float* w = net ? w_tg : w_on;
+        tab_act16[i] = __float2bfloat16(use_act ? w[(int64_t)h * D_in + O + a] : 0.f);
+    }
+}
+
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
                     float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, uint32_t* relu_mask, void* scratch,
                     int64_t scratch_bytes, cudaStream_t s) {
@@ -809,7 +982,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     int64_t wp_bytes = align_up(tc_packed_elems(128, d->O) * 2, 256);
     int64_t ta_bytes = align_up((int64_t)2 * d->A * 64 * 4, 256);
     int64_t ti_bytes = align_up((int64_t)2 * d->N * 64 * 4, 256);
-    if (scratch_bytes < wp_bytes + ta_bytes + ti_bytes) { set_error("tc_fc1: scratch too small"); return PMB_ERR_WORKSPACE; }
+    if (scratch_bytes < tc_fc1_scratch_bytes(d)) { set_error("tc_fc1: scratch too small"); return PMB_ERR_WORKSPACE; }
     __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
     float* tab_act = reinterpret_cast<float*>(static_cast<char*>(scratch) + wp_bytes);
     float* tab_id = reinterpret_cast<float*>(static_cast<char*>(scratch) + wp_bytes + ta_bytes);
@@ -839,15 +1012,28 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
         const int n_chunks = (d->O + tc::BK - 1) / tc::BK;
         const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 512, 128);
         const int64_t smem_need = 1024 + 2 * (int64_t)n_chunks * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes +
-                                  tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
+                                  2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
         if (t0 == 0 && n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
+            const int fold_id = n_chunks * tc::BK - d->O >= d->N + 1;
+            __nv_bfloat16* tab_act16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(scratch) + wp_bytes + ta_bytes + ti_bytes);
+            const int64_t n_pack = (int64_t)128 * n_chunks * 8 + (int64_t)d->A * 128;
+            fc1_stream_pack_kernel<<<(unsigned)ceil_div(n_pack, 256), 256, 0, s>>>(
+                on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A, d->N, D_in, d->obs_last_action, d->obs_agent_id, fold_id,
+                n_chunks, wp, tab_act16);
+            PMB_LAUNCH_CHECK("fc1_stream_pack_kernel");
             tc::Fc1StreamParams Q;
             Q.obs = b->obs; Q.obs_sb = b->obs_sb; Q.Wp = wp; Q.obs_img = obs_img_out; Q.R = R;
             Q.T = nt; Q.N = d->N; Q.O = d->O; Q.n_tiles = n_tiles; Q.n_chunks = n_chunks; Q.slot_bytes = slot_bytes;
+            Q.fold_id = fold_id; Q.tab_act16 = reinterpret_cast<const uint4*>(tab_act16); Q.tab_id = tab_id;
+            Q.actions = b->actions; Q.actions_sb = b->actions_sb; Q.filled = b->filled; Q.filled_sb = b->filled_sb;
+            Q.x_on = reinterpret_cast<uint8_t*>(x_on); Q.x_tg = reinterpret_cast<uint8_t*>(x_tg);
+            Q.relu_mask = relu_mask; Q.use_act = d->obs_last_action;
+            Q.dbg = getenv("PMB_FC1_DBG") ? atoi(getenv("PMB_FC1_DBG")) : 0;
+            if (Q.dbg & 1) Q.obs_img = nullptr;
             PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
             const int64_t n_items = (int64_t)nt * n_tiles;
             const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
-            tc::fc1_stream_kernel<<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q, epi);
+            tc::fc1_stream_kernel<<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q);
             PMB_LAUNCH_CHECK("fc1_stream_kernel");
             return PMB_OK;
         }
@@ -859,7 +1045,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
 }
 int64_t tc_fc1_scratch_bytes(const pmb_dims* d) {
     return align_up(tc_packed_elems(128, d->O) * 2, 256) + align_up((int64_t)2 * d->A * 64 * 4, 256) +
-           align_up((int64_t)2 * d->N * 64 * 4, 256);
+           align_up((int64_t)2 * d->N * 64 * 4, 256) + align_up((int64_t)d->A * 128 * 2, 256);
 }
 
 // permuted bias for the mixer: packed order [w1 | b1 | w_final | v0] from flat order [w1 | w_final | b1 | v0]
