@@ -40,6 +40,15 @@ __device__ __forceinline__ void ld_tmem_16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void ld_tmem_8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void lds_v4(uint32_t addr, float (&v)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
 // 16 fp32 values (columns 16*c16 .. +15 of row r) -> two 16-byte chunks of a tile image
 __device__ __forceinline__ void st_row16(uint8_t* tile, uint32_t r, int c16, const float (&f)[16]) {
     uint4 a = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -61,8 +70,8 @@ constexpr int ST = HT + 2 * TILE_BYTES2;           // [4][16 KB]        gate sta
 constexpr int BIAS = ST + 4 * TILE_BYTES2;         // brz[128] | bin[64] | bhn[64]
 constexpr int BARS = BIAS + 1024;
 constexpr int SMEM_BYTES = 1024 + BARS + 256;
-constexpr int N_EPI_WARPS = 8, MMA_WARP = 8, IO_WARP = 9;
-constexpr int THREADS = 320;
+constexpr int N_EPI_WARPS = 16, MMA_WARP = 16, IO_WARP = 17;
+constexpr int THREADS = 576;
 }  // namespace g2
 
 struct GruFwd2Params {
@@ -187,18 +196,20 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
                 }
         }
     } else {
-        // ===== epilogue: 8 warps; warp w owns TMEM lanes 32 (w & 3) .. +31 and hidden columns 32 (w >> 2) .. +31 =====
-        const int q4 = warp & 3, ch = warp >> 2;
+        // ===== epilogue: 16 warps (4 per scheduler, to hide the tcgen05.ld / MUFU / barrier latencies);
+        // warp w owns TMEM lanes 32 (w & 3) .. +31 and hidden columns 16 (w >> 2) .. +15 =====
+        const int q4 = warp & 3, c16 = warp >> 2;
         const uint32_t r = (uint32_t)(q4 * 32 + lane);
-        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 32 * ch;
-        float h[2][32];
+        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 16 * c16;
+        float h[2][16];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[i][j] = 0.f;
+            for (int j = 0; j < 16; ++j) h[i][j] = 0.f;
         bool valid[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) valid[i] = (int64_t)(tile0 + i) * TILE_ROWS2 + r < P.R;
+        const uint32_t bias_s = smem_u32(bias) + 64 * c16;     // this thread's 16 columns of brz | bin | bhn
         uint32_t use = 0;                                      // staging-buffer use counter (all tiles, all steps)
         for (int t = 0; t < P.nt; ++t) {
 #pragma unroll
@@ -211,49 +222,52 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
                     ++use;
                     tc_fence_after();
                     uint8_t* hti = smem + HT + i * TILE_BYTES2;
+                    const uint32_t ta = tlane + 256 * i;
 #pragma unroll
-                    for (int sc = 0; sc < 2; ++sc) {
-                        uint32_t ar[16], az[16], ain[16], ahn[16];
-                        const uint32_t ta = tlane + 256 * i + 16 * sc;
-                        ld_tmem_16(ta, ar);
-                        ld_tmem_16(ta + 64, az);
-                        ld_tmem_16(ta + 128, ain);
-                        ld_tmem_16(ta + 192, ahn);
+                    for (int hf = 0; hf < 2; ++hf) {             // 8 columns at a time (register budget: 96 / thread)
+                        uint32_t ar[8], az[8], ain[8], ahn[8];
+                        ld_tmem_8(ta + 8 * hf, ar);
+                        ld_tmem_8(ta + 64 + 8 * hf, az);
+                        ld_tmem_8(ta + 128 + 8 * hf, ain);
+                        ld_tmem_8(ta + 192 + 8 * hf, ahn);
+                        float br[8], bz[8], bn[8], bh[8];
+                        lds_v4(bias_s + 32 * hf, *reinterpret_cast<float(*)[4]>(&br[0]));
+                        lds_v4(bias_s + 32 * hf + 16, *reinterpret_cast<float(*)[4]>(&br[4]));
+                        lds_v4(bias_s + 256 + 32 * hf, *reinterpret_cast<float(*)[4]>(&bz[0]));
+                        lds_v4(bias_s + 256 + 32 * hf + 16, *reinterpret_cast<float(*)[4]>(&bz[4]));
+                        lds_v4(bias_s + 512 + 32 * hf, *reinterpret_cast<float(*)[4]>(&bn[0]));
+                        lds_v4(bias_s + 512 + 32 * hf + 16, *reinterpret_cast<float(*)[4]>(&bn[4]));
+                        lds_v4(bias_s + 768 + 32 * hf, *reinterpret_cast<float(*)[4]>(&bh[0]));
+                        lds_v4(bias_s + 768 + 32 * hf + 16, *reinterpret_cast<float(*)[4]>(&bh[4]));
                         tmem_wait_ld();
-                        float fr[16], fz[16], fn[16], fhn[16], fh[16];
-                        const int c0 = 32 * ch + 16 * sc;
+                        uint32_t pr[4], pz[4], pn[4], phn[4], ph[4];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 b_r = *reinterpret_cast<const float4*>(bias + c0 + 4 * j4);
-                            const float4 b_z = *reinterpret_cast<const float4*>(bias + 64 + c0 + 4 * j4);
-                            const float4 b_n = *reinterpret_cast<const float4*>(bias + 128 + c0 + 4 * j4);
-                            const float4 b_h = *reinterpret_cast<const float4*>(bias + 192 + c0 + 4 * j4);
-                            const float br[4] = {b_r.x, b_r.y, b_r.z, b_r.w}, bz[4] = {b_z.x, b_z.y, b_z.z, b_z.w};
-                            const float bn[4] = {b_n.x, b_n.y, b_n.z, b_n.w}, bh[4] = {b_h.x, b_h.y, b_h.z, b_h.w};
+                        for (int k = 0; k < 4; ++k) {
+                            float vr[2], vz[2], vn[2], vhn[2], vh[2];
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = 4 * j4 + jj;
-                                const float rg = sigmoid_tanh(__uint_as_float(ar[j]) + br[jj]);
-                                const float zg = sigmoid_tanh(__uint_as_float(az[j]) + bz[jj]);
-                                const float hn = __uint_as_float(ahn[j]) + bh[jj];
-                                const float ng = tanh_approx(fmaf(rg, hn, __uint_as_float(ain[j]) + bn[jj]));
-                                float hv = fmaf(zg, h[i][16 * sc + j] - ng, ng);
+                            for (int e = 0; e < 2; ++e) {
+                                const int j = 2 * k + e;
+                                const float rg = sigmoid_tanh(__uint_as_float(ar[j]) + br[j]);
+                                const float zg = sigmoid_tanh(__uint_as_float(az[j]) + bz[j]);
+                                const float hn = __uint_as_float(ahn[j]) + bh[j];
+                                const float ng = tanh_approx(fmaf(rg, hn, __uint_as_float(ain[j]) + bn[j]));
+                                float hv = fmaf(zg, h[i][8 * hf + j] - ng, ng);
                                 if (!valid[i]) hv = 0.f;
-                                h[i][16 * sc + j] = hv;
-                                fr[j] = rg; fz[j] = zg; fn[j] = ng; fhn[j] = hn; fh[j] = hv;
+                                h[i][8 * hf + j] = hv;
+                                vr[e] = rg; vz[e] = zg; vn[e] = ng; vhn[e] = hn; vh[e] = hv;
                             }
+                            pr[k] = pack_bf16x2(vr[0], vr[1]); pz[k] = pack_bf16x2(vz[0], vz[1]);
+                            pn[k] = pack_bf16x2(vn[0], vn[1]); phn[k] = pack_bf16x2(vhn[0], vhn[1]);
+                            ph[k] = pack_bf16x2(vh[0], vh[1]);
                         }
-                        const int c16 = 2 * ch + sc;
-                        st_row16(hti, r, c16, fh);
+                        const uint32_t off = sw128_offset(r, (uint32_t)(2 * c16 + hf));
+                        *reinterpret_cast<uint4*>(hti + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                         if (stash) {
-                            if (!valid[i]) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) { fr[j] = 0.f; fz[j] = 0.f; fn[j] = 0.f; fhn[j] = 0.f; }
-                            }
-                            st_row16(smem + ST, r, c16, fr);
-                            st_row16(smem + ST + TILE_BYTES2, r, c16, fz);
-                            st_row16(smem + ST + 2 * TILE_BYTES2, r, c16, fn);
-                            st_row16(smem + ST + 3 * TILE_BYTES2, r, c16, fhn);
+                            const uint4 zero = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(smem + ST + off) = valid[i] ? make_uint4(pr[0], pr[1], pr[2], pr[3]) : zero;
+                            *reinterpret_cast<uint4*>(smem + ST + TILE_BYTES2 + off) = valid[i] ? make_uint4(pz[0], pz[1], pz[2], pz[3]) : zero;
+                            *reinterpret_cast<uint4*>(smem + ST + 2 * TILE_BYTES2 + off) = valid[i] ? make_uint4(pn[0], pn[1], pn[2], pn[3]) : zero;
+                            *reinterpret_cast<uint4*>(smem + ST + 3 * TILE_BYTES2 + off) = valid[i] ? make_uint4(phn[0], phn[1], phn[2], phn[3]) : zero;
                         }
                     }
                     tc_fence_before();
