@@ -95,9 +95,11 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
     uint64_t* x_full = bars + 1;             // [tile][buf]
     uint64_t* x_empty = bars + 5;            // [tile][buf]
     uint64_t* gates_full = bars + 9;         // [tile]
-    uint64_t* h_ready = bars + 11;           // [tile]  epilogue wrote h (and the gate staging)
-    uint64_t* st_free = bars + 13;           // bulk stores of the previous use finished reading shared memory
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* h_ready = bars + 11;           // [tile]  epilogue wrote the h tile and drained the accumulators
+    uint64_t* ht_free = bars + 13;           // [tile]  the bulk store of the h tile has finished reading it
+    uint64_t* st_ready = bars + 15;          // gate staging written
+    uint64_t* st_free = bars + 16;           // the bulk store of the gate staging has finished reading it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile0 = 2 * blockIdx.x;
@@ -107,8 +109,8 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&gates_full[i], 1); mbar_init(&h_ready[i], N_EPI_WARPS); }
-        mbar_init(st_free, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&gates_full[i], 1); mbar_init(&h_ready[i], N_EPI_WARPS); mbar_init(&ht_free[i], 1); }
+        mbar_init(st_ready, N_EPI_WARPS); mbar_init(st_free, 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -146,17 +148,27 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
                 bulk_copy_s2g(P.h_ti + (int64_t)(tile0 + i) * TILE_BYTES2, smem + HT + i * TILE_BYTES2, TILE_BYTES2);
             bulk_commit_group();
             bulk_wait_group_read<0>();
-            mbar_arrive(st_free);                              // arrival #0: the h_0 stores no longer read the operand tiles
+            for (int i = 0; i < n_my; ++i) mbar_arrive(&ht_free[i]);    // arrival #0: the h_0 stores no longer read HT
+            uint32_t use = 0;
             for (int t = 0; t < P.nt; ++t)
-                for (int i = 0; i < n_my; ++i) {
+                for (int i = 0; i < n_my; ++i, ++use) {
                     mbar_wait(&h_ready[i], (uint32_t)(t & 1));
                     const int64_t tt = (int64_t)t * P.n_tiles + tile0 + i;
                     bulk_copy_s2g(P.h_ti + (tt + P.n_tiles) * TILE_BYTES2, smem + HT + i * TILE_BYTES2, TILE_BYTES2);
-                    if (stash) bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, smem + ST, 4 * TILE_BYTES2);
                     bulk_commit_group();
                     if (t + 2 < P.nt) load_x(i, t + 2);
-                    bulk_wait_group_read<0>();
-                    mbar_arrive(st_free);
+                    if (stash) {
+                        mbar_wait(st_ready, use & 1);
+                        bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, smem + ST, 4 * TILE_BYTES2);
+                        bulk_commit_group();
+                        bulk_wait_group_read<1>();             // the h store (all but the newest group) is done reading
+                        mbar_arrive(&ht_free[i]);
+                        bulk_wait_group_read<0>();
+                        mbar_arrive(st_free);
+                    } else {
+                        bulk_wait_group_read<0>();
+                        mbar_arrive(&ht_free[i]);
+                    }
                 }
             bulk_wait_group<0>();
         }
@@ -216,13 +228,11 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
             for (int i = 0; i < 2; ++i) {
                 if (i < n_my) {
                     mbar_wait(&gates_full[i], (uint32_t)(t & 1));
-                    // the previous use's bulk stores must have finished reading HT / the staging tiles (use k needs
-                    // arrival #k of the IO thread; #0 covers the h_0 stores)
-                    mbar_wait(st_free, use & 1);
-                    ++use;
+                    mbar_wait(&ht_free[i], (uint32_t)(t & 1));   // the store of h_{t-1} (arrival #t) has read HT[i]
                     tc_fence_after();
                     uint8_t* hti = smem + HT + i * TILE_BYTES2;
                     const uint32_t ta = tlane + 256 * i;
+                    uint32_t pr[8], pz[8], pn[8], phn[8];        // packed gates of the 16 columns, kept for the staging write
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {             // 8 columns at a time (register budget: 96 / thread)
                         uint32_t ar[8], az[8], ain[8], ahn[8];
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
                         lds_v4(bias_s + 768 + 32 * hf, *reinterpret_cast<float(*)[4]>(&bh[0]));
                         lds_v4(bias_s + 768 + 32 * hf + 16, *reinterpret_cast<float(*)[4]>(&bh[4]));
                         tmem_wait_ld();
-                        uint32_t pr[4], pz[4], pn[4], phn[4], ph[4];
+                        uint32_t ph[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             float vr[2], vz[2], vn[2], vhn[2], vh[2];
@@ -256,24 +266,39 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
                                 h[i][8 * hf + j] = hv;
                                 vr[e] = rg; vz[e] = zg; vn[e] = ng; vhn[e] = hn; vh[e] = hv;
                             }
-                            pr[k] = pack_bf16x2(vr[0], vr[1]); pz[k] = pack_bf16x2(vz[0], vz[1]);
-                            pn[k] = pack_bf16x2(vn[0], vn[1]); phn[k] = pack_bf16x2(vhn[0], vhn[1]);
+                            pr[4 * hf + k] = pack_bf16x2(vr[0], vr[1]); pz[4 * hf + k] = pack_bf16x2(vz[0], vz[1]);
+                            pn[4 * hf + k] = pack_bf16x2(vn[0], vn[1]); phn[4 * hf + k] = pack_bf16x2(vhn[0], vhn[1]);
                             ph[k] = pack_bf16x2(vh[0], vh[1]);
                         }
-                        const uint32_t off = sw128_offset(r, (uint32_t)(2 * c16 + hf));
-                        *reinterpret_cast<uint4*>(hti + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        if (stash) {
-                            const uint4 zero = make_uint4(0, 0, 0, 0);
-                            *reinterpret_cast<uint4*>(smem + ST + off) = valid[i] ? make_uint4(pr[0], pr[1], pr[2], pr[3]) : zero;
-                            *reinterpret_cast<uint4*>(smem + ST + TILE_BYTES2 + off) = valid[i] ? make_uint4(pz[0], pz[1], pz[2], pz[3]) : zero;
-                            *reinterpret_cast<uint4*>(smem + ST + 2 * TILE_BYTES2 + off) = valid[i] ? make_uint4(pn[0], pn[1], pn[2], pn[3]) : zero;
-                            *reinterpret_cast<uint4*>(smem + ST + 3 * TILE_BYTES2 + off) = valid[i] ? make_uint4(phn[0], phn[1], phn[2], phn[3]) : zero;
-                        }
+                        *reinterpret_cast<uint4*>(hti + sw128_offset(r, (uint32_t)(2 * c16 + hf))) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                     }
+                    // h is in place and the accumulators are drained: the next step's MMAs may start
                     tc_fence_before();
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&h_ready[i]);
+                    if (stash) {
+                        // the gate staging is shared by both tiles: wait until the previous use's store has read it
+                        if (use > 0) mbar_wait(st_free, (use - 1) & 1);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const uint32_t off = sw128_offset(r, (uint32_t)(2 * c16 + hf));
+                            const uint4 zero = make_uint4(0, 0, 0, 0);
+                            const int k0 = 4 * hf;
+                            *reinterpret_cast<uint4*>(smem + ST + off) =
+                                valid[i] ? make_uint4(pr[k0], pr[k0 + 1], pr[k0 + 2], pr[k0 + 3]) : zero;
+                            *reinterpret_cast<uint4*>(smem + ST + TILE_BYTES2 + off) =
+                                valid[i] ? make_uint4(pz[k0], pz[k0 + 1], pz[k0 + 2], pz[k0 + 3]) : zero;
+                            *reinterpret_cast<uint4*>(smem + ST + 2 * TILE_BYTES2 + off) =
+                                valid[i] ? make_uint4(pn[k0], pn[k0 + 1], pn[k0 + 2], pn[k0 + 3]) : zero;
+                            *reinterpret_cast<uint4*>(smem + ST + 3 * TILE_BYTES2 + off) =
+                                valid[i] ? make_uint4(phn[k0], phn[k0 + 1], phn[k0 + 2], phn[k0 + 3]) : zero;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(st_ready);
+                    }
+                    ++use;
                 }
             }
         }
