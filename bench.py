@@ -51,10 +51,38 @@ def load_peaks():
 # algorithmic work per phase: (FLOPs, HBM bytes) of one launch
 # ------------------------------------------------------------------------------------------
 def phase_work(name, B, T, N, O, S, A, H, E, mixer):
+    """(FLOPs, HBM bytes) one launch of a phase has to do.  bf16-tier phases end in _tc:
+    their activations are bf16 tile images (128 B per row of 64 columns)."""
     rows = B * T * N
     M = B * (T - 1)
+    BT = B * T
     C = (N + 3) * E
     f4 = 4
+    ko = -(-O // 64) * 64                      # obs image width (padded to 64-column chunks)
+    ks = -(-(S + 1) // 64) * 64                # state image width
+    kc = -(-(N + 3) // 2) * 64                 # raw (hypernet output) image width
+    if name == "fc1_fwd_both_tc":              # obs fp32 in; obs image, x of both nets, relu mask out
+        return 2.0 * rows * O * 2 * H, rows * (O * f4 + ko * 2 + 2 * 128 + 8)
+    if name == "gru_unroll_fwd_online_tc":     # x in; h + 4 gate tiles out
+        return 2.0 * rows * H * 6 * H, rows * (128 + 128 + 512)
+    if name == "gru_unroll_fwd_target_tc":
+        return 2.0 * rows * H * 6 * H, rows * (128 + 128)
+    if name == "q_select_tc":                  # h of both nets, avail, actions in; chosen / tmax out
+        return 2.0 * rows * H * 2 * A, rows * (2 * 128 + A * f4 + 8 + 8)
+    if name == "state_to_images":
+        return 0.0, BT * (S * f4 + ks * 2)
+    if name == "mixer_fwd_target_tc":
+        return 2.0 * BT * ks * C, BT * (ks * 2 + N * f4 + f4)
+    if name == "mixer_fwd_online_tc":
+        return 2.0 * BT * ks * C, BT * (ks * 2 + kc * 2 + N * f4 + f4)
+    if name == "mixer_bwd" and mixer == "qmix":   # mix backward on the raw images + weight-gradient GEMM over both images
+        return 2.0 * BT * ks * C, BT * (2 * kc * 2 + kc * 2 + ks * 2 + 2 * N * f4)
+    if name == "gru_unroll_bwd_tc":            # 4 gate tiles + h in; 4 gate-gradient tiles + dpre1 out
+        return 2.0 * rows * H * 6 * H, rows * (640 + 640 + 8)
+    if name == "dW_rnn_tc":
+        return 2.0 * rows * H * 6 * H, rows * (512 + 128 + 128)
+    if name == "dW_fc1_fc2_tc":
+        return 2.0 * rows * H * (ko + H + 2 * H), rows * (128 + 128 + ko * 2 + 16)
     if name.startswith("fc1_fwd"):
         return 2.0 * rows * O * H, rows * (O + H) * f4
     if name == "gru_unroll_fwd_online":
@@ -82,6 +110,16 @@ def phase_work(name, B, T, N, O, S, A, H, E, mixer):
     if name == "agent_scatter_grads":
         return 0.0, rows * (2 * H) * f4
     return 0.0, 0.0
+
+
+def measured_traffic(name, rows):
+    """DRAM bytes per launch of a phase's dominant kernel from the committed ncu capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per (b, t, n) row), scaled to this run's rows; None if not captured."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get("bytes_per_row", {})
+    return d[name] * rows if name in d else None
 
 
 def step_roofline(B, T, N, O, S, A, H, E, mixer, peaks):
@@ -212,7 +250,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=0)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 tensor-core tier (fp32 accumulate, parity 1e-2); fp32 = CUDA-core tier (parity 1e-5)")
     a = ap.parse_args()
     cfg = dict(BASELINE_CONFIGS[a.config])
     if a.batch:
@@ -301,7 +340,8 @@ def main():
         else:
             ach, peak, unit, bound = by / tsec / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
         roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                    "traffic": None, "peak_source": peaks["source"], "kernel_ms": phase_ms[top],
+                    "traffic": measured_traffic(top, B * T * N), "algorithmic_bytes": by, "algorithmic_flops": fl,
+                    "peak_source": peaks["source"], "kernel_ms": phase_ms[top],
                     "share_of_step": phase_ms[top] / sum(phase_ms.values())}
     fl_s, by_s, t_roof, bound_s = step_roofline(B, T, N, O, S, A, H, E, cfg["mixer"], peaks)
 
