@@ -558,7 +558,8 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     };
     char* gru_img = reinterpret_cast<char*>(v.scratch);
     // fc1/fc2 weight gradients as one image-fed GEMM kernel (needs the obs tile images written by fc1)
-    const bool fused_dw = tc_agent && d->O <= 320 && d->N <= 64;
+    // needs the obs images of the streaming fc1 kernel with one-hot(agent) + ones folded into the K padding
+    const bool fused_dw = tc_agent && d->O <= 320 && d->N <= 64 && ((d->O + 63) / 64) * 64 - d->O >= d->N + 1;
     uint8_t* obs_ti = reinterpret_cast<uint8_t*>(v.obs_img);
     if (tc_agent) {
         if ((rc = tc_ti_zero_pad(x_on_ti, d->T, n_tiles, R, s))) return rc;

@@ -607,18 +607,20 @@ __global__ void gru_dw_reduce_kernel(const float* __restrict__ partial, int n_ct
 
 // ------------------------------------------------------------------------------------------
 // fc1 / fc2 weight gradients from tile images, one-hot operands generated on the fly.
-//   item = (t, tile, half): 64 rows.  A1 = [dpre1 | Q1], A2 = [P1 | ID] (MN-major, M = 128), where
+//   item = (t, tile, half): 64 rows.  A1 = [dpre1 | Q1], A2 = [P1 | (ignored)] (MN-major, M = 128), where
 //     Q1[row, a]  = dq[row]        if a == action[row]          (-> fc2.weight / fc2.bias)
 //     P1[row, a]  = 1              if a == action[row at t-1] and that step was filled (-> fc1 last-action columns)
-//     ID[row, n]  = 1              if n == agent(row)                                  (-> fc1 agent-id columns)
-//   D_obs = A1 x obs (fc1.weight[:, :O] in rows 0..63), D_h = A1 x h_t (fc2.weight in rows 64..),
-//   D_one = A1 x 1 (fc1.bias | fc2.bias), D_a2 = A2 x dpre1 (last-action | agent-id columns).
+//   D_obs = A1 x obs image (rows 0..63: fc1.weight[:, :O]; the image carries one-hot(agent) and a ones column in its K
+//   padding - written by the streaming fc1 kernel - so columns O.. give the agent-id columns and fc1.bias),
+//   D_h = A1 x h_t (fc2.weight in rows 64..), D_one = A1 x 1 (fc2.bias in rows 64..), D_a2 = A2 x dpre1 (rows 0..63:
+//   last-action columns).  Three 72 KB stages.
 // ------------------------------------------------------------------------------------------
 namespace ad {
 constexpr int HALF = 8192;                                   // 64 rows x 128 B
 constexpr int MAX_CHUNKS = 5;                                // obs width <= 320
-constexpr int STAGE_BYTES = (5 + MAX_CHUNKS) * HALF;         // dpre1 | Q1 | P1 | ID | h_t | obs chunks
-constexpr int ONES = 2 * STAGE_BYTES;
+constexpr int STAGES = 3;
+constexpr int STAGE_BYTES = (4 + MAX_CHUNKS) * HALF;         // dpre1 | Q1 | P1 | h_t | obs chunks
+constexpr int ONES = STAGES * STAGE_BYTES;
 constexpr int BARS = ONES + HALF;
 constexpr int SMEM_BYTES = 1024 + BARS + 128;
 constexpr int THREADS = 192;
@@ -639,14 +641,14 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
-    uint64_t* full = bars;               // [2]: loader bytes + 2 generator warps
-    uint64_t* empty = bars + 2;          // [2]
-    uint64_t* done = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* full = bars;               // [STAGES]: loader bytes + 2 generator warps
+    uint64_t* empty = bars + STAGES;     // [STAGES]
+    uint64_t* done = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 3); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 3); mbar_init(&empty[i], 1); }
         mbar_init(done, 1);
         fence_barrier_init();
     }
@@ -666,18 +668,18 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
     if (warp == 5) {
         if (lane == 0) {
             for (int64_t i = 0; i < n_my; ++i) {
-                const int s = (int)(i & 1);
+                const int s = (int)(i % STAGES);
                 const int64_t item = beg + i;
                 const int64_t tt = item >> 1;                  // t * n_tiles + tile
                 const int half = (int)(item & 1);
                 const int64_t t = tt / P.n_tiles, tile = tt - t * P.n_tiles;
-                mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_wait(&empty[s], (uint32_t)(((i / STAGES) & 1) ^ 1));
                 mbar_arrive_expect_tx(&full[s], (2 + P.n_chunks) * HALF);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 bulk_copy_g2s(st, P.dpre1_ti + tt * TILE_BYTES + half * HALF, HALF, &full[s]);
-                bulk_copy_g2s(st + 4 * HALF, P.h_ti + ((t + 1) * P.n_tiles + tile) * TILE_BYTES + half * HALF, HALF, &full[s]);
+                bulk_copy_g2s(st + 3 * HALF, P.h_ti + ((t + 1) * P.n_tiles + tile) * TILE_BYTES + half * HALF, HALF, &full[s]);
                 for (int c = 0; c < P.n_chunks; ++c)
-                    bulk_copy_g2s(st + (5 + c) * HALF, P.obs_ti + (tt * P.n_chunks + c) * TILE_BYTES + half * HALF, HALF,
+                    bulk_copy_g2s(st + (4 + c) * HALF, P.obs_ti + (tt * P.n_chunks + c) * TILE_BYTES + half * HALF, HALF,
                                   &full[s]);
             }
         }
@@ -688,19 +690,19 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
             const uint32_t id64 = umma_idesc_bf16(128, 64, 1, 1), id16 = umma_idesc_bf16(128, 16, 1, 1);
             const uint32_t ones = smem_u32(smem + ONES);
             for (int64_t i = 0; i < n_my; ++i) {
-                const int s = (int)(i & 1);
-                mbar_wait(&full[s], (i >> 1) & 1);
+                const int s = (int)(i % STAGES);
+                mbar_wait(&full[s], (uint32_t)((i / STAGES) & 1));
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {               // 64 rows = 4 x (K = 16)
                     const uint32_t acc = (i | kk) != 0;
                     const uint64_t a1 = umma_desc_sw128(st + kk * 2048, HALF, 1024);              // [dpre1 | Q1]
-                    const uint64_t a2 = umma_desc_sw128(st + 2 * HALF + kk * 2048, HALF, 1024);   // [P1 | ID]
-                    umma_bf16(tmem_base, a1, umma_desc_sw128(st + 5 * HALF + kk * 2048, HALF, 1024), id_o1, acc);
+                    const uint64_t a2 = umma_desc_sw128(st + 2 * HALF + kk * 2048, HALF, 1024);   // [P1 | h (rows 64.. unused)]
+                    umma_bf16(tmem_base, a1, umma_desc_sw128(st + 4 * HALF + kk * 2048, HALF, 1024), id_o1, acc);
                     if (n2 > 0)
-                        umma_bf16(tmem_base + 256, a1, umma_desc_sw128(st + 9 * HALF + kk * 2048, HALF, 1024), id_o2, acc);
-                    umma_bf16(tmem_base + 320, a1, umma_desc_sw128(st + 4 * HALF + kk * 2048, HALF, 1024), id64, acc);
+                        umma_bf16(tmem_base + 256, a1, umma_desc_sw128(st + 8 * HALF + kk * 2048, HALF, 1024), id_o2, acc);
+                    umma_bf16(tmem_base + 320, a1, umma_desc_sw128(st + 3 * HALF + kk * 2048, HALF, 1024), id64, acc);
                     umma_bf16(tmem_base + 384, a1, umma_desc_sw128(ones + kk * 2048, HALF, 1024), id16, acc);
                     umma_bf16(tmem_base + 400, a2, umma_desc_sw128(st + kk * 2048, HALF, 1024), id64, acc);
                 }
@@ -714,9 +716,9 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
         // pipeline: the generators, not the copies or the MMAs, were the critical path).  All four warps: final epilogue.
         {
             const int rr = (warp & 1) * 32 + lane;             // row within the half tile
-            struct Idx { int a, ap, n; float dq; };
+            struct Idx { int a, ap; float dq; };
             auto fetch = [&](int64_t i) {
-                Idx x{-1, -1, -1, 0.f};
+                Idx x{-1, -1, 0.f};
                 if (i >= n_my) return x;
                 const int64_t item = beg + i;
                 const int64_t tt = item >> 1;
@@ -724,39 +726,36 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
                 const int64_t t = tt / P.n_tiles, tile = tt - t * P.n_tiles;
                 const int64_t p = tile * TILE_ROWS + half * 64 + rr;
                 if (p < P.R) {
-                    const int64_t b = p / P.N;
-                    x.n = (int)(p - b * P.N);
+                    const int64_t b = (int64_t)((uint32_t)p / (uint32_t)P.N);
+                    const int n = (int)(p - b * P.N);
                     if (t < P.T - 1) {
-                        x.dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + x.n);
-                        x.a = (int)__ldg(P.actions + b * P.actions_sb + t * P.N + x.n);
+                        x.dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
+                        x.a = (int)__ldg(P.actions + b * P.actions_sb + t * P.N + n);
                     }
                     if (P.use_act && t > 0) {                  // both loads issued unconditionally, then selected
                         const int64_t f = __ldg(P.filled + b * P.filled_sb + (t - 1));
-                        const int apv = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + x.n);
+                        const int apv = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + n);
                         x.ap = f != 0 ? apv : -1;
                     }
-                    if (!P.use_id) x.n = -1;
                 }
                 return x;
             };
             Idx cur = fetch(warp >> 1);
             for (int64_t i = warp >> 1; i < n_my; i += 2) {
-                const int s = (int)(i & 1);
+                const int s = (int)(i % STAGES);
                 const Idx nxt = fetch(i + 2);
-                const int a = cur.a, ap = cur.ap, n = cur.n;
+                const int a = cur.a, ap = cur.ap;
                 const uint32_t dqb = pack_bf16x2(cur.dq, 0.f) & 0xffffu;      // bf16 bits of dq
-                mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_wait(&empty[s], (uint32_t)(((i / STAGES) & 1) ^ 1));
                 uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t off = sw128_offset((uint32_t)rr, (uint32_t)j);
-                    uint32_t q[4] = {0, 0, 0, 0}, pp[4] = {0, 0, 0, 0}, id[4] = {0, 0, 0, 0};
+                    uint32_t q[4] = {0, 0, 0, 0}, pp[4] = {0, 0, 0, 0};
                     if ((a >> 3) == j) q[(a & 7) >> 1] = dqb << (16 * (a & 1));
                     if ((ap >> 3) == j) pp[(ap & 7) >> 1] = 0x3f80u << (16 * (ap & 1));
-                    if ((n >> 3) == j) id[(n & 7) >> 1] = 0x3f80u << (16 * (n & 1));
                     *reinterpret_cast<uint4*>(st + 1 * HALF + off) = make_uint4(q[0], q[1], q[2], q[3]);
                     *reinterpret_cast<uint4*>(st + 2 * HALF + off) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-                    *reinterpret_cast<uint4*>(st + 3 * HALF + off) = make_uint4(id[0], id[1], id[2], id[3]);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -818,17 +817,17 @@ __global__ void agent_dw_reduce_kernel(const float* __restrict__ partial, int n_
     if (i < 64 * OBS_LD) {
         int j = i / OBS_LD, k = i - j * OBS_LD;
         if (k < O) fc1_w[(int64_t)j * D_in + k] = s;
+        else if (k - O < N) { if (use_id) fc1_w[(int64_t)j * D_in + O + (use_act ? A : 0) + (k - O)] = s; }   // one-hot(agent) columns
+        else if (k - O == N) fc1_b[j] = s;                                                                   // ones column
     } else if (i < 64 * OBS_LD + 64 * 64) {
         int q = i - 64 * OBS_LD, a = q / 64, j = q - a * 64;
         if (a < A) fc2_w[a * 64 + j] = s;
     } else if (i < 64 * OBS_LD + 64 * 64 + 128) {
         int q = i - (64 * OBS_LD + 64 * 64);
-        if (q < 64) fc1_b[q] = s;
-        else if (q - 64 < A) fc2_b[q - 64] = s;
+        if (q >= 64 && q - 64 < A) fc2_b[q - 64] = s;
     } else {
         int q = i - (64 * OBS_LD + 64 * 64 + 128), r = q / 64, j = q - r * 64;
-        if (r < 64) { if (use_act && r < A) fc1_w[(int64_t)j * D_in + O + r] = s; }
-        else if (use_id && r - 64 < N) fc1_w[(int64_t)j * D_in + O + (use_act ? A : 0) + (r - 64)] = s;
+        if (r < 64 && use_act && r < A) fc1_w[(int64_t)j * D_in + O + r] = s;
     }
 }
 

@@ -418,26 +418,28 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
         const uint32_t r = (uint32_t)(warp * 32 + lane);
         const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
         const bool vec_ok = (P.A & 3) == 0 && (P.avail_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
+        const uint32_t bias_s = smem_u32(bias);
+        const int n_q4 = (P.A + 3) >> 2;
         uint32_t it = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b2 = it & 1;
-            const int t = (int)(item / P.n_tiles);
-            const int64_t tile = item - (int64_t)t * P.n_tiles;
-            const int64_t p = tile * TILE_ROWS2 + r;
+            const int t = (int)((uint32_t)item / (uint32_t)P.n_tiles);           // T * n_tiles < 2^31
+            const int tile = (int)item - t * P.n_tiles;
+            const int64_t p = (int64_t)tile * TILE_ROWS2 + r;
             const bool valid = p < P.R;
-            const int64_t b = valid ? p / P.N : 0;
+            const int64_t b = valid ? (int64_t)((uint32_t)p / (uint32_t)P.N) : 0;
             const int n = valid ? (int)(p - b * P.N) : 0;
             // issue the index / avail loads before waiting for the accumulator
             int a_taken = -1;
             if (valid && t < P.T - 1) a_taken = (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n);
             const int32_t* av = P.avail + b * P.avail_sb + ((int64_t)t * P.N + n) * P.A;
             const bool want_t = valid && t >= 1;
-            // the whole avail row goes to registers before the accumulator wait (16-byte loads when the layout allows)
+            // the whole avail row goes to registers (16-byte loads when the layout allows); columns >= A read as 0
             int4 avv[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 avv[q] = make_int4(0, 0, 0, 0);
-                if (want_t && 4 * q < P.A) {
+                if (want_t && q < n_q4) {
                     if (vec_ok) avv[q] = __ldg(reinterpret_cast<const int4*>(av) + q);
                     else {
                         avv[q].x = __ldg(av + 4 * q);
@@ -449,10 +451,10 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
             }
             mbar_wait(&tfull[b2], (it >> 1) & 1);
             tc_fence_after();
+            // padding columns (a >= A) have zero weights, zero bias and avail = 0: they are masked like unavailable
+            // actions and can never win the arg-max against column 0 (strict >), so the loop needs no a < A tests
             float best = -INFINITY, chosen = 0.f, tsel = 0.f, mt0 = 0.f;
             int bidx = 0x7fffffff;
-            float* qo = P.q_on_out ? P.q_on_out + ((int64_t)t * P.R + p) * P.A : nullptr;
-            float* qt = P.q_tg_out ? P.q_tg_out + ((int64_t)t * P.R + p) * P.A : nullptr;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int c0 = 16 * cc;
@@ -460,26 +462,33 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
                     uint32_t von[16], vtg[16];
                     ld_tmem_16(tl + 128 * b2 + c0, von);
                     ld_tmem_16(tl + 128 * b2 + 64 + c0, vtg);
+                    float bo[16], bt[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        lds_v4(bias_s + 4 * (c0 + 4 * j4), *reinterpret_cast<float(*)[4]>(&bo[4 * j4]));
+                        lds_v4(bias_s + 256 + 4 * (c0 + 4 * j4), *reinterpret_cast<float(*)[4]>(&bt[4 * j4]));
+                    }
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int a = c0 + j;
-                        if (a < P.A) {
-                            const float q_on = __uint_as_float(von[j]) + bias[a];
-                            const float q_tg = __uint_as_float(vtg[j]) + bias[64 + a];
-                            if (a == a_taken) chosen = q_on;
-                            if (want_t) {
-                                const int4 w = avv[4 * cc + (j >> 2)];
-                                const int avj = (j & 3) == 0 ? w.x : ((j & 3) == 1 ? w.y : ((j & 3) == 2 ? w.z : w.w));
-                                const bool ok = avj != 0;
-                                const float mt = ok ? q_tg : kMaskValue;
-                                const float v = P.double_q ? (ok ? q_on : kMaskValue) : mt;
-                                if (a == 0) mt0 = mt;
-                                if (v > best) { best = v; bidx = a; tsel = mt; }      // ascending a, strict >: lowest index wins
-                            }
-                            if (valid && qo) qo[a] = q_on;
-                            if (valid && qt) qt[a] = q_tg;
-                        }
+                        const float q_on = __uint_as_float(von[j]) + bo[j];
+                        const float q_tg = __uint_as_float(vtg[j]) + bt[j];
+                        chosen = a == a_taken ? q_on : chosen;
+                        const int4 w = avv[4 * cc + (j >> 2)];
+                        const int avj = (j & 3) == 0 ? w.x : ((j & 3) == 1 ? w.y : ((j & 3) == 2 ? w.z : w.w));
+                        const bool ok = avj != 0;
+                        const float mt = ok ? q_tg : kMaskValue;
+                        const float v = P.double_q ? (ok ? q_on : kMaskValue) : mt;
+                        if (a == 0) mt0 = mt;
+                        if (v > best) { best = v; bidx = a; tsel = mt; }          // ascending a, strict >: lowest index wins
+                    }
+                    if (P.q_on_out != nullptr && valid) {                        // tests / diagnostics only
+                        float* qo = P.q_on_out + ((int64_t)t * P.R + p) * P.A;
+                        float* qt = P.q_tg_out + ((int64_t)t * P.R + p) * P.A;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < P.A) { qo[c0 + j] = __uint_as_float(von[j]) + bo[j]; qt[c0 + j] = __uint_as_float(vtg[j]) + bt[j]; }
                     }
                 }
             }
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
             if (lane == 0) mbar_arrive(&tempty[b2]);
             if (valid && t < P.T - 1) P.chosen[(b * (P.T - 1) + t) * P.N + n] = chosen;
             if (want_t) {
-                if (bidx == 0x7fffffff) tsel = mt0;             // all-NaN row: index 0, as target_select_kernel
+                if (bidx >= P.A) { tsel = mt0; best = -INFINITY; }   // all-NaN row: index 0, as target_select_kernel
                 P.tmax[(b * (P.T - 1) + (t - 1)) * P.N + n] = P.double_q ? tsel : best;
             }
         }
