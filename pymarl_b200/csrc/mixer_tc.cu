@@ -33,6 +33,7 @@ struct MixBwdParams {
 
 constexpr int MB_WARPS = 8;
 
+template <int MAXCB>
 __global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img_kernel(MixBwdParams P) {
     __shared__ float red[MB_WARPS][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -59,19 +60,29 @@ __global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img_kernel(MixBwdParams
         }
         const float gm = __ldg(P.g + mq);
         const float* qs = P.agent_qs + mq * N;
-        // pass 1: pre-activation of the mixing layer and the three special groups
+        // the whole row goes to registers first (all loads in flight), q_n of this lane's groups alongside
+        uint32_t wv[MAXCB];
+        float qv[MAXCB];
+#pragma unroll
+        for (int cb = 0; cb < MAXCB; ++cb) {
+            wv[cb] = 0u; qv[cb] = 0.f;
+            if (cb < P.n_cblk) {
+                wv[cb] = *reinterpret_cast<const uint32_t*>(base + (int64_t)cb * 16384);
+                if (2 * cb + h < N) qv[cb] = __ldg(qs + 2 * cb + h);
+            }
+        }
+        // pre-activation of the mixing layer and the three special groups
         float acc0 = 0.f, acc1 = 0.f;
         uint32_t w_b1 = 0u, w_wf = 0u, w_v0 = 0u;
-        for (int cb = 0; cb < P.n_cblk; ++cb) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(base + (int64_t)cb * 16384);
+#pragma unroll
+        for (int cb = 0; cb < MAXCB; ++cb) {
             const int grp = 2 * cb + h;
             if (grp < N) {
-                const float qn = __ldg(qs + grp);
-                acc0 = fmaf(qn, fabsf(mt_lo(w)), acc0);
-                acc1 = fmaf(qn, fabsf(mt_hi(w)), acc1);
-            } else if (grp == N) w_b1 = w;
-            else if (grp == N + 1) w_wf = w;
-            else if (grp == N + 2) w_v0 = w;
+                acc0 = fmaf(qv[cb], fabsf(mt_lo(wv[cb])), acc0);
+                acc1 = fmaf(qv[cb], fabsf(mt_hi(wv[cb])), acc1);
+            } else if (grp == N) w_b1 = wv[cb];
+            else if (grp == N + 1) w_wf = wv[cb];
+            else if (grp == N + 2) w_v0 = wv[cb];
         }
         // the partner lane (lane ^ 16) holds the same e0 for the other group parity
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16);
@@ -94,28 +105,29 @@ __global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img_kernel(MixBwdParams
             dv2w1 = fmaf(gm, fmaxf(v01, 0.f), dv2w1);
         }
         if (lane == 0) dv2b += gm;
-        // pass 2: d_raw in place (every lane re-reads exactly the word it overwrites), d_q
-        for (int cb = 0; cb < P.n_cblk; ++cb) {
-            uint32_t* p = reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384);
-            const uint32_t w = *p;
-            const int grp = 2 * cb + h;
-            uint32_t out = 0u;
-            float part = 0.f;
-            if (grp < N) {
-                const float qn = __ldg(qs + grp);
-                const float a = mt_lo(w), b = mt_hi(w);
-                out = pack_bf16x2(mt_sgn(a) * qn * dp0, mt_sgn(b) * qn * dp1);
-                part = fmaf(fabsf(a), dp0, fabsf(b) * dp1);
-            } else if (grp == N) out = d_b1;
-            else if (grp == N + 1) out = d_wf;
-            else if (grp == N + 2) out = d_v0;
-            *p = out;
-            // sum over the 16 lanes of this parity (lane bits 0..3)
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 4);
-            part += __shfl_xor_sync(0xffffffffu, part, 8);
-            if ((lane & 15) == 0 && grp < N) P.d_qs[mq * N + grp] = part;
+        // d_raw in place, d_q
+#pragma unroll
+        for (int cb = 0; cb < MAXCB; ++cb) {
+            if (cb < P.n_cblk) {
+                const uint32_t w = wv[cb];
+                const int grp = 2 * cb + h;
+                uint32_t out = 0u;
+                float part = 0.f;
+                if (grp < N) {
+                    const float a = mt_lo(w), b = mt_hi(w);
+                    out = pack_bf16x2(mt_sgn(a) * qv[cb] * dp0, mt_sgn(b) * qv[cb] * dp1);
+                    part = fmaf(fabsf(a), dp0, fabsf(b) * dp1);
+                } else if (grp == N) out = d_b1;
+                else if (grp == N + 1) out = d_wf;
+                else if (grp == N + 2) out = d_v0;
+                *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = out;
+                // sum over the 16 lanes of this parity (lane bits 0..3)
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                part += __shfl_xor_sync(0xffffffffu, part, 4);
+                part += __shfl_xor_sync(0xffffffffu, part, 8);
+                if ((lane & 15) == 0 && grp < N) P.d_qs[mq * N + grp] = part;
+            }
         }
     }
     // V.2 gradients: fixed lane -> e mapping per warp, fixed warp order -> deterministic partials
@@ -326,7 +338,8 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
     tc::MixBwdParams B;
     B.raw_img = raw_img; B.agent_qs = agent_qs; B.g = g; B.v2_w = mp.v2_w; B.d_qs = d_agent_qs; B.v2_partial = v2_partial;
     B.BT = (int64_t)d->B * d->T; B.rows_total = tc_mix_row_tiles(d) * 128; B.T = d->T; B.N = d->N; B.n_cblk = tc_mix_cblks(d);
-    tc::mix_bwd_img_kernel<<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
+    if (B.n_cblk <= 16) tc::mix_bwd_img_kernel<16><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
+    else tc::mix_bwd_img_kernel<34><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
     PMB_LAUNCH_CHECK("mix_bwd_img_kernel");
     tc::mix_v2_reduce_kernel<<<1, 64, 0, s>>>(v2_partial, grid, gv2_w, gv2_b);
     PMB_LAUNCH_CHECK("mix_v2_reduce_kernel");
