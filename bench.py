@@ -243,7 +243,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="27m_vs_30m", choices=sorted(BASELINE_CONFIGS))
+    ap.add_argument("--config", default="27m_vs_30m", choices=sorted(BASELINE_CONFIGS) + ["select_actions"],
+                    help="select_actions = BASELINE config 5: BasicMAC.select_actions over 16384 envs x 27 agents")
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: BASELINE batch)")
     ap.add_argument("--ragged", action="store_true", help="variable-length episodes instead of full-length")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -253,6 +254,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core tier (fp32 accumulate, parity 1e-2); fp32 = CUDA-core tier (parity 1e-5)")
     a = ap.parse_args()
+    if a.config == "select_actions":
+        return rollout_bench(a)
     cfg = dict(BASELINE_CONFIGS[a.config])
     if a.batch:
         cfg["batch"] = a.batch
@@ -396,6 +399,143 @@ def main():
             "phases_ms": phase_ms,
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rollout_bench(a):
+    """BASELINE config 5: one BasicMAC.select_actions step (fc1 -> GRUCell -> fc2 -> avail mask -> epsilon-greedy) over
+    `--batch` (default 16384) synthetic envs x 27 agents; metric = agent-steps/s.  The obs of 4 timesteps live in HBM and
+    the step index cycles over them (2 GB, larger than L2)."""
+    import numpy as np
+    shape = SMAC_SHAPES["27m_vs_30m"]
+    N, O, A, H = shape.n_agents, shape.obs_dim, shape.n_actions, 64
+    envs = a.batch or 16384
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric, unit = "mac_agent_steps_per_sec", "agent-steps/s"
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import copy
+        from oracle import qlearner_oracle as orc
+        from pymarl_b200.synthetic import numpy_episode_fields
+        cb = a.cpu_batch or 256
+        rng = np.random.default_rng(7)
+        agent = orc.init_params(orc.agent_param_shapes(O + A + N, H, A), rng)
+        fields = numpy_episode_fields(shape, cb, 4, seed=0, ragged=False)
+        if "actions_onehot" not in fields:
+            fields["actions_onehot"] = np.eye(A, dtype=np.float32)[fields["actions"][..., 0]]
+        hstate = np.zeros((cb * N, H), np.float32)
+        steps, warm = max(1, min(a.steps, 20)), max(1, min(a.warmup, 3))
+        times = []
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            t = 1 + i % 3
+            u = rng.random((cb, N), dtype=np.float32)
+            e = rng.exponential(size=(cb, N, A)).astype(np.float32)
+            _, _, hstate = orc.mac_select_actions(agent, fields, t, hstate, 0.5, u, e)
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        val = cb * N / (ms * 1e-3)
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": a.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BasicMAC.select_actions step, 27m_vs_30m shapes", "envs": cb, "n_agents": N},
+                "cpu_baseline": {"value": val, "unit": unit, "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "%d envs x %d agents per step, %d steps (numpy oracle)" % (cb, N, steps)},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch as th
+    import torch.distributed as dist
+    from pymarl_b200 import mac_REGISTRY, _lib
+    from pymarl_b200.synthetic import make_scheme, torch_episode_fields
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    th.cuda.set_device(local_rank)
+    dev = th.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    args = default_args(shape, mixer="qmix", device="cuda", use_cuda=True, precision=a.precision)
+    th.manual_seed(7)
+    scheme, groups = make_scheme(shape)
+    scheme["actions_onehot"] = {"vshape": (A,), "dtype": th.float32, "group": "agents"}
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    mac.cuda()
+    Tb = 4
+    fields = torch_episode_fields(shape, envs, Tb, seed=1000 + rank, ragged=False, device=dev, with_onehot=False)
+    batch = _DictBatch(fields, envs, Tb)
+    mac.init_hidden(envs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    for i in range(a.warmup):
+        mac.select_actions(batch, 1 + i % 3, 1000 * i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.lib().pmb_launch_count()
+    ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(a.steps):
+        mac.select_actions(batch, 1 + i % 3, 1000 * i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = (_lib.lib().pmb_launch_count() - launches0) // max(1, a.steps)
+    ms = ev0.elapsed_time(ev1) / a.steps
+    t = th.tensor([ms], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * envs * N / (ms * 1e-3)
+    rows = envs * N
+    algo_bytes = rows * (O * 4 + 2 * H * 4 + A * 4 + 8 + 8)          # SURVEY.md section 8d
+    ach = algo_bytes / (ms * 1e-3) / 1e9
+    # e2e: obs / avail of the step start in pinned host memory, the chosen actions are read back (what a runner does)
+    e2e = None
+    if not a.no_e2e:
+        host = {k: th.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in fields.items()}
+        hb = _DictBatch(host, envs, Tb)
+        out = th.empty(envs, N, dtype=th.int64, pin_memory=True)
+        mac.select_actions(hb, 1, 0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(a.e2e_steps):
+            acts = mac.select_actions(hb, 1 + i % 3, 1000 * i)
+            out.copy_(acts, non_blocking=True)
+            th.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / a.e2e_steps
+        h2d = sum(host[k][:, :2].numel() * host[k].element_size() for k in ("obs", "actions", "avail_actions", "filled"))
+        e2e = {"value": world * envs * N / dt, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": envs * N * 8,
+               "ms_per_step": dt * 1e3, "steps": a.e2e_steps}
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "select_actions", "--impl", "reference",
+                              "--steps", "10", "--warmup", "2"], capture_output=True, text=True)
+        try:
+            cpu = json.loads(sub.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception:
+            cpu = {"value": None, "error": (sub.stderr or "")[-200:]}
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if a.precision == "fp32" else "bf16 (fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "BasicMAC.select_actions step, 27m_vs_30m shapes", "envs_per_gpu": envs, "n_agents": N,
+                           "obs": O, "n_actions": A, "parallelism": "dp%d" % world,
+                           "l2_policy": "obs of 4 timesteps (%.1f GB) cycled, larger than L2" % (fields["obs"].numel() * 4 / 1e9)},
+                "roofline": {"kernel": "select_actions_step (all launches)", "bound": "hbm", "achieved": ach,
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                             "algorithmic_bytes": algo_bytes, "peak_source": peaks["source"]},
+                "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -45,7 +45,7 @@ class BasicMAC:
         obs = ep_batch["obs"]
         return _lib.make_dims(B=ep_batch.batch_size, T=obs.shape[1], N=self.n_agents, O=obs.shape[-1], S=1,
                               A=a.n_actions, H=a.rnn_hidden_dim, E=1, obs_last_action=a.obs_last_action,
-                              obs_agent_id=a.obs_agent_id, mixer=None)
+                              obs_agent_id=a.obs_agent_id, mixer=None, precision=getattr(a, "precision", "fp32"))
 
     def _step_batch(self, ep_batch, t, keep):
         """pmb_batch with just the fields a rollout step reads.  When the runner keeps its

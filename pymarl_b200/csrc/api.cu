@@ -279,6 +279,20 @@ int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, co
     return scatter_grads_dispatch(d, b, h_stash, dpre1, d_chosen, gr, scratch, scratch_bytes, s);
 }
 
+// GRU / fc2 weight images of one agent: [w_ih 24 KB | w_hh 24 KB | fc2 8 KB] (bf16, K-major, 128B swizzle)
+int pack_gru_images(const pmb_dims* d, const AgentParams& ap, char* base, cudaStream_t s) {
+    const float* p1[1] = {ap.w_ih}; const float* p2[1] = {ap.w_hh}; const float* p3[2] = {ap.fc2_w, nullptr};
+    int r1[1] = {192}, l1[1] = {64}, r3[2] = {d->A, 64 - d->A}, l3[2] = {64, 64};
+    int e;
+    if ((e = tc_pack_w(p1, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base), s))) return e;
+    if ((e = tc_pack_w(p2, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base + 24576), s))) return e;
+    return tc_pack_w(p3, r3, l3, 2, 64, reinterpret_cast<__nv_bfloat16*>(base + 49152), s);
+}
+
+bool rollout_tc_ok(const pmb_dims* d) {
+    return d->precision == PMB_PREC_BF16 && d->H == 64 && d->A <= 64 && d->O <= 320;
+}
+
 }  // namespace
 }  // namespace pmb
 
@@ -467,7 +481,10 @@ int pmb_epsilon_greedy(int64_t rows, int32_t A, const float* q, const int32_t* a
 int64_t pmb_select_actions_workspace_bytes(const pmb_dims* d) {
     if (validate_dims(d)) return -1;
     const int64_t R = (int64_t)d->B * d->N;
-    return align_up(R * d->H * 4, 256) + align_up(R * d->A * 4, 256);
+    int64_t n = align_up(R * d->H * 4, 256) + align_up(R * d->A * 4, 256);
+    if (rollout_tc_ok(d))          // x tile images | GRU weight images | fc1 scratch
+        n += align_up(ceil_div(R, 128) * 16384, 256) + 65536 + align_up(tc_fc1_scratch_bytes(d), 256);
+    return n;
 }
 
 int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, const float* flat_agent, float* hidden,
@@ -485,10 +502,31 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
     float* x = static_cast<float*>(scratch);
     float* q = q_out ? q_out : reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(R * d->H * 4, 256));
     AgentParams ap = agent_params(d, flat_agent);
-    rc = fc1_fwd(d, b, t, 1, ap, x, s);
-    if (rc) return rc;
-    rc = gru_fwd_dispatch(d, ap, R, 1, x, hidden, nullptr, nullptr, q, hidden, s);
-    if (rc) return rc;
+    if (rollout_tc_ok(d)) {
+        // bf16 tier: streaming fc1 (online net only) -> x tile images -> one tcgen05 GRU step with fc2
+        char* base = static_cast<char*>(scratch) + align_up(R * d->H * 4, 256) + align_up(R * d->A * 4, 256);
+        const int n_tiles = (int)ceil_div(R, 128);
+        uint8_t* x_ti = reinterpret_cast<uint8_t*>(base);
+        char* gru_img = base + align_up((int64_t)n_tiles * 16384, 256);
+        void* fc1_scr = gru_img + 65536;
+        if ((rc = tc_ti_zero_pad(x_ti, 1, n_tiles, R, s))) return rc;
+        if ((rc = tc_fc1_fwd_both(d, b, t, 1, ap, ap, reinterpret_cast<float*>(x_ti), nullptr, 1, nullptr, nullptr, fc1_scr,
+                                  align_up(tc_fc1_scratch_bytes(d), 256), s))) return rc;
+        if ((rc = pack_gru_images(d, ap, gru_img, s))) return rc;
+        tc::GruFwdParams fp;
+        fp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img);
+        fp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576);
+        fp.w2_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 49152);
+        fp.b_ih = ap.b_ih; fp.b_hh = ap.b_hh; fp.b2 = ap.fc2_b;
+        fp.x_ti = x_ti; fp.h0 = hidden; fp.h_ti = nullptr; fp.g_ti = nullptr; fp.q = q; fp.h_last = hidden;
+        fp.R = R; fp.nt = 1; fp.A = d->A; fp.n_tiles = n_tiles;
+        if ((rc = tc_gru_fwd(fp, s))) return rc;
+    } else {
+        rc = fc1_fwd(d, b, t, 1, ap, x, s);
+        if (rc) return rc;
+        rc = gru_fwd_dispatch(d, ap, R, 1, x, hidden, nullptr, nullptr, q, hidden, s);
+        if (rc) return rc;
+    }
     if (!actions_out) return PMB_OK;
     return launch_epsilon_greedy(R, d->N, d->A, q, b->avail + (int64_t)t * d->N * d->A, b->avail_sb, epsilon, u, expo,
                                  seed, offset, actions_out, s);
@@ -548,14 +586,7 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     uint8_t *h_ti = reinterpret_cast<uint8_t*>(v.h_stash), *g_ti = reinterpret_cast<uint8_t*>(v.gates);
     uint8_t* hg_ti = reinterpret_cast<uint8_t*>(v.h_tg);
     // GRU weight images live at the start of the scratch area: [online: w_ih | w_hh | w2][target: same]
-    auto pack_gru = [&](const AgentParams& ap, char* base) -> int {
-        const float* p1[1] = {ap.w_ih}; const float* p2[1] = {ap.w_hh}; const float* p3[2] = {ap.fc2_w, nullptr};
-        int r1[1] = {192}, l1[1] = {64}, r3[2] = {d->A, 64 - d->A}, l3[2] = {64, 64};
-        int e;
-        if ((e = tc_pack_w(p1, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base), s))) return e;
-        if ((e = tc_pack_w(p2, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base + 24576), s))) return e;
-        return tc_pack_w(p3, r3, l3, 2, 64, reinterpret_cast<__nv_bfloat16*>(base + 49152), s);
-    };
+    auto pack_gru = [&](const AgentParams& ap, char* base) -> int { return pack_gru_images(d, ap, base, s); };
     char* gru_img = reinterpret_cast<char*>(v.scratch);
     // fc1/fc2 weight gradients as one image-fed GEMM kernel (needs the obs tile images written by fc1)
     // needs the obs images of the streaming fc1 kernel with one-hot(agent) + ones folded into the K padding

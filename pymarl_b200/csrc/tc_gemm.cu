@@ -13,7 +13,6 @@
 // 4 TMEM allocator + single-thread tcgen05.mma issuer, 5 W bulk-copy issuer, 6-13 A producers.
 // Pipelines: 4 shared-memory stages (full/empty mbarriers), 2 accumulator buffers (tmem_full/tmem_empty).
 // Persistent over 128-row tiles: grid = min(#tiles, #SMs).
-#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mixer_tc.cuh"
@@ -556,7 +555,8 @@ struct Fc1StreamParams {
     uint8_t* x_on; uint8_t* x_tg;  // tile images [T][n_tiles][16 KB]
     uint32_t* relu_mask;           // [T][n_tiles][2][128]
     int use_act;
-    int dbg;                       // timing experiments only (PMB_FC1_DBG): 2 = skip epilogue work, 4 = skip conversion
+    int n_nets;                    // 2: online + target (learner step), 1: online only (rollout step)
+    int t0;                        // batch timestep of item t = 0 (rollout: the step index; obs is addressed at t0 + t)
 };
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -611,32 +611,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             mbar_arrive_expect_tx(w_full, (uint32_t)tile_bytes);
             bulk_copy_g2s(w_s, P.Wp, (uint32_t)tile_bytes, w_full);
         }
-        // L2 prefetch of the runs of a whole tile (lane l takes the l-th episode of the tile): issued PF_AHEAD tiles ahead
-        // so that the staging ring (3 x 18 KB, all the shared memory that is left) sees L2 latency, not HBM latency.
-        auto prefetch_tile = [&](int64_t item) {
-            if (item >= n_items) return;
-            const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
-            const int64_t p0 = tile * BM;
-            int64_t p1 = p0 + BM;
-            if (p1 > P.R) p1 = P.R;
-            const int64_t b0 = p0 / P.N;
-            for (int64_t b = b0 + lane; b * P.N < p1; b += 32) {
-                const int64_t ps = b * P.N > p0 ? b * P.N : p0;
-                const int64_t pe = (b + 1) * P.N < p1 ? (b + 1) * P.N : p1;
-                const char* ga = reinterpret_cast<const char*>(P.obs + b * P.obs_sb + (t * P.N + (ps - b * P.N)) * (int64_t)P.O);
-                const uintptr_t a0 = (reinterpret_cast<uintptr_t>(ga) + 15) & ~(uintptr_t)15;
-                const uintptr_t a1 = (reinterpret_cast<uintptr_t>(ga) + (uint64_t)(pe - ps) * P.O * 4) & ~(uintptr_t)15;
-                if (a1 > a0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
-            }
-        };
-        constexpr int PF_AHEAD = 2;
-        if (pw == 0 && (P.dbg & 8))
-            for (int k = 0; k < PF_AHEAD; ++k) prefetch_tile((int64_t)blockIdx.x + (int64_t)k * gridDim.x);
         uint32_t git = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
-            if (pw == 0 && (P.dbg & 8)) prefetch_tile(item + (int64_t)PF_AHEAD * gridDim.x);
             for (int g = 0; g < GROUPS; ++g, ++git) {
                 if ((g & (N_PROD - 1)) != pw) continue;
                 const int slot = git % N_SLOTS;
@@ -655,7 +632,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     int cnt = P.N - n0;
                     if (cnt > GROUP_ROWS - lr) cnt = GROUP_ROWS - lr;
                     if ((int64_t)cnt > P.R - p) cnt = (int)(P.R - p);
-                    const char* ga = reinterpret_cast<const char*>(P.obs + b * P.obs_sb + (t * P.N + n0) * (int64_t)P.O);
+                    const char* ga = reinterpret_cast<const char*>(P.obs + b * P.obs_sb + ((t + P.t0) * P.N + n0) * (int64_t)P.O);
                     const uint32_t bytes = (uint32_t)cnt * P.O * 4u;
                     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
                     cur = ((cur + 15u) & ~15u) + phase;
@@ -716,7 +693,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 const int2 off2 = *reinterpret_cast<const int2*>(rowoff + slot * GROUP_ROWS + 2 * cw);
                 const int2 nn2 = *reinterpret_cast<const int2*>(rown + slot * GROUP_ROWS + 2 * cw);
                 float v0[2][MAX_CHUNKS], v1[2][MAX_CHUNKS];
-                if (!(P.dbg & 4)) {
+                {
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {             // all 20 loads first
                         const int off = rr ? off2.y : off2.x;
@@ -757,7 +734,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         }
     } else if (warp == MMA_W) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BM, 128, 0, 0);
+            const uint32_t idesc = umma_idesc_bf16(BM, 64 * P.n_nets, 0, 0);
             mbar_wait(w_full, 0);
             uint32_t ti = 0;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
@@ -803,9 +780,10 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             if (p >= P.R) return -2;
             const int64_t b = p / P.N;
             n_out = (int)(p - b * P.N);
-            if (!P.use_act || t == 0) return -1;
-            const int64_t f = __ldg(P.filled + b * P.filled_sb + (t - 1));
-            const int a = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + n_out);
+            const int64_t tb = t + P.t0;                       // timestep in the batch
+            if (!P.use_act || tb == 0) return -1;
+            const int64_t f = __ldg(P.filled + b * P.filled_sb + (tb - 1));
+            const int a = (int)__ldg(P.actions + b * P.actions_sb + (tb - 1) * P.N + n_out);
             return f != 0 ? a : -1;
         };
         int n_cur, n_nxt;
@@ -822,7 +800,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + 32 * g, v);
                 tmem_wait_ld();
-                if (a_prev != -2 && !(P.dbg & 2)) {
+                if (a_prev != -2 && g < 2 * P.n_nets) {
                     const int net = g >> 1, h0 = (g & 1) * 32;
                     uint8_t* tile_img = (net ? P.x_tg : P.x_on) + item * A_STAGE_BYTES;
                     const uint4* tac = a_prev >= 0 ? P.tab_act16 + ((int64_t)a_prev * 2 + net) * 8 + (h0 >> 3) : nullptr;
@@ -1013,7 +991,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
         const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 512, 128);
         const int64_t smem_need = 1024 + 2 * (int64_t)n_chunks * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes +
                                   2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
-        if (t0 == 0 && n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
+        if (n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
             const int fold_id = n_chunks * tc::BK - d->O >= d->N + 1;
             __nv_bfloat16* tab_act16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(scratch) + wp_bytes + ta_bytes + ti_bytes);
             const int64_t n_pack = (int64_t)128 * n_chunks * 8 + (int64_t)d->A * 128;
@@ -1028,8 +1006,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             Q.actions = b->actions; Q.actions_sb = b->actions_sb; Q.filled = b->filled; Q.filled_sb = b->filled_sb;
             Q.x_on = reinterpret_cast<uint8_t*>(x_on); Q.x_tg = reinterpret_cast<uint8_t*>(x_tg);
             Q.relu_mask = relu_mask; Q.use_act = d->obs_last_action;
-            Q.dbg = getenv("PMB_FC1_DBG") ? atoi(getenv("PMB_FC1_DBG")) : 0;
-            if (Q.dbg & 1) Q.obs_img = nullptr;
+            Q.n_nets = x_tg ? 2 : 1; Q.t0 = t0;
             PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
             const int64_t n_items = (int64_t)nt * n_tiles;
             const int grid = (int)(n_items < sm_count() ? n_items : sm_count());

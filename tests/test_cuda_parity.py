@@ -420,3 +420,38 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
         for name, prm in mod.named_parameters():
             gg = prm.grad.cpu().numpy()
             assert rel_err(prm.detach().cpu().numpy(), expect(init[name], gg)) < 1e-5, (kind, name)
+
+
+@pytest.mark.parametrize("shape_name,B", [("3m", 37), ("27m_vs_30m", 19)])
+def test_bf16_tier_rollout_steps_match_oracle(shape_name, B):
+    """BasicMAC.forward over three consecutive rollout steps on the tensor-core tier (streaming fc1 with the batch
+    timestep offset, one tcgen05 GRU step with fc2) against the oracle MAC: Q and the carried hidden state within the
+    bf16-tier tolerance; the host-resident batch path gives the same numbers."""
+    from cuda_utils import to_batch
+    from pymarl_b200 import mac_REGISTRY
+    from pymarl_b200.synthetic import make_scheme
+    shape = SMAC_SHAPES[shape_name]
+    args = default_args(shape, device="cuda", precision="bf16")
+    scheme, groups = make_scheme(shape)
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    mac.cuda()
+    rng = np.random.default_rng(5)
+    d_in = shape.obs_dim + shape.n_actions + shape.n_agents
+    agent = orc.init_params(orc.agent_param_shapes(d_in, 64, shape.n_actions), rng)
+    mac.agent.load_state_dict({k: th.from_numpy(v) for k, v in agent.items()})
+    fields = numpy_episode_fields(shape, B, 5, seed=3, ragged=False)
+    fields["actions_onehot"] = np.eye(shape.n_actions, dtype=np.float32)[fields["actions"][..., 0]] * \
+        fields["filled"][:, :, None, :].astype(np.float32)
+    results = {}
+    for device in ("cuda", "cpu"):
+        batch = to_batch(shape, {k: v for k, v in fields.items() if k != "actions_onehot"}, device=device)
+        mac.init_hidden(B)
+        h = np.zeros((B * shape.n_agents, 64), np.float32)
+        for t in range(3):
+            q = mac.forward(batch, t).cpu().numpy()
+            q_ref, h = orc.rnn_agent_forward(agent, orc.build_inputs(fields, t), h)
+            assert rel_err(q.reshape(q_ref.shape), q_ref) < TOL_BF16, (device, t)
+            assert rel_err(mac.hidden_states.cpu().numpy().reshape(h.shape), h) < TOL_BF16, (device, t)
+            results[(device, t)] = q
+    for t in range(3):
+        np.testing.assert_array_equal(results[("cuda", t)], results[("cpu", t)])
