@@ -72,6 +72,8 @@ constexpr int THREADS = 192;
 
 
 __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams P) {
+    // Persistent over row tiles (grid = min(#tiles, 2 x #SMs)): the weights are loaded once per CTA.  `it` counts
+    // (tile, step) iterations and drives every barrier parity.
     using namespace gf;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -82,12 +84,11 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
     uint64_t* x_empty = bars + 3;        // [2]
     uint64_t* gates_full = bars + 5;
     uint64_t* q_full = bars + 6;
-    uint64_t* h_ready = bars + 7;        // epilogue wrote the h operand tile
+    uint64_t* h_ready = bars + 7;        // epilogue wrote the h operand tile (also: h_0 of a new tile)
     uint64_t* tmem_free = bars + 8;      // epilogue finished reading q
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
     const int A_pad = (P.A + 15) & ~15;
 
     if (threadIdx.x == 0) {
@@ -106,47 +107,27 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
         bias[192 + i] = P.b_hh[128 + i];
         bias[256 + i] = i < P.A ? P.b2[i] : 0.f;
     }
-    // initial hidden state: registers (fp32) + operand tile (bf16)
-    float h[64];
-    const uint32_t r = warp * 32 + lane;                      // tile row of an epilogue thread
-    const int64_t row = (int64_t)tile * TILE_ROWS + r;
-    const bool valid = warp < 4 && row < P.R;
-    if (warp < 4) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) h[j] = 0.f;
-        if (valid && P.h0) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) h[j] = P.h0[row * 64 + j];
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = h[16 * c + j];
-            store_row16(smem + HT, r, c, f);
-            if (P.h_ti) store_row16(P.h_ti + (int64_t)tile * TILE_BYTES, r, c, f);
-        }
-        fence_proxy_async_smem();
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 5) {
-        // ===== loader: weights once, then one x tile per step =====
+        // ===== loader: weights once, then one x tile per (tile, step) =====
         if (lane == 0) {
             mbar_arrive_expect_tx(w_full, 24576 + 24576 + 8192);
             bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
             bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
             bulk_copy_g2s(smem + W2, P.w2_img, 8192, w_full);
-            for (int t = 0; t < P.nt; ++t) {
-                const int b = t & 1;
-                mbar_wait(&x_empty[b], ((t >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&x_full[b], TILE_BYTES);
-                bulk_copy_g2s(smem + XB + b * TILE_BYTES, P.x_ti + ((int64_t)t * P.n_tiles + tile) * TILE_BYTES, TILE_BYTES,
-                              &x_full[b]);
-            }
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+                for (int t = 0; t < P.nt; ++t, ++it) {
+                    const int b = it & 1;
+                    mbar_wait(&x_empty[b], ((it >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&x_full[b], TILE_BYTES);
+                    bulk_copy_g2s(smem + XB + b * TILE_BYTES, P.x_ti + ((int64_t)t * P.n_tiles + tile) * TILE_BYTES, TILE_BYTES,
+                                  &x_full[b]);
+                }
         }
     } else if (warp == 4) {
         // ===== MMA issuer =====
@@ -156,109 +137,155 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
             const uint32_t id128 = umma_idesc_bf16(128, 128, 0, 0), id64 = umma_idesc_bf16(128, 64, 0, 0);
             const uint32_t idq = umma_idesc_bf16(128, A_pad, 0, 0);
             mbar_wait(w_full, 0);
-            for (int t = 0; t < P.nt; ++t) {
-                const int b = t & 1;
-                const uint32_t xt = smem_u32(smem + XB + b * TILE_BYTES);
-                mbar_wait(&x_full[b], (t >> 1) & 1);
-                mbar_wait(tmem_free, (t & 1) ^ 1);             // q(t-1) drained (passes at t = 0)
-                tc_fence_after();
+            uint32_t it = 0, hr = 0;                           // hr: h_ready completions consumed
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+                for (int t = 0; t < P.nt; ++t, ++it) {
+                    const int b = it & 1;
+                    const uint32_t xt = smem_u32(smem + XB + b * TILE_BYTES);
+                    mbar_wait(&x_full[b], (it >> 1) & 1);
+                    mbar_wait(tmem_free, (it & 1) ^ 1);            // q of the previous iteration drained (passes at it = 0)
+                    if (t == 0) { mbar_wait(h_ready, hr & 1); ++hr; }   // h_0 of this tile is in the operand tile
+                    tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {               // r|z : x . W_i{r,z}^T
-                    umma_bf16(tmem_base, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024),
-                              id128, kk != 0);
-                }
+                    for (int kk = 0; kk < 4; ++kk) {               // r|z : x . W_i{r,z}^T
+                        umma_bf16(tmem_base, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024),
+                                  id128, kk != 0);
+                    }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {               //       + h . W_h{r,z}^T
-                    umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024),
-                              id128, 1);
-                }
+                    for (int kk = 0; kk < 4; ++kk) {               //       + h . W_h{r,z}^T
+                        umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024),
+                                  id128, 1);
+                    }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {               // n, input part
-                    umma_bf16(tmem_base + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
-                              umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
-                }
+                    for (int kk = 0; kk < 4; ++kk) {               // n, input part
+                        umma_bf16(tmem_base + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
+                                  umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+                    }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {               // n, hidden part
-                    umma_bf16(tmem_base + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
-                              umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
-                }
-                umma_commit(&x_empty[b]);
-                umma_commit(gates_full);
-                // fc2 on the new hidden state
-                mbar_wait(h_ready, t & 1);
-                tc_fence_after();
+                    for (int kk = 0; kk < 4; ++kk) {               // n, hidden part
+                        umma_bf16(tmem_base + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
+                                  umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+                    }
+                    umma_commit(&x_empty[b]);
+                    umma_commit(gates_full);
+                    // fc2 on the new hidden state
+                    mbar_wait(h_ready, hr & 1); ++hr;
+                    tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(w2 + kk * 32, 16, 1024),
-                              idq, kk != 0);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(w2 + kk * 32, 16, 1024),
+                                  idq, kk != 0);
+                    }
+                    umma_commit(q_full);
                 }
-                umma_commit(q_full);
-            }
         }
     } else {
         // ===== epilogue: gate math, hidden state update, q =====
         const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int t = 0; t < P.nt; ++t) {
-            mbar_wait(gates_full, t & 1);
-            tc_fence_after();
-            uint8_t* hti = P.h_ti ? P.h_ti + ((int64_t)(t + 1) * P.n_tiles + tile) * TILE_BYTES : nullptr;
-            uint8_t* gti = P.g_ti ? P.g_ti + ((int64_t)t * P.n_tiles + tile) * 4 * TILE_BYTES : nullptr;
+        const uint32_t r = warp * 32 + lane;                      // tile row of an epilogue thread
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            // initial hidden state: registers (fp32) + operand tile (bf16).  The MMAs of the previous tile have
+            // completed (its last q_full was waited for), so the operand tile may be overwritten.
+            float h[64];
+            const int64_t row = (int64_t)tile * TILE_ROWS + r;
+            const bool valid = row < P.R;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t ar[16], az[16], ain[16], ahn[16];
-                tmem_ld_32x16(tlane + 16 * c, ar);
-                tmem_ld_32x16(tlane + 64 + 16 * c, az);
-                tmem_ld_32x16(tlane + 128 + 16 * c, ain);
-                tmem_ld_32x16(tlane + 192 + 16 * c, ahn);
-                tmem_wait_ld();
-                float fr[16], fz[16], fn[16], fhn[16], fh[16];
+            for (int j = 0; j < 64; ++j) h[j] = 0.f;
+            if (valid && P.h0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int jj = 16 * c + j;
-                    float rg = fast_sigmoid(__uint_as_float(ar[j]) + bias[jj]);
-                    float zg = fast_sigmoid(__uint_as_float(az[j]) + bias[64 + jj]);
-                    float hn = __uint_as_float(ahn[j]) + bias[192 + jj];
-                    float ng = fast_tanh(__uint_as_float(ain[j]) + bias[128 + jj] + rg * hn);
-                    float hv = ng + zg * (h[jj] - ng);
-                    h[jj] = hv;
-                    fr[j] = rg; fz[j] = zg; fn[j] = ng; fhn[j] = hn; fh[j] = hv;
-                }
-                store_row16(smem + HT, r, c, fh);
-                if (valid) {
-                    if (hti) store_row16(hti, r, c, fh);
-                    if (gti) {
-                        store_row16(gti, r, c, fr);
-                        store_row16(gti + TILE_BYTES, r, c, fz);
-                        store_row16(gti + 2 * TILE_BYTES, r, c, fn);
-                        store_row16(gti + 3 * TILE_BYTES, r, c, fhn);
-                    }
+                for (int j4 = 0; j4 < 16; ++j4) {
+                    const float4 v = *reinterpret_cast<const float4*>(P.h0 + row * 64 + 4 * j4);
+                    h[4 * j4] = v.x; h[4 * j4 + 1] = v.y; h[4 * j4 + 2] = v.z; h[4 * j4 + 3] = v.w;
                 }
             }
-            tc_fence_before();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = h[16 * c + j];
+                store_row16(smem + HT, r, c, f);
+                if (P.h_ti) store_row16(P.h_ti + (int64_t)tile * TILE_BYTES, r, c, f);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(h_ready);
-            if (valid && P.h_last && t == P.nt - 1) {
+            for (int t = 0; t < P.nt; ++t, ++it) {
+                mbar_wait(gates_full, it & 1);
+                tc_fence_after();
+                uint8_t* hti = P.h_ti ? P.h_ti + ((int64_t)(t + 1) * P.n_tiles + tile) * TILE_BYTES : nullptr;
+                uint8_t* gti = P.g_ti ? P.g_ti + ((int64_t)t * P.n_tiles + tile) * 4 * TILE_BYTES : nullptr;
 #pragma unroll
-                for (int j = 0; j < 64; ++j) P.h_last[row * 64 + j] = h[j];
-            }
-            // q = fc2(h)
-            mbar_wait(q_full, t & 1);
-            tc_fence_after();
-            float* qo = P.q + ((int64_t)t * P.R + row) * P.A;
-            for (int c0 = 0; c0 < A_pad; c0 += 16) {
-                uint32_t aq[16];
-                tmem_ld_32x16(tlane + c0, aq);
-                tmem_wait_ld();
-                if (valid) {
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t ar[16], az[16], ain[16], ahn[16];
+                    tmem_ld_32x16(tlane + 16 * c, ar);
+                    tmem_ld_32x16(tlane + 64 + 16 * c, az);
+                    tmem_ld_32x16(tlane + 128 + 16 * c, ain);
+                    tmem_ld_32x16(tlane + 192 + 16 * c, ahn);
+                    tmem_wait_ld();
+                    float fr[16], fz[16], fn[16], fhn[16], fh[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < P.A) qo[c0 + j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
+                    for (int j = 0; j < 16; ++j) {
+                        const int jj = 16 * c + j;
+                        float rg = fast_sigmoid(__uint_as_float(ar[j]) + bias[jj]);
+                        float zg = fast_sigmoid(__uint_as_float(az[j]) + bias[64 + jj]);
+                        float hn = __uint_as_float(ahn[j]) + bias[192 + jj];
+                        float ng = fast_tanh(__uint_as_float(ain[j]) + bias[128 + jj] + rg * hn);
+                        float hv = ng + zg * (h[jj] - ng);
+                        h[jj] = hv;
+                        fr[j] = rg; fz[j] = zg; fn[j] = ng; fhn[j] = hn; fh[j] = hv;
+                    }
+                    store_row16(smem + HT, r, c, fh);
+                    if (valid) {
+                        if (hti) store_row16(hti, r, c, fh);
+                        if (gti) {
+                            store_row16(gti, r, c, fr);
+                            store_row16(gti + TILE_BYTES, r, c, fz);
+                            store_row16(gti + 2 * TILE_BYTES, r, c, fn);
+                            store_row16(gti + 3 * TILE_BYTES, r, c, fhn);
+                        }
+                    }
                 }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_ready);
+                if (valid && P.h_last && t == P.nt - 1) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4)
+                        *reinterpret_cast<float4*>(P.h_last + row * 64 + 4 * j4) =
+                            make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+                }
+                // q = fc2(h)
+                mbar_wait(q_full, it & 1);
+                tc_fence_after();
+                float* qo = P.q + ((int64_t)t * P.R + row) * P.A;
+                const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
+                for (int c0 = 0; c0 < A_pad; c0 += 16) {
+                    uint32_t aq[16];
+                    tmem_ld_32x16(tlane + c0, aq);
+                    tmem_wait_ld();
+                    if (valid) {
+                        if (q_vec) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                if (c0 + 4 * j4 < P.A)
+                                    *reinterpret_cast<float4*>(qo + c0 + 4 * j4) = make_float4(
+                                        __uint_as_float(aq[4 * j4]) + bias[256 + c0 + 4 * j4],
+                                        __uint_as_float(aq[4 * j4 + 1]) + bias[256 + c0 + 4 * j4 + 1],
+                                        __uint_as_float(aq[4 * j4 + 2]) + bias[256 + c0 + 4 * j4 + 2],
+                                        __uint_as_float(aq[4 * j4 + 3]) + bias[256 + c0 + 4 * j4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < P.A) qo[c0 + j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_free);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_free);
         }
     }
     tc_fence_before();
@@ -850,7 +877,8 @@ __global__ void ti_zero_pad_kernel(uint8_t* buf, int n_t, int n_tiles, int64_t R
 
 int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
     PMB_CUDA(cudaFuncSetAttribute(tc::gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gf::SMEM_BYTES));
-    tc::gru_fwd_tc_kernel<<<P.n_tiles, tc::gf::THREADS, tc::gf::SMEM_BYTES, s>>>(P);
+    const int grid = P.n_tiles < 2 * sm_count() ? P.n_tiles : 2 * sm_count();
+    tc::gru_fwd_tc_kernel<<<grid, tc::gf::THREADS, tc::gf::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("gru_fwd_tc_kernel");
     return PMB_OK;
 }
