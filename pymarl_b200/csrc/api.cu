@@ -46,9 +46,6 @@ int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, co
                    float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
 int64_t tc_atb_ti_scratch_bytes(int T, int n_tiles, int K);
 int64_t tc_fc1_scratch_bytes(const pmb_dims* d);
-int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
-                 __nv_bfloat16* raw_out, float* raw_f32, float* q_tot, void* scratch, int64_t scratch_bytes,
-                 cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;

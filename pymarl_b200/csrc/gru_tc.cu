@@ -6,13 +6,11 @@
 // a tile in, and the same bytes serve as K-major A operand (forward) and as MN-major operand (weight
 // gradients) - only the descriptor changes.
 //
-//   gru_fwd_tc : one CTA per 128-row tile, persistent over t.  W_ih / W_hh / fc2 images stay in shared
-//                memory, the hidden state stays in registers (fp32, one row per epilogue thread) and in
-//                a bf16 operand tile.  Per step: 16 tcgen05.mma for the gates (r|z fused over [x|h],
-//                n input part, n hidden part), gate math out of TMEM, 4 mma for fc2, q out of TMEM.
-//                2 CTAs per SM so one tile's gate math overlaps the other tile's MMAs.
-//   gru_bwd_tc : BPTT, two 128-row sub-tiles per CTA in ping-pong (the gate-gradient math of one
-//                overlaps the 24 mma of the other); dh stays in fp32 registers.
+//   gru_fwd_tc : the ROLLOUT step kernel (fp32 hidden state in and out, fc2 inside): persistent over 128-row tiles,
+//                W_ih / W_hh / fc2 images resident in shared memory, hidden state in registers (fp32, one row per
+//                epilogue thread) and in a bf16 operand tile.  Per step: 16 tcgen05.mma for the gates (r|z fused over
+//                [x|h], n input part, n hidden part), gate math out of TMEM, 4 mma for fc2, q out of TMEM.
+//                2 CTAs per SM.  (The learner step uses gru_fwd2 / gru_bwd2 / q_select in gru_tc2.cu.)
 //   gru_dw_tc  : rnn.weight_ih / weight_hh / biases: sum over (t, tile) of [dg]^T . [x | h | 1] with
 //                every operand bulk-copied (no conversion) - a pure HBM-bandwidth kernel.
 #include "common.cuh"
@@ -291,196 +289,6 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// backward (BPTT), two sub-tiles per CTA in ping-pong
-// ------------------------------------------------------------------------------------------
-namespace gb {
-constexpr int WIH = 0, WHH = 24576, DG = 49152;               // DG: [2 sub-tiles][4 gates][16 KB]
-constexpr int BARS = DG + 2 * 4 * TILE_BYTES;                 // 180224
-constexpr int SMEM_BYTES = 1024 + BARS + 128;
-constexpr int THREADS = 256;                                  // 2 sub-tiles x 4 warps; warp 0 of a sub-tile also issues its MMAs
-}  // namespace gb
-
-
-__device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
-    f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
-    f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-}
-
-__global__ void __launch_bounds__(gb::THREADS, 1) gru_bwd_tc_kernel(GruBwdParams P) {
-    using namespace gb;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
-    uint64_t* w_full = bars;
-    uint64_t* dg_ready = bars + 1;       // [2]
-    uint64_t* mma_done = bars + 3;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        mbar_init(w_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&dg_ready[i], 4); mbar_init(&mma_done[i], 1); }
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(w_full, 2 * 24576);
-        bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
-        bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
-    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);          // A K-major, B MN-major
-    {
-        const int st = warp >> 2;
-        const int tile = 2 * blockIdx.x + st;
-        if (tile < P.n_tiles) {
-            const uint32_t r = (warp & 3) * 32 + lane;
-            const int64_t row = (int64_t)tile * TILE_ROWS + r;
-            const bool valid = row < P.R;
-            const int64_t b = valid ? row / P.N : 0;
-            const int n = valid ? (int)(row - b * P.N) : 0;
-            uint8_t* dgs = smem + DG + st * 4 * TILE_BYTES;
-            const uint32_t tlane = tmem_base + st * 128 + ((uint32_t)((warp & 3) * 32) << 16);
-            float dh[64], zk[64];
-            uint64_t xmask = 0;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) dh[j] = 0.f;
-
-            for (int i = 0; i < P.T; ++i) {
-                const int t = P.T - 1 - i;
-                const int64_t toff = ((int64_t)t * P.n_tiles + tile) * TILE_BYTES;
-                uint8_t* g_t = P.g_ti + toff * 4;
-                // chosen-action gradient enters through fc2: dh += dq * fc2_w[a, :]
-                if (valid && t < P.T - 1) {
-                    const float dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
-                    if (dq != 0.f) {
-                        const int a = (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n);
-                        const float4* w2 = reinterpret_cast<const float4*>(P.fc2_w + (int64_t)a * 64);
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            float4 w = __ldg(w2 + q);
-                            dh[4 * q] = fmaf(dq, w.x, dh[4 * q]); dh[4 * q + 1] = fmaf(dq, w.y, dh[4 * q + 1]);
-                            dh[4 * q + 2] = fmaf(dq, w.z, dh[4 * q + 2]); dh[4 * q + 3] = fmaf(dq, w.w, dh[4 * q + 3]);
-                        }
-                    }
-                }
-                xmask = 0;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    // issue all loads of this half (32 columns = 4 chunks) before using them
-                    uint4 vr[4], vz[4], vn[4], vhn[4], vhp[4], vx[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t off = sw128_offset(r, 4 * half + c);
-                        if (valid) {
-                            vr[c] = *reinterpret_cast<const uint4*>(g_t + off);
-                            vz[c] = *reinterpret_cast<const uint4*>(g_t + TILE_BYTES + off);
-                            vn[c] = *reinterpret_cast<const uint4*>(g_t + 2 * TILE_BYTES + off);
-                            vhn[c] = *reinterpret_cast<const uint4*>(g_t + 3 * TILE_BYTES + off);
-                            vhp[c] = __ldg(reinterpret_cast<const uint4*>(P.h_ti + toff + off));
-                            vx[c] = __ldg(reinterpret_cast<const uint4*>(P.x_ti + toff + off));
-                        } else {
-                            vr[c] = vz[c] = vn[c] = vhn[c] = vhp[c] = vx[c] = make_uint4(0, 0, 0, 0);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float fr[8], fz[8], fn[8], fhn[8], fhp[8], fx[8], dr[8], dz[8], dn[8], dnr[8];
-                        unpack8(vr[c], fr); unpack8(vz[c], fz); unpack8(vn[c], fn); unpack8(vhn[c], fhn);
-                        unpack8(vhp[c], fhp); unpack8(vx[c], fx);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int jj = 32 * half + 8 * c + j;
-                            const float d = dh[jj];
-                            const float dnn = d * (1.f - fz[j]);
-                            const float dzz = d * (fhp[j] - fn[j]);
-                            const float da_n = dnn * (1.f - fn[j] * fn[j]);
-                            dr[j] = (da_n * fhn[j]) * fr[j] * (1.f - fr[j]);
-                            dz[j] = dzz * fz[j] * (1.f - fz[j]);
-                            dn[j] = da_n;
-                            dnr[j] = da_n * fr[j];
-                            zk[jj] = fz[j];
-                            xmask |= (uint64_t)(fx[j] > 0.f ? 1u : 0u) << jj;
-                        }
-                        const uint32_t off = sw128_offset(r, 4 * half + c);
-                        const uint4 pr = pack8(dr), pz = pack8(dz), pn = pack8(dn), pnr = pack8(dnr);
-                        *reinterpret_cast<uint4*>(dgs + off) = pr;
-                        *reinterpret_cast<uint4*>(dgs + TILE_BYTES + off) = pz;
-                        *reinterpret_cast<uint4*>(dgs + 2 * TILE_BYTES + off) = pn;
-                        *reinterpret_cast<uint4*>(dgs + 3 * TILE_BYTES + off) = pnr;
-                        // every row is written (padding rows of the last tile hold zeros) so that the
-                        // row reduction in gru_dw_tc sees finite values
-                        *reinterpret_cast<uint4*>(g_t + off) = pr;
-                        *reinterpret_cast<uint4*>(g_t + TILE_BYTES + off) = pz;
-                        *reinterpret_cast<uint4*>(g_t + 2 * TILE_BYTES + off) = pn;
-                        *reinterpret_cast<uint4*>(g_t + 3 * TILE_BYTES + off) = pnr;
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&dg_ready[st]);
-                if ((warp & 3) == 0 && lane == 0) {
-                    // this sub-tile's MMA issuer: wait for its four warps, then 24 tcgen05.mma
-                    if (i == 0) mbar_wait(w_full, 0);
-                    mbar_wait(&dg_ready[st], i & 1);
-                    tc_fence_after();
-                    const uint32_t dg = smem_u32(dgs);
-                    const uint32_t t_dx = tmem_base + st * 128, t_dh = t_dx + 64;
-                    // dx = da_r W_ir + da_z W_iz + da_n W_in
-#pragma unroll
-                    for (int g = 0; g < 3; ++g)
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16(t_dx, umma_desc_sw128(dg + g * TILE_BYTES + kk * 32, 16, 1024),
-                                      umma_desc_sw128(wih + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
-                    // dh_prev (recurrent part) = da_r W_hr + da_z W_hz + (da_n r) W_hn
-#pragma unroll
-                    for (int g = 0; g < 3; ++g)
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16(t_dh, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES + kk * 32, 16, 1024),
-                                      umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
-                    umma_commit(&mma_done[st]);
-                }
-                __syncwarp();
-
-                mbar_wait(&mma_done[st], i & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t ax[16], ah[16];
-                    tmem_ld_32x16(tlane + 16 * c, ax);
-                    tmem_ld_32x16(tlane + 64 + 16 * c, ah);
-                    tmem_wait_ld();
-                    float dp[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int jj = 16 * c + j;
-                        dp[j] = (xmask >> jj) & 1ull ? __uint_as_float(ax[j]) : 0.f;
-                        dh[jj] = dh[jj] * zk[jj] + __uint_as_float(ah[j]);
-                    }
-                    if (valid) store_row16(P.dpre1_ti + toff, r, c, dp);
-                }
-                tc_fence_before();
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
     }
@@ -936,11 +744,5 @@ int tc_ti_zero_pad(uint8_t* buf, int n_t, int n_tiles, int64_t R, cudaStream_t s
     return PMB_OK;
 }
 
-int tc_gru_bwd(const tc::GruBwdParams& P, cudaStream_t s) {
-    PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gb::SMEM_BYTES));
-    tc::gru_bwd_tc_kernel<<<(P.n_tiles + 1) / 2, tc::gb::THREADS, tc::gb::SMEM_BYTES, s>>>(P);
-    PMB_LAUNCH_CHECK("gru_bwd_tc_kernel");
-    return PMB_OK;
-}
 
 }  // namespace pmb

@@ -23,24 +23,10 @@ struct GruFwdParams {
     int nt, A, n_tiles;
 };
 
-struct GruBwdParams {
-    const __nv_bfloat16* w_ih_img;
-    const __nv_bfloat16* w_hh_img;
-    const float* fc2_w;              // fp32 [A][64]
-    const uint8_t* x_ti;             // [T][n_tiles][16 KB]  (online fc1 output, for the ReLU mask)
-    const uint8_t* h_ti;             // [(T+1)][n_tiles][16 KB]
-    uint8_t* g_ti;                   // [T][n_tiles][4][16 KB]: in (r, z, n, hn) -> out (da_r, da_z, da_n, da_n*r)
-    uint8_t* dpre1_ti;               // [T][n_tiles][16 KB]
-    const float* d_chosen;           // [B][T-1][N]
-    const int64_t* actions; int64_t actions_sb;
-    int64_t R;
-    int T, N, n_tiles;
-};
 
 }  // namespace tc
 
 int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s);
-int tc_gru_bwd(const tc::GruBwdParams& P, cudaStream_t s);
 int64_t tc_gru_dw_scratch_bytes();
 int tc_gru_dw(const uint8_t* g_ti, const uint8_t* x_ti, const uint8_t* h_ti, int T, int n_tiles, float* w_ih, float* w_hh,
               float* b_ih, float* b_hh, void* scratch, int64_t scratch_bytes, cudaStream_t s);

@@ -387,62 +387,6 @@ struct Fc1TiEpi {
 
 // QMIX mixing on the hypernet outputs, E = 32.  Packed column order: [ w1 (N*32) | b1 | w_final | v0 ].
 //   hidden = ELU(sum_n q[n] |w1[n, :]| + b1);  q_tot = hidden . |w_final| + V.2(ReLU(v0))
-// raw_out (optional, bf16 [M][(N+3)*32], packed column order) keeps the hypernet outputs for the backward.
-struct MixEpi {
-    struct Row { float hidden[32]; float y; };
-    const float* bias;          // [(N+3)*32] packed order
-    const float* agent_qs;      // [M][N]
-    const float* v2_w; const float* v2_b;
-    float* q_tot;               // [M]
-    __nv_bfloat16* raw_out;
-    float* raw_f32;             // optional fp32 copy in the FLAT column order [w1 | w_final | b1 | v0]
-    int N;
-    __device__ void begin(Row& r, int64_t, bool) const {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) r.hidden[e] = 0.f;
-        r.y = 0.f;
-    }
-    __device__ void cols(Row& r, int64_t m, bool valid, int col0, const uint32_t (&v)[32]) const {
-        const int grp = col0 >> 5;
-        float raw[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) raw[e] = __uint_as_float(v[e]) + __ldg(bias + col0 + e);
-        if (raw_out && valid) {
-            uint4* o = reinterpret_cast<uint4*>(raw_out + m * (int64_t)((N + 3) * 32) + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                o[q] = make_uint4(pack_bf16x2(raw[8 * q], raw[8 * q + 1]), pack_bf16x2(raw[8 * q + 2], raw[8 * q + 3]),
-                                  pack_bf16x2(raw[8 * q + 4], raw[8 * q + 5]), pack_bf16x2(raw[8 * q + 6], raw[8 * q + 7]));
-        }
-        if (raw_f32 && valid) {
-            const int fgrp = grp < N ? grp : (grp == N ? N + 1 : (grp == N + 1 ? N : N + 2));
-            float4* o = reinterpret_cast<float4*>(raw_f32 + m * (int64_t)((N + 3) * 32) + fgrp * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
-        }
-        if (grp < N) {
-            const float qn = valid ? __ldg(agent_qs + m * N + grp) : 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) r.hidden[e] = fmaf(qn, fabsf(raw[e]), r.hidden[e]);
-        } else if (grp == N) {                      // b1 -> hidden = ELU(pre)
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                float pre = r.hidden[e] + raw[e];
-                r.hidden[e] = pre > 0.f ? pre : expm1f(pre);
-            }
-        } else if (grp == N + 1) {                  // w_final
-#pragma unroll
-            for (int e = 0; e < 32; ++e) r.y = fmaf(r.hidden[e], fabsf(raw[e]), r.y);
-        } else {                                    // v0
-#pragma unroll
-            for (int e = 0; e < 32; ++e) r.y = fmaf(fmaxf(raw[e], 0.f), __ldg(v2_w + e), r.y);
-        }
-    }
-    __device__ void end(Row& r, int64_t m, bool valid) const {
-        if (valid) q_tot[m] = r.y + __ldg(v2_b);
-    }
-};
-
 // Mixer epilogue for the image-fed path: GEMM rows are ALL (b, t) pairs, m' = b*T + t.  The online mixer
 // (t_off = 0) uses rows t < T-1, the target mixer (t_off = 1) rows t >= 1; agent_qs / q_tot are indexed by
 // mq = b*(T-1) + t - t_off.  raw_img (online only): hypernet outputs as bf16 tile images
@@ -1038,28 +982,6 @@ __global__ void mix_bias_perm_kernel(const float* __restrict__ b_cat, int N, flo
 int64_t tc_mixer_scratch_bytes(const pmb_dims* d) {
     const int C = (d->N + 3) * 32;
     return align_up(tc_packed_elems((int)align_up(C, 32), d->S + 1) * 2, 256) + align_up((int64_t)C * 4, 256);
-}
-
-int tc_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const MixerParams& mp, const float* agent_qs, int t_off,
-                 __nv_bfloat16* raw_out, float* raw_f32, float* q_tot, void* scratch, int64_t scratch_bytes,
-                 cudaStream_t s) {
-    const int N = d->N, S = d->S, C = (N + 3) * 32;
-    if (scratch_bytes < tc_mixer_scratch_bytes(d)) { set_error("tc_mixer: scratch too small"); return PMB_ERR_WORKSPACE; }
-    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
-    float* bias = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(tc_packed_elems(C, S) * 2, 256));
-    // flat W_cat rows: [w1 (N*32) | w_final (32) | b1 (32) | v0 (32)]  ->  packed [w1 | b1 | w_final | v0]
-    const float* ptrs[4] = {mp.w_cat, mp.w_cat + (int64_t)(N + 1) * 32 * S, mp.w_cat + (int64_t)N * 32 * S,
-                            mp.w_cat + (int64_t)(N + 2) * 32 * S};
-    int rows[4] = {N * 32, 32, 32, 32}, lds[4] = {S, S, S, S};
-    int rc = tc_pack_w(ptrs, rows, lds, 4, S, wp, s);
-    if (rc) return rc;
-    mix_bias_perm_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, s>>>(mp.b_cat, N, bias);
-    PMB_LAUNCH_CHECK("mix_bias_perm_kernel");
-    const int64_t M = (int64_t)d->B * (d->T - 1);
-    RowMap smap{b->state_sb, (int64_t)S, 0, d->T - 1, 1};
-    tc::GemmParams P{b->state + (int64_t)t_off * S, smap, M, S, (S + tc::BK - 1) / tc::BK, wp, C, 0, 0, 0, 0, nullptr, nullptr};
-    tc::MixEpi epi{bias, agent_qs, mp.v2_w, mp.v2_b, q_tot, raw_out, raw_f32, N};
-    return tc::launch_tc_gemm(P, epi, s);
 }
 
 // ---- image-fed mixer path -------------------------------------------------------------------------

@@ -420,6 +420,14 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
         for name, prm in mod.named_parameters():
             gg = prm.grad.cpu().numpy()
             assert rel_err(prm.detach().cpu().numpy(), expect(init[name], gg)) < 1e-5, (kind, name)
+    # ... and the north_star statement itself: post-update parameters within 1e-2 of the reference algorithm's
+    # (norm-wise, per tensor), with the same pre-warmed RMSprop state on both sides.
+    oracle_after = {"agent": olr.agent, "mixer": olr.mixer_p}
+    for kind, mod in (("agent", learner.mac.agent), ("mixer", learner.mixer)):
+        if mod is None:
+            continue
+        for name, prm in mod.named_parameters():
+            assert rel_err(prm.detach().cpu().numpy(), oracle_after[kind][name]) < TOL_BF16, (kind, name)
 
 
 @pytest.mark.parametrize("shape_name,B", [("3m", 37), ("27m_vs_30m", 19)])
