@@ -629,7 +629,6 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         const uint32_t a_base = smem_u32(a_s) + ((uint32_t)(lane >> 2) << 4) + (lane & 3) * 4;   // + row*128, ^ swizzle
         uint32_t git = 0, ti = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
-            mbar_wait(a_free, (ti & 1) ^ 1);                 // MMAs and the image store of the previous tile are done with A
             for (int g = 0; g < GROUPS; ++g, ++git) {
                 const int slot = git % N_SLOTS;
                 mbar_wait(&st_full[slot], (git / N_SLOTS) & 1);
@@ -650,27 +649,37 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                             if ((m1 >> c) & 1u) v1[rr][c] = lds_f32(src + c * 256 + 4);
                         }
                     }
+                    // pack first (consumes every loaded value), release the staging slot, then write the A tile
+                    uint32_t pk[2][MAX_CHUNKS];
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
                         const int off = rr ? off2.y : off2.x;
                         const int nn = rr ? nn2.y : nn2.x;
-                        const uint32_t rt = (uint32_t)(g * GROUP_ROWS + 2 * cw + rr);
-                        const uint32_t dst = (a_base + rt * 128u) ^ ((rt & 7u) << 4);
                         // one-hot(agent) and the bias column live in the K padding of the last chunk
                         const bool fold = P.fold_id && off >= 0;
                         const bool hit0 = fold && j_pad >= 0 && (j_pad == nn || j_pad == P.N);
                         const bool hit1 = fold && j_pad + 1 >= 0 && (j_pad + 1 == nn || j_pad + 1 == P.N);
 #pragma unroll
+                        for (int c = 0; c < MAX_CHUNKS; ++c) {
+                            float a = v0[rr][c], b = v1[rr][c];
+                            if (c == c_last) { a = hit0 ? 1.0f : a; b = hit1 ? 1.0f : b; }
+                            pk[rr][c] = pack_bf16x2(a, b);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&st_empty[slot]);
+                    // the first group of a tile waits here (values already in registers, slot already released) until
+                    // the MMAs and the image store of the previous tile are done with the A tile
+                    if (g == 0) mbar_wait(a_free, (ti & 1) ^ 1);
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const uint32_t rt = (uint32_t)(g * GROUP_ROWS + 2 * cw + rr);
+                        const uint32_t dst = (a_base + rt * 128u) ^ ((rt & 7u) << 4);
+#pragma unroll
                         for (int c = 0; c < MAX_CHUNKS; ++c)
-                            if (c < P.n_chunks) {
-                                float a = v0[rr][c], b = v1[rr][c];
-                                if (c == c_last) { a = hit0 ? 1.0f : a; b = hit1 ? 1.0f : b; }
-                                sts_b32(dst + c * A_STAGE_BYTES, pack_bf16x2(a, b));
-                            }
+                            if (c < P.n_chunks) sts_b32(dst + c * A_STAGE_BYTES, pk[rr][c]);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&st_empty[slot]);
             }
             fence_proxy_async_smem();
             __syncwarp();
