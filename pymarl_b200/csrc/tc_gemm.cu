@@ -477,8 +477,9 @@ namespace fs {
 constexpr int MAX_CHUNKS = 5;
 constexpr int GROUP_ROWS = 16, GROUPS = BM / GROUP_ROWS;
 constexpr int N_SLOTS = 3;
-constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_PROD = 2, STORE_W = 7, FIRST_CONV_W = 8, N_CONV = 8;
-constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);       // 512
+constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_PROD = 3, STORE_W = 8, FIRST_CONV_W = 9, N_CONV = 8;
+constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);       // 544
+static_assert(N_PROD == N_SLOTS, "every producer warp owns one staging slot (parity waits are only safe one phase apart)");
 constexpr int N_FIX_LANES = 6;                              // lanes 1-3 head floats, 4-6 tail floats
 }  // namespace fs
 
@@ -548,8 +549,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
     const int64_t n_items = (int64_t)P.T * P.n_tiles;
 
     if (warp >= PROD_W && warp < PROD_W + N_PROD) {
-        // two producer warps take alternate groups: the address walk of ONE warp (dependent integer code) capped the
-        // stream at 2.9 TB/s
+        // one producer warp per staging slot: the address walk of a warp is ~300 dependent integer instructions per
+        // group (~1.5 us); ONE warp capped the stream at 2.9 TB/s, two at 4.6 TB/s.  A slot is always filled by the
+        // same warp, so consecutive uses of a slot are program-ordered (a parity wait must never be two phases ahead).
         const int pw = warp - PROD_W;
         if (pw == 0 && lane == 0) {
             mbar_arrive_expect_tx(w_full, (uint32_t)tile_bytes);
@@ -559,8 +561,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
             for (int g = 0; g < GROUPS; ++g, ++git) {
-                if ((g & (N_PROD - 1)) != pw) continue;
                 const int slot = git % N_SLOTS;
+                if (slot != pw) continue;
                 mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
                 uint8_t* sl = stage + slot * P.slot_bytes;
                 int* ro = rowoff + slot * GROUP_ROWS;
