@@ -231,6 +231,12 @@ int64_t pmb_launch_count(void);      /* kernels launched by this library since i
 int pmb_profile_begin(void);
 int pmb_profile_end(float* ms_host, char* names_host, int32_t names_stride, int32_t max_phases, int32_t* n_out);
 
+/* Strided host -> device copy of `rows` pieces of `row_bytes` (source pitch `src_pitch_bytes`, destination dense):
+ * one cudaMemcpy2DAsync.  Replaces the per-timestep `.to(self.args.device)` of a host-resident runner batch
+ * (controllers/basic_controller.py:32,105,113), which materialises a contiguous host copy of `batch[k][:, t]` first. */
+int pmb_h2d_rows(void* dst_dev, const void* src_host, int64_t rows, int64_t row_bytes, int64_t src_pitch_bytes,
+                 pmb_stream stream);
+
 /* views into the learner workspace, for tests and the Python mirror */
 typedef struct pmb_ws_views {
     float *x_on, *x_tg, *h_stash, *gates, *q_on, *q_tg, *chosen, *tmax, *raw_on, *raw_tg,

@@ -73,6 +73,7 @@ _SIGS = {
     "pmb_launch_count": (C.c_int64, []),
     "pmb_profile_begin": (C.c_int, []),
     "pmb_profile_end": (C.c_int, [C.POINTER(C.c_float), C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "pmb_h2d_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "pmb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)]),
     "pmb_flat_layout": (C.c_int, [C.POINTER(Dims), C.POINTER(Layout)]),
     "pmb_learner_workspace_bytes": (C.c_int64, [C.POINTER(Dims)]),
@@ -183,6 +184,23 @@ def _batch_stride(t, inner):
 
 _FIELD_DTYPES = {"obs": th.float32, "state": th.float32, "actions": th.int64, "avail_actions": th.int32,
                  "reward": th.float32, "terminated": th.uint8, "filled": th.int64}
+
+
+def h2d_time_slice(t, lo, hi, dev):
+    """``t[:, lo:hi]`` of a host tensor [B, T, ...] as a dense device tensor, copied with ONE strided
+    cudaMemcpy2DAsync (no contiguous host temporary).  Falls back to torch for exotic layouts."""
+    import torch as th
+    B, T = t.shape[0], t.shape[1]
+    inner = 1
+    for s in t.shape[2:]:
+        inner *= s
+    if t.is_cuda or t.dim() < 2 or not t[0].is_contiguous() or t.stride(0) != T * inner or B == 0:
+        return t[:, lo:hi].to(dev, non_blocking=True)
+    out = th.empty((B, hi - lo) + tuple(t.shape[2:]), dtype=t.dtype, device=dev)
+    es = t.element_size()
+    check(lib().pmb_h2d_rows(ptr(out), C.c_void_p(t.data_ptr() + lo * inner * es), B, (hi - lo) * inner * es,
+                             T * inner * es, stream_ptr(dev)), "pmb_h2d_rows")
+    return out
 
 
 def make_batch(fields, need_state=True, keep=None):

@@ -61,7 +61,7 @@ class BasicMAC:
         else:
             lo = max(t - 1, 0)
             for k in ("obs", "actions", "avail_actions", "filled"):
-                fields[k] = ep_batch[k][:, lo:t + 1].to(dev, non_blocking=True)
+                fields[k] = _lib.h2d_time_slice(ep_batch[k], lo, t + 1, dev)
             t_local, T_local = t - lo, t + 1 - lo
         zero = th.zeros(1, dtype=th.float32, device=dev)
         fields.update(state=zero, reward=zero, terminated=zero.to(th.uint8))

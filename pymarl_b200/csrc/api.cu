@@ -327,7 +327,15 @@ int pmb_profile_end(float* ms_host, char* names_host, int32_t names_stride, int3
     t.n = 0;
     return PMB_OK;
 }
-int pmb_version(void) { return 100; }
+int pmb_version(void) { return 101; }
+
+int pmb_h2d_rows(void* dst_dev, const void* src_host, int64_t rows, int64_t row_bytes, int64_t src_pitch_bytes,
+                 pmb_stream stream) {
+    PMB_REQUIRE(dst_dev && src_host && rows > 0 && row_bytes > 0 && src_pitch_bytes >= row_bytes, "h2d_rows: bad arguments");
+    PMB_CUDA(cudaMemcpy2DAsync(dst_dev, (size_t)row_bytes, src_host, (size_t)src_pitch_bytes, (size_t)row_bytes, (size_t)rows,
+                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return PMB_OK;
+}
 
 int pmb_device_info(int32_t* sm, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin) {
     int dev = 0;
