@@ -143,6 +143,122 @@ __global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img_kernel(MixBwdParams
     }
 }
 
+// Lean variant for up to 16 column blocks (N <= 29), ~3x fewer instructions per row than the generic kernel above
+// (which was issue-bound at 1370 warp instructions per row): sign(w) is applied to both bf16 halves of a word with
+// one XOR on the packed product, group membership tests are hoisted into two per-lane bounds, and the 16 per-lane
+// d_q partials are reduced with a 4-stage reduce-scatter (15 shuffles instead of 60) that leaves one group sum per
+// lane for a single coalesced store.
+__global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img16_kernel(MixBwdParams P) {
+    __shared__ float red[MB_WARPS][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t n_warps = (int64_t)gridDim.x * MB_WARPS;          // multiple of 8: (row & 7) is fixed per warp
+    const int N = P.N;
+    float dv2w0 = 0.f, dv2w1 = 0.f, dv2b = 0.f;
+    const int j = (lane >> 2) ^ wib;                                // logical 16-byte chunk (row & 7 == wib)
+    const int h = j >> 2;                                           // group parity: this lane sees group 2*cb + h
+    const int e0 = (j & 3) * 8 + (lane & 3) * 2;
+    const float v2w0 = __ldg(P.v2_w + e0), v2w1 = __ldg(P.v2_w + e0 + 1);
+    const int n_w1 = (N - h + 1) >> 1;                              // cb < n_w1  <=>  group 2*cb + h is a w1 group
+    // block index / need-partner flags of the three special groups for this lane
+    const int cb_b1 = N >> 1, cb_wf = (N + 1) >> 1, cb_v0 = (N + 2) >> 1;
+    const bool sw_b1 = h != (N & 1), sw_wf = h != ((N + 1) & 1), sw_v0 = h != ((N + 2) & 1);
+    const int my_grp = 2 * (lane & 15) + h;                         // the group whose d_q this lane ends up holding
+
+    for (int64_t m = (int64_t)blockIdx.x * MB_WARPS + wib; m < P.rows_total; m += n_warps) {
+        uint8_t* base = P.raw_img + (m >> 7) * (int64_t)P.n_cblk * 16384 + (m & 127) * 128 + lane * 4;
+        int64_t mq = -1;
+        if (m < P.BT) {
+            const uint32_t b = (uint32_t)m / (uint32_t)P.T;          // B*T < 2^31 (checked by the launcher)
+            const int t = (int)((uint32_t)m - b * (uint32_t)P.T);
+            if (t < P.T - 1) mq = (int64_t)b * (P.T - 1) + t;
+        }
+        if (mq < 0) {                                               // no online-mixer row here: d_raw = 0
+            for (int cb = 0; cb < P.n_cblk; ++cb) *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = 0u;
+            continue;
+        }
+        const float gm = __ldg(P.g + mq);
+        const float* qs = P.agent_qs + mq * N + h;
+        uint32_t wv[16];
+        float qv[16];
+#pragma unroll
+        for (int cb = 0; cb < 16; ++cb) {
+            wv[cb] = 0u; qv[cb] = 0.f;
+            if (cb < P.n_cblk) wv[cb] = *reinterpret_cast<const uint32_t*>(base + (int64_t)cb * 16384);
+            if (cb < n_w1) qv[cb] = __ldg(qs + 2 * cb);
+        }
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int cb = 0; cb < 16; ++cb) {                           // qv = 0 outside the w1 groups
+            acc0 = fmaf(qv[cb], fabsf(mt_lo(wv[cb])), acc0);
+            acc1 = fmaf(qv[cb], fabsf(mt_hi(wv[cb])), acc1);
+        }
+        uint32_t w_b1 = 0u, w_wf = 0u, w_v0 = 0u;
+#pragma unroll
+        for (int cb = 0; cb < 16; ++cb) {
+            w_b1 = cb == cb_b1 ? wv[cb] : w_b1;
+            w_wf = cb == cb_wf ? wv[cb] : w_wf;
+            w_v0 = cb == cb_v0 ? wv[cb] : w_v0;
+        }
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
+        const uint32_t o_b1 = __shfl_xor_sync(0xffffffffu, w_b1, 16), o_wf = __shfl_xor_sync(0xffffffffu, w_wf, 16),
+                       o_v0 = __shfl_xor_sync(0xffffffffu, w_v0, 16);
+        w_b1 = sw_b1 ? o_b1 : w_b1; w_wf = sw_wf ? o_wf : w_wf; w_v0 = sw_v0 ? o_v0 : w_v0;
+        const float pre0 = acc0 + mt_lo(w_b1), pre1 = acc1 + mt_hi(w_b1);
+        const float hid0 = pre0 > 0.f ? pre0 : expm1f(pre0), hid1 = pre1 > 0.f ? pre1 : expm1f(pre1);
+        const float wf0 = mt_lo(w_wf), wf1 = mt_hi(w_wf), v00 = mt_lo(w_v0), v01 = mt_hi(w_v0);
+        const float dp0 = gm * fabsf(wf0) * (pre0 > 0.f ? 1.f : __expf(pre0));
+        const float dp1 = gm * fabsf(wf1) * (pre1 > 0.f ? 1.f : __expf(pre1));
+        const uint32_t d_wf = pack_bf16x2(mt_sgn(wf0) * gm * hid0, mt_sgn(wf1) * gm * hid1);
+        const uint32_t d_b1 = pack_bf16x2(dp0, dp1);
+        const uint32_t d_v0 = pack_bf16x2(v00 > 0.f ? gm * v2w0 : 0.f, v01 > 0.f ? gm * v2w1 : 0.f);
+        if (h == 0) {
+            dv2w0 = fmaf(gm, fmaxf(v00, 0.f), dv2w0);
+            dv2w1 = fmaf(gm, fmaxf(v01, 0.f), dv2w1);
+        }
+        if (lane == 0) dv2b += gm;
+        float part[16];
+#pragma unroll
+        for (int cb = 0; cb < 16; ++cb) {
+            const uint32_t w = wv[cb];
+            // d_w1 = sign(w) q dpre : sign bits XORed into the packed product, exact zeros of w (sign(0) = 0) masked out
+            const uint32_t prod = pack_bf16x2(qv[cb] * dp0, qv[cb] * dp1);
+            const uint32_t mag = w & 0x7fff7fffu;
+            const uint32_t nz = (((mag + 0x7fff7fffu) | mag) & 0x80008000u) >> 15;      // 1 per non-zero half
+            uint32_t out = (prod ^ (w & 0x80008000u)) & (nz * 0xffffu);
+            part[cb] = fmaf(fabsf(mt_lo(w)), dp0, fabsf(mt_hi(w)) * dp1);               // garbage for non-w1 groups: not stored
+            out = cb < n_w1 ? out : 0u;
+            out = cb == cb_b1 && !sw_b1 ? d_b1 : out;
+            out = cb == cb_wf && !sw_wf ? d_wf : out;
+            out = cb == cb_v0 && !sw_v0 ? d_v0 : out;
+            if (cb < P.n_cblk) *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = out;
+        }
+        // reduce-scatter over the 16 lanes of a parity: after the stage with distance d a lane keeps the half of
+        // its values selected by (lane & d); lane l ends with the sum for block l & 15
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1) {
+            const bool up = (lane & d) != 0;
+#pragma unroll
+            for (int i = 0; i < d; ++i) {
+                const float send = up ? part[i] : part[i + d];
+                const float keep = up ? part[i + d] : part[i];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+            }
+        }
+        if (my_grp < N) P.d_qs[mq * N + my_grp] = part[0];
+    }
+    for (int i = lane; i < 33; i += 32) red[wib][i] = 0.f;
+    __syncwarp();
+    if (h == 0) { red[wib][e0] = dv2w0; red[wib][e0 + 1] = dv2w1; }
+    if (lane == 0) red[wib][32] = dv2b;
+    __syncthreads();
+    if (threadIdx.x < 33) {
+        float s = 0.f;
+        for (int w = 0; w < MB_WARPS; ++w) s += red[w][threadIdx.x];
+        P.v2_partial[(int64_t)blockIdx.x * 33 + threadIdx.x] = s;
+    }
+}
+
 __global__ void mix_v2_reduce_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ dv2_w,
                                      float* __restrict__ dv2_b) {
     const int i = threadIdx.x;
@@ -338,7 +454,7 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
     tc::MixBwdParams B;
     B.raw_img = raw_img; B.agent_qs = agent_qs; B.g = g; B.v2_w = mp.v2_w; B.d_qs = d_agent_qs; B.v2_partial = v2_partial;
     B.BT = (int64_t)d->B * d->T; B.rows_total = tc_mix_row_tiles(d) * 128; B.T = d->T; B.N = d->N; B.n_cblk = tc_mix_cblks(d);
-    if (B.n_cblk <= 16) tc::mix_bwd_img_kernel<16><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
+    if (B.n_cblk <= 16 && B.rows_total < (1ll << 31)) tc::mix_bwd_img16_kernel<<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
     else tc::mix_bwd_img_kernel<34><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
     PMB_LAUNCH_CHECK("mix_bwd_img_kernel");
     tc::mix_v2_reduce_kernel<<<1, 64, 0, s>>>(v2_partial, grid, gv2_w, gv2_b);
