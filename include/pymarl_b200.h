@@ -231,6 +231,21 @@ int64_t pmb_launch_count(void);      /* kernels launched by this library since i
 int pmb_profile_begin(void);
 int pmb_profile_end(float* ms_host, char* names_host, int32_t names_stride, int32_t max_phases, int32_t* n_out);
 
+/* ---- replay buffer in HBM ---------------------------------------------------------------
+ * pmb_gather_episodes: dst[f][j] = src[f][ep_ids[j]] for every field f, whole episodes (contiguous [T, ...] blocks of
+ * bytes_per_episode bytes) - ReplayBuffer.sample / EpisodeBatch.__getitem__(ndarray) (components/episode_buffer.py:
+ * 205-217, 291-298) in ONE launch.  `fields` is a HOST array; ep_ids is a device array of n_ids (< 65536) ids in
+ * [0, n_src_episodes).
+ * pmb_max_t_filled: out[0] = max_b sum_t filled[b, t]  (episode_buffer.py:255-256), device scalar. */
+typedef struct pmb_gather_field {
+    const void* src;
+    void* dst;
+    int64_t bytes_per_episode;
+} pmb_gather_field;
+int pmb_gather_episodes(const pmb_gather_field* fields_host, int32_t n_fields, const int64_t* ep_ids, int64_t n_ids,
+                        int64_t n_src_episodes, pmb_stream stream);
+int pmb_max_t_filled(const int64_t* filled, int64_t B, int32_t T, int64_t filled_sb, int64_t* out, pmb_stream stream);
+
 /* Strided host -> device copy of `rows` pieces of `row_bytes` (source pitch `src_pitch_bytes`, destination dense):
  * one cudaMemcpy2DAsync.  Replaces the per-timestep `.to(self.args.device)` of a host-resident runner batch
  * (controllers/basic_controller.py:32,105,113), which materialises a contiguous host copy of `batch[k][:, t]` first. */

@@ -52,6 +52,10 @@ class HParams(C.Structure):
                 ("keep_q", C.c_int32)]
 
 
+class GatherField(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes_per_episode", C.c_int64)]
+
+
 class WsViews(C.Structure):
     _names = ("x_on", "x_tg", "h_stash", "gates", "q_on", "q_tg", "chosen", "tmax", "raw_on", "raw_tg",
               "q_tot", "t_tot", "g", "d_chosen", "scratch")
@@ -73,6 +77,8 @@ _SIGS = {
     "pmb_launch_count": (C.c_int64, []),
     "pmb_profile_begin": (C.c_int, []),
     "pmb_profile_end": (C.c_int, [C.POINTER(C.c_float), C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "pmb_gather_episodes": (C.c_int, [C.POINTER(GatherField), C.c_int32, _P, C.c_int64, C.c_int64, _P]),
+    "pmb_max_t_filled": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P]),
     "pmb_h2d_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "pmb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)]),
     "pmb_flat_layout": (C.c_int, [C.POINTER(Dims), C.POINTER(Layout)]),
@@ -200,6 +206,27 @@ def h2d_time_slice(t, lo, hi, dev):
     es = t.element_size()
     check(lib().pmb_h2d_rows(ptr(out), C.c_void_p(t.data_ptr() + lo * inner * es), B, (hi - lo) * inner * es,
                              T * inner * es, stream_ptr(dev)), "pmb_h2d_rows")
+    return out
+
+
+def gather_episodes(src_tensors, ep_ids, n_src):
+    """out[k][j] = src[k][ep_ids[j]] for a dict of contiguous CUDA tensors [n_src, ...] in one launch."""
+    import torch as th
+    keys = list(src_tensors)
+    dev = src_tensors[keys[0]].device
+    ids = th.as_tensor(ep_ids, dtype=th.int64).to(dev)
+    n = ids.numel()
+    out = {k: th.empty((n,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in src_tensors.items()}
+    for i in range(0, len(keys), 16):
+        chunk = keys[i:i + 16]
+        arr = (GatherField * len(chunk))()
+        for j, k in enumerate(chunk):
+            v = src_tensors[k]
+            require_cuda(v, "buffer[%r]" % k)
+            if not v.is_contiguous():
+                raise PmbError("gather_episodes needs contiguous buffer fields (%r is not)" % k)
+            arr[j] = GatherField(v.data_ptr(), out[k].data_ptr(), v[0].numel() * v.element_size())
+        check(lib().pmb_gather_episodes(arr, len(chunk), ptr(ids), n, n_src, stream_ptr(dev)), "pmb_gather_episodes")
     return out
 
 

@@ -128,12 +128,37 @@ class EpisodeBatch:
             return EpisodeBatch(scheme, groups, self.batch_size, self.max_seq_length, data=new, device=self.device)
         sl = self._parse_slices(item)
         new = SimpleNamespace(transition_data={}, episode_data={})
+        if self._gpu_gather_ok(sl):
+            # episode ids on a buffer that lives in HBM: ONE gather launch for all fields (pmb_gather_episodes),
+            # then the (contiguous) time slice as a view
+            from .. import _lib
+            ids = np.asarray(sl[0].cpu() if isinstance(sl[0], th.Tensor) else sl[0]).reshape(-1)
+            if ids.size and (ids.min() < 0 or ids.max() >= self.batch_size):
+                raise IndexError("episode id out of range")
+            tr = _lib.gather_episodes(self.data.transition_data, ids, self.batch_size)
+            new.transition_data = {k: v[:, sl[1]] for k, v in tr.items()}
+            if self.data.episode_data:
+                new.episode_data = _lib.gather_episodes(self.data.episode_data, ids, self.batch_size)
+            return EpisodeBatch(self.scheme, self.groups, int(ids.size), self._num_items(sl[1], self.max_seq_length),
+                                data=new, device=self.device)
         for k, v in self.data.transition_data.items():
             new.transition_data[k] = v[tuple(sl)]
         for k, v in self.data.episode_data.items():
             new.episode_data[k] = v[sl[0]]
         return EpisodeBatch(self.scheme, self.groups, self._num_items(sl[0], self.batch_size),
                             self._num_items(sl[1], self.max_seq_length), data=new, device=self.device)
+
+    def _gpu_gather_ok(self, sl):
+        if not isinstance(sl[0], (list, np.ndarray, th.Tensor)) or not isinstance(sl[1], slice):
+            return False
+        if isinstance(sl[0], th.Tensor) and sl[0].dtype == th.bool:
+            return False
+        if isinstance(sl[0], np.ndarray) and sl[0].dtype == np.bool_:
+            return False
+        tensors = list(self.data.transition_data.values()) + list(self.data.episode_data.values())
+        n = len(sl[0]) if not isinstance(sl[0], th.Tensor) else sl[0].numel()
+        return bool(tensors) and 0 < n < 65536 and all(v.is_cuda and v.is_contiguous() for v in tensors) and \
+            (sl[1].step in (None, 1))
 
     @staticmethod
     def _num_items(idx, max_size):
@@ -153,7 +178,14 @@ class EpisodeBatch:
         return [slice(it, it + 1) if isinstance(it, int) else it for it in items]
 
     def max_t_filled(self):
-        return th.sum(self.data.transition_data["filled"], 1).max(0)[0]
+        f = self.data.transition_data["filled"]
+        if f.is_cuda and f.dtype == th.int64 and f.dim() == 3 and f.shape[2] == 1 and f.stride(1) == 1 and f.shape[0] > 0:
+            from .. import _lib
+            out = th.empty(1, dtype=th.int64, device=f.device)
+            _lib.check(_lib.lib().pmb_max_t_filled(_lib.ptr(f), f.shape[0], f.shape[1], f.stride(0), _lib.ptr(out),
+                                                   _lib.stream_ptr(f.device)), "pmb_max_t_filled")
+            return out[0]
+        return th.sum(f, 1).max(0)[0]
 
     def __repr__(self):
         return "EpisodeBatch. Batch Size:{} Max_seq_len:{} Keys:{} Groups:{}".format(

@@ -483,3 +483,41 @@ def test_bf16_tier_rollout_steps_match_oracle(shape_name, B):
             results[(device, t)] = q
     for t in range(3):
         np.testing.assert_array_equal(results[("cuda", t)], results[("cpu", t)])
+
+
+def test_replay_sample_on_device_is_bit_exact():
+    """ReplayBuffer in HBM: sample() = numpy ids (same legacy RandomState as the reference) + ONE
+    pmb_gather_episodes launch over all fields; max_t_filled on the device.  Everything is integer / byte copying:
+    bit-exact against the same buffer held on the host, including odd field sizes (1-, 4-, 8- and 16-byte paths)."""
+    from pymarl_b200 import ReplayBuffer
+    from pymarl_b200.components.transforms import OneHot
+    shape = SmacShape("odd", 3, 7, 5, 6, 11)                 # obs 3*7*4 = 84 B per step: only 4-byte aligned
+    from pymarl_b200.synthetic import make_scheme
+    scheme, groups = make_scheme(shape)
+    preprocess = {"actions": ("actions_onehot", [OneHot(out_dim=shape.n_actions)])}
+    fields = numpy_episode_fields(shape, 24, shape.max_seq_length, seed=4, ragged=True)
+    bufs = {}
+    for dev in ("cpu", "cuda"):
+        buf = ReplayBuffer(scheme, groups, 32, shape.max_seq_length, preprocess=preprocess, device=dev)
+        for k, v in fields.items():
+            buf.data.transition_data[k][:24] = th.from_numpy(np.ascontiguousarray(v)).to(dev)
+        buf.buffer_index, buf.episodes_in_buffer = 24, 24
+        bufs[dev] = buf
+    for n in (1, 5, 16):
+        np.random.seed(123 + n)
+        a = bufs["cpu"].sample(n)
+        np.random.seed(123 + n)
+        b = bufs["cuda"].sample(n)
+        assert b.batch_size == n and b.device == "cuda"
+        for k in a.data.transition_data:
+            assert b[k].is_cuda
+            np.testing.assert_array_equal(a[k].numpy(), b[k].cpu().numpy(), err_msg=k)
+        assert int(a.max_t_filled()) == int(b.max_t_filled())
+        t = int(b.max_t_filled())
+        at, bt = a[:, :t], b[:, :t]
+        np.testing.assert_array_equal(at["obs"].numpy(), bt["obs"].cpu().numpy())
+    # explicit ids, repeated and out of order; an out-of-range id raises like torch indexing does
+    ids = np.array([7, 0, 7, 23, 3])
+    np.testing.assert_array_equal(bufs["cpu"][ids]["avail_actions"].numpy(), bufs["cuda"][ids]["avail_actions"].cpu().numpy())
+    with pytest.raises(IndexError):
+        bufs["cuda"][np.array([0, 32])]
