@@ -519,6 +519,10 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
 //   elements it has just read), are the K-major A operands of the 24 tcgen05.mma (dx = dg . W_ih, dh_rec = dg' . W_hh;
 //   B = the weight images read MN-major) and leave as ONE 64 KB bulk store into the gate stash (gru_dw reads them);
 //   the h_prev slot is reused as the staging tile of dpre1 = relu'(x) dx.  dh stays in fp32 registers.
+//   rnn.weight_hh is accumulated HERE (the gate gradients and h_{t-1} are in shared memory anyway): 16 more
+//   tcgen05.mma per step, [da_r|da_z]^T h_{t-1} and [da_n|da_n r]^T h_{t-1} with both operands read MN-major, into 128
+//   TMEM columns that live for the whole kernel; sum(da_n r) (bias_hh[n]) in fp32 registers.  Only three gradient tiles
+//   (da_r, da_z, da_n) go back to the stash for gru_dw_tc (rnn.weight_ih).
 namespace b2 {
 constexpr int WIH = 0, WHH = 24576;
 constexpr int BUF = 49152;                         // [2][5][16 KB]
@@ -542,6 +546,7 @@ struct GruBwd2Params {
     const uint32_t* relu_mask;       // [T][n_tiles][2][128]: bit j of word (half, row) = fc1 output column 32*half + j > 0
     const float* d_chosen;           // [B][T-1][N]
     const int64_t* actions; int64_t actions_sb;
+    float* whh_partial;              // [n_tiles][192*64 + 64]: this tile's rnn.weight_hh gradient and sum of da_n*r
     int64_t R;
     int T, N, A, n_tiles;
 };
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
         mbar_init(dg_ready, N_EPI_WARPS); mbar_init(mma_done, 1); mbar_init(dp_ready, N_EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 128);
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
     // fc2.weight table (bf16, padded rows)
     for (int i = threadIdx.x; i < P.A * 32; i += THREADS) {
         const int a = i >> 5, c = (i & 31) * 2;
@@ -577,6 +582,14 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // epilogue-warp coordinates (used again in the common tail): warp w owns rows 32 (w & 3) .. +31 and hidden
+    // columns 32 ((w >> 2) & 1) .. +31
+    const int q4 = warp & 3, ch = (warp >> 2) & 1;
+    const uint32_t r = (uint32_t)(q4 * 32 + lane);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 32 * ch;
+    float bsum[32];                                            // sum over steps of da_n * r of this row / these columns
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bsum[j] = 0.f;
 
     if (warp == IO_WARP) {
         if (lane == 0) {
@@ -598,7 +611,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                 const int64_t tt = (int64_t)t * P.n_tiles + tile;
                 uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
                 mbar_wait(dg_ready, (uint32_t)(i & 1));
-                bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, buf, 4 * TILE_BYTES2);
+                bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, buf, 3 * TILE_BYTES2);      // da_r, da_z, da_n for gru_dw_tc
                 bulk_commit_group();
                 mbar_wait(dp_ready, (uint32_t)(i & 1));        // implies the MMAs of this step have completed
                 bulk_copy_s2g(P.dpre1_ti + tt * TILE_BYTES2, buf + 4 * TILE_BYTES2, TILE_BYTES2);
@@ -612,6 +625,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
         if (lane == 0) {
             const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
             const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);          // A K-major, B MN-major
+            const uint32_t idesc_dw = umma_idesc_bf16(128, 64, 1, 1);       // both MN-major: reduction over the 128 rows
             mbar_wait(w_full, 0);
             for (int i = 0; i < P.T; ++i) {
                 const uint32_t dg = smem_u32(smem + BUF + (i & 1) * BUF_BYTES);
@@ -631,14 +645,20 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16(tmem_base + 64, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES2 + kk * 32, 16, 1024),
                                   umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                // rnn.weight_hh += [da_r|da_z]^T h_prev  and  [da_n|da_n r]^T h_prev  (accumulated over all steps)
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t acc = (i | kk) != 0;
+                    const uint64_t b_h = umma_desc_sw128(dg + 4 * TILE_BYTES2 + kk * 2048, TILE_BYTES2, 1024);
+                    umma_bf16(tmem_base + 128, umma_desc_sw128(dg + kk * 2048, TILE_BYTES2, 1024), b_h, idesc_dw, acc);
+                    umma_bf16(tmem_base + 192, umma_desc_sw128(dg + 2 * TILE_BYTES2 + kk * 2048, TILE_BYTES2, 1024), b_h,
+                              idesc_dw, acc);
+                }
                 umma_commit(mma_done);
             }
         }
     } else {
-        // ===== 8 warps: warp w owns rows 32 (w & 3) .. +31 and hidden columns 32 (w >> 2) .. +31 =====
-        const int q4 = warp & 3, ch = warp >> 2;
-        const uint32_t r = (uint32_t)(q4 * 32 + lane);
-        const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 32 * ch;
+        // ===== 8 warps: gate-gradient math, dh update =====
         const int64_t row = (int64_t)tile * TILE_ROWS2 + r;
         const bool valid = row < P.R;
         const int64_t b = valid ? row / P.N : 0;
@@ -703,6 +723,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                         dz2[e] = d * (fhp - fn) * fz * (1.f - fz);
                         dn2[e] = da_n;
                         dnr2[e] = da_n * fr;
+                        bsum[jj] += dnr2[e];
                         zk[jj] = fz;
                     }
                     o_r[k] = pack_bf16x2(dr2[0], dr2[1]); o_z[k] = pack_bf16x2(dz2[0], dz2[1]);
@@ -741,11 +762,48 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
             dq = dq_n; act = act_n; xm = xm_n;
         }
     }
+    // ---- end of the tile: every role is done (all MMAs complete, the IO thread has drained its bulk stores) ----
     tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    float* part = P.whh_partial + (int64_t)tile * (192 * 64 + 64);
+    float* red = reinterpret_cast<float*>(smem + BUF);        // [128 rows][64] fp32: the stage buffers are free now
+    if (warp < N_EPI_WARPS) {
+        // weight_hh partial out of TMEM: accumulator row = gate column, accumulator column = h_{t-1} column
+#pragma unroll
+        for (int sc = 0; sc < 2; ++sc) {
+            uint32_t a1[16], a2[16];
+            ld_tmem_16(tlane + 128 + 16 * sc, a1);
+            ld_tmem_16(tlane + 192 + 16 * sc, a2);
+            tmem_wait_ld();
+            float* o1 = part + (int64_t)r * 64 + 32 * ch + 16 * sc;                    // rows r (0..63), z (64..127)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4*>(o1 + 4 * j4) =
+                    make_float4(__uint_as_float(a1[4 * j4]), __uint_as_float(a1[4 * j4 + 1]), __uint_as_float(a1[4 * j4 + 2]),
+                                __uint_as_float(a1[4 * j4 + 3]));
+            if (r >= 64) {                                                              // rows n: the da_n*r half
+                float* o2 = part + (int64_t)(128 + r - 64) * 64 + 32 * ch + 16 * sc;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                    *reinterpret_cast<float4*>(o2 + 4 * j4) =
+                        make_float4(__uint_as_float(a2[4 * j4]), __uint_as_float(a2[4 * j4 + 1]),
+                                    __uint_as_float(a2[4 * j4 + 2]), __uint_as_float(a2[4 * j4 + 3]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) red[r * 64 + 32 * ch + j] = bsum[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 64) {                                    // bias_hh[n] partial: column sums in row order
+        float sacc = 0.f;
+        for (int rr = 0; rr < 128; ++rr) sacc += red[rr * 64 + threadIdx.x];
+        part[192 * 64 + threadIdx.x] = sacc;
+    }
     if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -782,10 +840,11 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
 
 int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* fc2_w, const uint8_t* h_ti,
                 uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask, const float* d_chosen, const int64_t* actions,
-                int64_t actions_sb, int64_t R, int T, int N, int A, int n_tiles, cudaStream_t s) {
+                int64_t actions_sb, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial, cudaStream_t s) {
     tc::GruBwd2Params P;
     P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.fc2_w = fc2_w; P.h_ti = h_ti; P.g_ti = g_ti; P.dpre1_ti = dpre1_ti;
     P.relu_mask = relu_mask; P.d_chosen = d_chosen; P.actions = actions; P.actions_sb = actions_sb;
+    P.whh_partial = whh_partial;
     P.R = R; P.T = T; P.N = N; P.A = A; P.n_tiles = n_tiles;
     PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::b2::SMEM_BYTES));
     tc::gru_bwd2_kernel<<<n_tiles, tc::b2::THREADS, tc::b2::SMEM_BYTES, s>>>(P);
