@@ -352,6 +352,13 @@ def main():
     e2e = None
     if not a.no_e2e:
         try:
+            # every rank pins its whole batch: refuse (instead of risking the box) when the host cannot hold it
+            import psutil
+            need = world * input_bytes
+            avail = psutil.virtual_memory().available
+            if avail < 1.25 * need:
+                raise MemoryError("host has %.0f GB available, the pinned batches of %d ranks need %.0f GB"
+                                  % (avail / 1e9, world, need / 1e9))
             host = {k: th.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in fields.items()}
             hb = _DictBatch(host, B, T)
             del fields, batch
