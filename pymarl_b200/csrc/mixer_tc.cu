@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img_kernel(MixBwdParams
 // one XOR on the packed product, group membership tests are hoisted into two per-lane bounds, and the 16 per-lane
 // d_q partials are reduced with a 4-stage reduce-scatter (15 shuffles instead of 60) that leaves one group sum per
 // lane for a single coalesced store.
-__global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img16_kernel(MixBwdParams P) {
+__global__ void __launch_bounds__(32 * MB_WARPS, 3) mix_bwd_img16_kernel(MixBwdParams P) {
     __shared__ float red[MB_WARPS][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t n_warps = (int64_t)gridDim.x * MB_WARPS;          // multiple of 8: (row & 7) is fixed per warp
