@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
             const bool valid = m < P.M;
             typename Epi::Row row;
             epi.begin(row, m, valid);
+            epi.attach(row, smem + STAGES * (A_STAGE_BYTES + W_STAGE_BYTES) + 256 + warp * (Epi::EXTRA_SMEM / N_EPI_WARPS));
             for (int p = 0; p < n_pass; ++p, ++acc_it) {
                 const int b = acc_it & 1;
                 const int ncols = pass_cols(P.Ncols, p);
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
             }
             epi.end(row, m, valid);
         }
+        epi.finish();
     }
     tc_fence_before();
     __syncthreads();
@@ -271,6 +273,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(GemmParams P, Epi e
 // epilogues
 // ------------------------------------------------------------------------------------------
 struct PlainEpi {           // C[m*ldc + n] = acc + bias[n]
+    static constexpr int EXTRA_SMEM = 0;
+    template <class R> __device__ void attach(R&, uint8_t*) const {}
+    __device__ void finish() const {}
     struct Row {};
     float* C; int64_t ldc; const float* bias; int Nreal;
     __device__ void begin(Row&, int64_t, bool) const {}
@@ -286,6 +291,9 @@ struct PlainEpi {           // C[m*ldc + n] = acc + bias[n]
 // fc1 for the online and the target net in one GEMM: columns [0, 64) online, [64, 128) target.
 //   x = relu(acc + tab_id[net][n][h] (bias folded in) + tab_act[net][a_prev][h])
 struct Fc1Epi {
+    static constexpr int EXTRA_SMEM = 0;
+    template <class R> __device__ void attach(R&, uint8_t*) const {}
+    __device__ void finish() const {}
     struct Row { int64_t out_off; int n; int a_prev; };
     const float* tab_act;       // [2][A][64]
     const float* tab_id;        // [2][N][64]   W_id[:, n] + b1 (or just b1 when obs_agent_id is off)
@@ -331,6 +339,9 @@ struct Fc1Epi {
 
 // Same, but x is written as bf16 tile images [nt][n_tiles][16 KB] (the operand format of gru_tc.cu).
 struct Fc1TiEpi {
+    static constexpr int EXTRA_SMEM = 0;
+    template <class R> __device__ void attach(R&, uint8_t*) const {}
+    __device__ void finish() const {}
     struct Row { int64_t tile_off; uint32_t r; int n; int a_prev; };
     const float* tab_act; const float* tab_id;
     const int64_t* actions; int64_t actions_sb;
@@ -392,7 +403,10 @@ struct Fc1TiEpi {
 // mq = b*(T-1) + t - t_off.  raw_img (online only): hypernet outputs as bf16 tile images
 // [row tile][(N+3)/2 column blocks of 64][16 KB], packed column order, kept for the backward.
 struct MixImgEpi {
-    struct Row { float hidden[32]; float y; int64_t mq; uint8_t* img; uint32_t r; };
+    // raw images leave through shared memory: every epilogue warp stages its 32 rows of a 64-column block (4 KB, image
+    // layout) in its own double buffer and lane 0 bulk-stores it - no per-thread row-strided global stores
+    static constexpr int EXTRA_SMEM = N_EPI_WARPS * 2 * 4096;
+    struct Row { float hidden[32]; float y; int64_t mq; uint8_t* img; uint32_t r; uint8_t* stg; uint32_t nblk; };
     const float* bias; const float* agent_qs; const float* v2_w; const float* v2_b;
     float* q_tot; uint8_t* raw_img;
     int N, T, t_off, n_cblk;
@@ -401,13 +415,27 @@ struct MixImgEpi {
 #pragma unroll
         for (int e = 0; e < 32; ++e) r.hidden[e] = 0.f;
         r.y = 0.f; r.mq = -1;
-        r.img = raw_img ? raw_img + (m >> 7) * (int64_t)n_cblk * 16384 : nullptr;
+        // this warp's 32 rows of the tile: 4 KB inside every 16 KB block
+        r.img = raw_img ? raw_img + (m >> 7) * (int64_t)n_cblk * 16384 + ((m & 127) & ~31) * 128 : nullptr;
         r.r = (uint32_t)(m & 127);
+        r.nblk = 0;
         if (m < BT) {
             const int64_t b = m / T;
             const int t = (int)(m - b * T);
             if (t_off == 0 ? (t < T - 1) : (t >= 1)) r.mq = b * (T - 1) + t - t_off;
         }
+    }
+    __device__ void attach(Row& r, uint8_t* stg) const { r.stg = stg; }
+    __device__ void flush(Row& r, int blk) const {              // whole warp
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            bulk_copy_s2g(r.img + (int64_t)blk * 16384, r.stg + (r.nblk & 1) * 4096, 4096);
+            bulk_commit_group();
+            bulk_wait_group_read<1>();                          // the other buffer (previous block) has been read
+        }
+        __syncwarp();
+        ++r.nblk;
     }
     __device__ void cols(Row& r, int64_t, bool, int col0, const uint32_t (&v)[32]) const {
         const int grp = col0 >> 5;
@@ -415,13 +443,14 @@ struct MixImgEpi {
 #pragma unroll
         for (int e = 0; e < 32; ++e) raw[e] = __uint_as_float(v[e]) + __ldg(bias + col0 + e);
         if (r.img) {                                   // every row is written (finite values; the backward zeroes unused rows)
-            uint8_t* blk = r.img + (int64_t)(col0 >> 6) * 16384;
+            uint8_t* blk = r.stg + (r.nblk & 1) * 4096;
             const uint32_t ch0 = (uint32_t)((col0 & 63) >> 3);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(blk + sw128_offset(r.r, ch0 + q)) =
+                *reinterpret_cast<uint4*>(blk + sw128_offset(r.r & 31u, ch0 + q)) =
                     make_uint4(pack_bf16x2(raw[8 * q], raw[8 * q + 1]), pack_bf16x2(raw[8 * q + 2], raw[8 * q + 3]),
                                pack_bf16x2(raw[8 * q + 4], raw[8 * q + 5]), pack_bf16x2(raw[8 * q + 6], raw[8 * q + 7]));
+            if (col0 & 32) flush(r, col0 >> 6);        // second half of a 64-column block
         }
         if (grp < N) {
             const float qn = r.mq >= 0 ? __ldg(agent_qs + r.mq * N + grp) : 0.f;
@@ -443,6 +472,16 @@ struct MixImgEpi {
     }
     __device__ void end(Row& r, int64_t, bool) const {
         if (r.mq >= 0) q_tot[r.mq] = r.y + __ldg(v2_b);
+        // (N + 3) odd: the last 64-column block was only half produced (its other half is padding the backward ignores)
+        if (r.img) {
+            if ((N + 3) & 1) flush(r, (N + 3) >> 1);
+            // the next tile starts again with buffer 0: both buffers must have been read
+            if ((threadIdx.x & 31) == 0) bulk_wait_group_read<0>();
+            __syncwarp();
+        }
+    }
+    __device__ void finish() const {
+        if ((threadIdx.x & 31) == 0) bulk_wait_group<0>();
     }
 };
 
@@ -450,10 +489,10 @@ template <class Epi>
 int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
     if (P.M <= 0) return PMB_OK;
     auto kern = tc_gemm_kernel<Epi>;
-    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + Epi::EXTRA_SMEM));
     int64_t n_tiles = (P.M + BM - 1) / BM;
     int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    kern<<<grid, THREADS, SMEM_BYTES, s>>>(P, epi);
+    kern<<<grid, THREADS, SMEM_BYTES + Epi::EXTRA_SMEM, s>>>(P, epi);
     PMB_LAUNCH_CHECK("tc_gemm_kernel");
     return PMB_OK;
 }
