@@ -73,6 +73,11 @@ typedef struct pmb_batch {
     const float*   reward;     int64_t reward_sb;       /* [B,T,1]   f32 */
     const uint8_t* terminated; int64_t terminated_sb;   /* [B,T,1]   u8  */
     const int64_t* filled;     int64_t filled_sb;       /* [B,T,1]   i64 */
+    /* Optional (may be NULL): zero-copy replay sampling.  Batch row b is episode ep_index[b] of the fields above
+     * (which then are the WHOLE replay buffer): ReplayBuffer.sample / EpisodeBatch.__getitem__(ids)
+     * (components/episode_buffer.py:205-217,291-298) without the gather copy.  Device array of B ids.  Supported by
+     * the tensor-core tier of pmb_qlearner_train_step only. */
+    const int64_t* ep_index;
 } pmb_batch;
 
 /* Flat parameter layout.  Agent tensors keep the reference order (modules/agents/rnn_agent.py:19-21);

@@ -12,7 +12,7 @@ from .learners import REGISTRY as le_REGISTRY
 from .controllers import REGISTRY as mac_REGISTRY
 from .modules.agents import REGISTRY as agent_REGISTRY
 from .components.action_selectors import REGISTRY as action_REGISTRY
-from .components.episode_buffer import EpisodeBatch, ReplayBuffer
+from .components.episode_buffer import EpisodeBatch, ReplayBuffer, IndexedEpisodeBatch
 from .modules.mixers.qmix import QMixer
 from .modules.mixers.vdn import VDNMixer
 

@@ -38,7 +38,8 @@ class Batch(C.Structure):
                 ("avail", C.c_void_p), ("avail_sb", C.c_int64),
                 ("reward", C.c_void_p), ("reward_sb", C.c_int64),
                 ("terminated", C.c_void_p), ("terminated_sb", C.c_int64),
-                ("filled", C.c_void_p), ("filled_sb", C.c_int64)]
+                ("filled", C.c_void_p), ("filled_sb", C.c_int64),
+                ("ep_index", C.c_void_p)]
 
 
 class Layout(C.Structure):
@@ -230,7 +231,7 @@ def gather_episodes(src_tensors, ep_ids, n_src):
     return out
 
 
-def make_batch(fields, need_state=True, keep=None):
+def make_batch(fields, need_state=True, keep=None, ep_index=None):
     """Build the pmb_batch view of an EpisodeBatch-like mapping (``fields[k]`` -> tensor).
     Tensors that are not on CUDA, have the wrong dtype or non-contiguous inner dims are
     converted (the converted tensors are appended to ``keep`` so they outlive the call)."""
@@ -257,4 +258,12 @@ def make_batch(fields, need_state=True, keep=None):
             keep.append(t)
         setattr(b, cname, t.data_ptr())
         setattr(b, cname + "_sb", sb)
+    b.ep_index = None
+    if ep_index is not None:
+        require_cuda(ep_index, "ep_index")
+        if ep_index.dtype != th.int64 or not ep_index.is_contiguous():
+            raise PmbError("ep_index must be a contiguous int64 tensor")
+        if keep is not None:
+            keep.append(ep_index)
+        b.ep_index = ep_index.data_ptr()
     return b

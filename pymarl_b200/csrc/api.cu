@@ -376,6 +376,7 @@ int pmb_agent_fc1_fwd(const pmb_dims* d, const pmb_batch* b, int32_t t0, int32_t
     int rc = validate_dims(d);
     if (rc) return rc;
     PMB_REQUIRE(b && b->obs && flat_agent && x_out, "fc1_fwd: NULL pointer");
+    PMB_REQUIRE(b == nullptr || b->ep_index == nullptr, "pmb_agent_fc1_fwd: batch.ep_index is only supported by pmb_qlearner_train_step");
     PMB_REQUIRE(t0 >= 0 && nt > 0 && t0 + nt <= d->T, "fc1_fwd: bad time range [%d, %d) for T = %d", t0, t0 + nt, d->T);
     PMB_REQUIRE(!d->obs_last_action || (b->actions && b->filled), "fc1_fwd: obs_last_action needs actions and filled");
     return fc1_fwd(d, b, t0, nt, agent_params(d, flat_agent), x_out, (cudaStream_t)stream);
@@ -409,6 +410,7 @@ int pmb_target_select(const pmb_dims* d, const pmb_batch* b, const float* q_on, 
     if (rc) return rc;
     PMB_REQUIRE(d->T >= 2, "target_select: T must be >= 2");
     PMB_REQUIRE(b && b->avail && b->actions && q_on && q_tg && chosen && tmax, "target_select: NULL pointer");
+    PMB_REQUIRE(b == nullptr || b->ep_index == nullptr, "pmb_target_select: batch.ep_index is only supported by pmb_qlearner_train_step");
     return launch_target_select(d, b, q_on, q_tg, chosen, tmax, cur_max, (cudaStream_t)stream);
 }
 
@@ -418,6 +420,7 @@ int pmb_mixer_fwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer
     if (rc) return rc;
     PMB_REQUIRE(d->T >= 2 && (t_off == 0 || t_off == 1), "mixer_fwd: bad T / t_off");
     PMB_REQUIRE(agent_qs && q_tot, "mixer_fwd: NULL pointer");
+    PMB_REQUIRE(b == nullptr || b->ep_index == nullptr, "mixer_fwd: batch.ep_index is only supported by pmb_qlearner_train_step");
     return launch_mixer_fwd(d, b, flat_mixer, agent_qs, t_off, raw, q_tot, (cudaStream_t)stream);
 }
 
@@ -446,6 +449,7 @@ int pmb_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mixer
     int rc = validate_dims(d);
     if (rc) return rc;
     PMB_REQUIRE(d->T >= 2 && g && d_agent_qs, "mixer_bwd: bad arguments");
+    PMB_REQUIRE(b == nullptr || b->ep_index == nullptr, "mixer_bwd: batch.ep_index is only supported by pmb_qlearner_train_step");
     return launch_mixer_bwd(d, b, flat_mixer, agent_qs, raw, g, d_agent_qs, flat_grad_mixer, scratch, scratch_bytes,
                             (cudaStream_t)stream);
 }
@@ -461,6 +465,7 @@ int pmb_agent_unroll_bwd(const pmb_dims* d, const pmb_batch* b, const float* fla
     int rc = validate_dims(d);
     if (rc) return rc;
     PMB_REQUIRE(d->T >= 2, "agent_unroll_bwd: T must be >= 2");
+    PMB_REQUIRE(b == nullptr || b->ep_index == nullptr, "pmb_agent_unroll_bwd: batch.ep_index is only supported by pmb_qlearner_train_step");
     PMB_REQUIRE(b && b->obs && b->actions && b->filled && flat_agent && x_on && h_stash && gates && d_chosen && dpre1 &&
                     flat_grad_agent && scratch, "agent_unroll_bwd: NULL pointer");
     return agent_bwd(d, b, flat_agent, x_on, h_stash, gates, d_chosen, dpre1, flat_grad_agent, scratch, scratch_bytes,
@@ -499,6 +504,7 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
     int rc = validate_dims(d);
     if (rc) return rc;
     PMB_REQUIRE(b && b->obs && b->avail && flat_agent && hidden && scratch, "select_actions_step: NULL pointer");
+    PMB_REQUIRE(b == nullptr || b->ep_index == nullptr, "pmb_select_actions_step: batch.ep_index is only supported by pmb_qlearner_train_step");
     PMB_REQUIRE(t >= 0 && t < d->T, "select_actions_step: t = %d outside [0, %d)", t, d->T);
     PMB_REQUIRE((u == nullptr) == (expo == nullptr), "select_actions_step: inject both u and expo or neither");
     if (scratch_bytes < pmb_select_actions_workspace_bytes(d)) { set_error("select_actions_step: scratch too small"); return PMB_ERR_WORKSPACE; }
@@ -586,6 +592,9 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     // q_learner.py:47-52 / 58-62: both nets over all T steps
     const bool tc_agent = d->precision == PMB_PREC_BF16 && d->H == 64 && d->A <= 64;
     const bool tc_mixer = d->precision == PMB_PREC_BF16 && d->mixer == PMB_MIXER_QMIX && d->E == 32;
+    PMB_REQUIRE(b->ep_index == nullptr || (tc_agent && (d->mixer != PMB_MIXER_QMIX || tc_mixer) && d->O <= 320 &&
+                                           ((d->O + 63) / 64) * 64 - d->O >= d->N + 1),
+                "train_step: batch.ep_index (zero-copy replay sampling) needs the tensor-core tier with the fused kernels");
     const int n_tiles = (int)ceil_div(R, 128);
     uint8_t *x_on_ti = reinterpret_cast<uint8_t*>(v.x_on), *x_tg_ti = reinterpret_cast<uint8_t*>(v.x_tg);
     uint8_t *h_ti = reinterpret_cast<uint8_t*>(v.h_stash), *g_ti = reinterpret_cast<uint8_t*>(v.gates);
@@ -672,8 +681,8 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         float* whh_part = reinterpret_cast<float*>(sc2 + tc_gru_dw_scratch_bytes());
         if ((rc = tc_gru_bwd2(reinterpret_cast<const __nv_bfloat16*>(gru_img),
                               reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576), on.fc2_w, h_ti, g_ti, x_tg_ti,
-                              reinterpret_cast<const uint32_t*>(v.relu_mask), v.d_chosen, b->actions, b->actions_sb, R,
-                              d->T, d->N, d->A, n_tiles, whh_part, s))) return rc;
+                              reinterpret_cast<const uint32_t*>(v.relu_mask), v.d_chosen, b->actions, b->actions_sb, b->ep_index,
+                              R, d->T, d->N, d->A, n_tiles, whh_part, s))) return rc;
         PHASE(s, "dW_rnn_tc");
         if ((rc = tc_gru_whh_reduce(whh_part, n_tiles, gr.w_hh, gr.b_hh, s))) return rc;
         if ((rc = tc_gru_dw(g_ti, x_on_ti, d->T, n_tiles, gr.w_ih, gr.b_ih, gr.b_hh, sc2, tc_gru_dw_scratch_bytes(), s))) return rc;

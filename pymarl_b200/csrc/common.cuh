@@ -36,6 +36,9 @@ inline __host__ __device__ int64_t align_up(int64_t a, int64_t b) { return ceil_
 
 constexpr float kMaskValue = -9999999.0f;       // learners/q_learner.py:68,74
 
+// batch row -> episode of the underlying buffer (pmb_batch.ep_index; NULL = identity)
+__device__ __forceinline__ int64_t ep_row(const int64_t* ep_index, int64_t b) { return ep_index ? __ldg(ep_index + b) : b; }
+
 // ---- row maps ---------------------------------------------------------------------------
 // A logical row index m = (b*T + t)*N + n is mapped to  base + b*sb + t*st + n*sn  (element
 // offsets).  Dense [M, ld] matrices use T = N = 1, sb = ld.

@@ -474,6 +474,7 @@ constexpr int PARTIAL_FLOATS = 64 * OBS_LD + 64 * 64 + 128 + 128 * 64;   // dW1o
 struct AgentDwParams {
     const uint8_t* dpre1_ti; const uint8_t* h_ti; const uint8_t* obs_ti;
     const float* d_chosen; const int64_t* actions; int64_t actions_sb; const int64_t* filled; int64_t filled_sb;
+    const int64_t* ep_index;
     float* partial;
     int64_t R, n_items, items_per_cta;
     int T, N, A, n_tiles, n_chunks, use_act, use_id;
@@ -571,13 +572,14 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
                 if (p < P.R) {
                     const int64_t b = (int64_t)((uint32_t)p / (uint32_t)P.N);
                     const int n = (int)(p - b * P.N);
+                    const int64_t be = ep_row(P.ep_index, b);
                     if (t < P.T - 1) {
                         x.dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
-                        x.a = (int)__ldg(P.actions + b * P.actions_sb + t * P.N + n);
+                        x.a = (int)__ldg(P.actions + be * P.actions_sb + t * P.N + n);
                     }
                     if (P.use_act && t > 0) {                  // both loads issued unconditionally, then selected
-                        const int64_t f = __ldg(P.filled + b * P.filled_sb + (t - 1));
-                        const int apv = (int)__ldg(P.actions + b * P.actions_sb + (t - 1) * P.N + n);
+                        const int64_t f = __ldg(P.filled + be * P.filled_sb + (t - 1));
+                        const int apv = (int)__ldg(P.actions + be * P.actions_sb + (t - 1) * P.N + n);
                         x.ap = f != 0 ? apv : -1;
                     }
                 }
@@ -734,6 +736,7 @@ int tc_agent_dw(const pmb_dims* d, const pmb_batch* b, const uint8_t* dpre1_ti, 
     tc::AgentDwParams P;
     P.dpre1_ti = dpre1_ti; P.h_ti = h_ti; P.obs_ti = obs_ti; P.d_chosen = d_chosen;
     P.actions = b->actions; P.actions_sb = b->actions_sb; P.filled = b->filled; P.filled_sb = b->filled_sb;
+    P.ep_index = b->ep_index;
     P.R = (int64_t)d->B * d->N; P.T = d->T; P.N = d->N; P.A = d->A; P.n_tiles = n_tiles;
     P.n_chunks = (d->O + 63) / 64; P.use_act = d->obs_last_action; P.use_id = d->obs_agent_id;
     P.n_items = (int64_t)d->T * n_tiles * 2;

@@ -43,7 +43,8 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
                 float* chosen, float* tmax, float* q_on_out, float* q_tg_out, cudaStream_t s);
 int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* fc2_w, const uint8_t* h_ti,
                 uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask, const float* d_chosen, const int64_t* actions,
-                int64_t actions_sb, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial, cudaStream_t s);
+                int64_t actions_sb, const int64_t* ep_index, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial,
+                cudaStream_t s);
 int tc_ti_zero_pad(uint8_t* buf, int n_t, int n_tiles, int64_t R, cudaStream_t s);
 
 }  // namespace pmb

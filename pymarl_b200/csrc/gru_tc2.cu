@@ -332,6 +332,7 @@ struct QSelectParams {
     const uint8_t* h_tg_ti;
     const int32_t* avail; int64_t avail_sb;
     const int64_t* actions; int64_t actions_sb;
+    const int64_t* ep_index;         // optional batch row -> buffer episode
     float* chosen;                   // [B][T-1][N]
     float* tmax;                     // [B][T-1][N]
     float* q_on_out;                 // optional fp32 [T][R][A] (tests / diagnostics)
@@ -431,8 +432,9 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
             const int n = valid ? (int)(p - b * P.N) : 0;
             // issue the index / avail loads before waiting for the accumulator
             int a_taken = -1;
-            if (valid && t < P.T - 1) a_taken = (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n);
-            const int32_t* av = P.avail + b * P.avail_sb + ((int64_t)t * P.N + n) * P.A;
+            const int64_t be = ep_row(P.ep_index, b);
+            if (valid && t < P.T - 1) a_taken = (int)__ldg(P.actions + be * P.actions_sb + (int64_t)t * P.N + n);
+            const int32_t* av = P.avail + be * P.avail_sb + ((int64_t)t * P.N + n) * P.A;
             const bool want_t = valid && t >= 1;
             // the whole avail row goes to registers (16-byte loads when the layout allows); columns >= A read as 0
             int4 avv[16];
@@ -546,6 +548,7 @@ struct GruBwd2Params {
     const uint32_t* relu_mask;       // [T][n_tiles][2][128]: bit j of word (half, row) = fc1 output column 32*half + j > 0
     const float* d_chosen;           // [B][T-1][N]
     const int64_t* actions; int64_t actions_sb;
+    const int64_t* ep_index;         // optional batch row -> buffer episode
     float* whh_partial;              // [n_tiles][192*64 + 64]: this tile's rnn.weight_hh gradient and sum of da_n*r
     int64_t R;
     int T, N, A, n_tiles;
@@ -668,7 +671,8 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
         for (int j = 0; j < 32; ++j) dh[j] = 0.f;
         // per-step scalars, fetched one step ahead
         auto fetch_dq = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n) : 0.f; };
-        auto fetch_a = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? (int)__ldg(P.actions + b * P.actions_sb + (int64_t)t * P.N + n) : 0; };
+        const int64_t be = ep_row(P.ep_index, b);
+        auto fetch_a = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? (int)__ldg(P.actions + be * P.actions_sb + (int64_t)t * P.N + n) : 0; };
         auto fetch_m = [&](int t) { return t >= 0 ? __ldg(P.relu_mask + (((int64_t)t * P.n_tiles + tile) * 2 + ch) * 128 + r) : 0u; };
         float dq = fetch_dq(P.T - 1);
         int act = fetch_a(P.T - 1);
@@ -827,6 +831,7 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
     P.w2_on_img = w2_on_img; P.w2_tg_img = w2_tg_img; P.b2_on = b2_on; P.b2_tg = b2_tg;
     P.h_on_ti = h_on_ti; P.h_tg_ti = h_tg_ti;
     P.avail = b->avail; P.avail_sb = b->avail_sb; P.actions = b->actions; P.actions_sb = b->actions_sb;
+    P.ep_index = b->ep_index;
     P.chosen = chosen; P.tmax = tmax; P.q_on_out = q_on_out; P.q_tg_out = q_tg_out;
     P.R = (int64_t)d->B * d->N; P.T = d->T; P.N = d->N; P.A = d->A; P.n_tiles = n_tiles; P.double_q = d->double_q;
     const int64_t n_items = (int64_t)d->T * n_tiles;
@@ -840,11 +845,12 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
 
 int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* fc2_w, const uint8_t* h_ti,
                 uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask, const float* d_chosen, const int64_t* actions,
-                int64_t actions_sb, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial, cudaStream_t s) {
+                int64_t actions_sb, const int64_t* ep_index, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial,
+                cudaStream_t s) {
     tc::GruBwd2Params P;
     P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.fc2_w = fc2_w; P.h_ti = h_ti; P.g_ti = g_ti; P.dpre1_ti = dpre1_ti;
     P.relu_mask = relu_mask; P.d_chosen = d_chosen; P.actions = actions; P.actions_sb = actions_sb;
-    P.whh_partial = whh_partial;
+    P.whh_partial = whh_partial; P.ep_index = ep_index;
     P.R = R; P.T = T; P.N = N; P.A = A; P.n_tiles = n_tiles;
     PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::b2::SMEM_BYTES));
     tc::gru_bwd2_kernel<<<n_tiles, tc::b2::THREADS, tc::b2::SMEM_BYTES, s>>>(P);

@@ -26,8 +26,8 @@ __device__ __forceinline__ void block_sum5(double (&v)[5], double (*sh)[5]) {
 __global__ void __launch_bounds__(256)
 td_loss_kernel(int B, int T, int W, float gamma, const float* __restrict__ q_tot, const float* __restrict__ t_tot,
                const float* __restrict__ reward, int64_t reward_sb, const uint8_t* __restrict__ terminated,
-               int64_t term_sb, const int64_t* __restrict__ filled, int64_t filled_sb, float* __restrict__ g_out,
-               double* __restrict__ stats) {
+               int64_t term_sb, const int64_t* __restrict__ filled, int64_t filled_sb,
+               const int64_t* __restrict__ ep_index, float* __restrict__ g_out, double* __restrict__ stats) {
     __shared__ double sh[8][5];
     const int64_t total = (int64_t)B * (T - 1) * W;
     double acc[5] = {0, 0, 0, 0, 0};
@@ -35,10 +35,11 @@ td_loss_kernel(int B, int T, int W, float gamma, const float* __restrict__ q_tot
         int64_t m = i / W;
         int64_t b = m / (T - 1);
         int t = (int)(m - b * (T - 1));
-        float term = (float)__ldg(terminated + b * term_sb + t);
-        float mask = (float)__ldg(filled + b * filled_sb + t);
-        if (t > 0) mask = mask * (1.f - (float)__ldg(terminated + b * term_sb + (t - 1)));
-        float r = __ldg(reward + b * reward_sb + t);
+        const int64_t be = ep_row(ep_index, b);
+        float term = (float)__ldg(terminated + be * term_sb + t);
+        float mask = (float)__ldg(filled + be * filled_sb + t);
+        if (t > 0) mask = mask * (1.f - (float)__ldg(terminated + be * term_sb + (t - 1)));
+        float r = __ldg(reward + be * reward_sb + t);
         float q = __ldg(q_tot + i);
         float y = r + (gamma * (1.f - term)) * __ldg(t_tot + i);
         float td = q - y;
@@ -128,7 +129,7 @@ int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, co
     int64_t cap = 8 * (int64_t)sm_count();
     if (grid > cap) grid = cap;
     td_loss_kernel<<<(unsigned)grid, 256, 0, s>>>(d->B, d->T, W, gamma, q_tot, t_tot, b->reward, b->reward_sb,
-                                                  b->terminated, b->terminated_sb, b->filled, b->filled_sb, g_out,
+                                                  b->terminated, b->terminated_sb, b->filled, b->filled_sb, b->ep_index, g_out,
                                                   stats);
     PMB_LAUNCH_CHECK("td_loss_kernel");
     return PMB_OK;

@@ -523,6 +523,7 @@ constexpr int N_FIX_LANES = 6;                              // lanes 1-3 head fl
 }  // namespace fs
 
 struct Fc1StreamParams {
+    const int64_t* ep_index;       // optional batch row -> buffer episode
     const float* obs; int64_t obs_sb;
     const __nv_bfloat16* Wp;       // packed [chunk][128 x 128 B]
     uint8_t* obs_img;              // optional [T*n_tiles][n_chunks][16 KB]
@@ -617,7 +618,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     int cnt = P.N - n0;
                     if (cnt > GROUP_ROWS - lr) cnt = GROUP_ROWS - lr;
                     if ((int64_t)cnt > P.R - p) cnt = (int)(P.R - p);
-                    const char* ga = reinterpret_cast<const char*>(P.obs + b * P.obs_sb + ((t + P.t0) * P.N + n0) * (int64_t)P.O);
+                    const char* ga = reinterpret_cast<const char*>(P.obs + ep_row(P.ep_index, b) * P.obs_sb +
+                                                                   ((t + P.t0) * P.N + n0) * (int64_t)P.O);
                     const uint32_t bytes = (uint32_t)cnt * P.O * 4u;
                     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
                     cur = ((cur + 15u) & ~15u) + phase;
@@ -776,8 +778,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             n_out = (int)(p - b * P.N);
             const int64_t tb = t + P.t0;                       // timestep in the batch
             if (!P.use_act || tb == 0) return -1;
-            const int64_t f = __ldg(P.filled + b * P.filled_sb + (tb - 1));
-            const int a = (int)__ldg(P.actions + b * P.actions_sb + (tb - 1) * P.N + n_out);
+            const int64_t be = ep_row(P.ep_index, b);
+            const int64_t f = __ldg(P.filled + be * P.filled_sb + (tb - 1));
+            const int a = (int)__ldg(P.actions + be * P.actions_sb + (tb - 1) * P.N + n_out);
             return f != 0 ? a : -1;
         };
         int n_cur, n_nxt;
@@ -994,7 +997,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
                 n_chunks, wp, tab_act16);
             PMB_LAUNCH_CHECK("fc1_stream_pack_kernel");
             tc::Fc1StreamParams Q;
-            Q.obs = b->obs; Q.obs_sb = b->obs_sb; Q.Wp = wp; Q.obs_img = obs_img_out; Q.R = R;
+            Q.ep_index = b->ep_index; Q.obs = b->obs; Q.obs_sb = b->obs_sb; Q.Wp = wp; Q.obs_img = obs_img_out; Q.R = R;
             Q.T = nt; Q.N = d->N; Q.O = d->O; Q.n_tiles = n_tiles; Q.n_chunks = n_chunks; Q.slot_bytes = slot_bytes;
             Q.fold_id = fold_id; Q.tab_act16 = reinterpret_cast<const uint4*>(tab_act16); Q.tab_id = tab_id;
             Q.actions = b->actions; Q.actions_sb = b->actions_sb; Q.filled = b->filled; Q.filled_sb = b->filled_sb;
@@ -1008,8 +1011,10 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             PMB_LAUNCH_CHECK("fc1_stream_kernel");
             return PMB_OK;
         }
+        if (b->ep_index) { set_error("tc_fc1: ep_index needs the streaming kernel (obs dim <= 320)"); return PMB_ERR_INVALID; }
         return tc::launch_tc_gemm(P, epi, s);
     }
+    if (b->ep_index) { set_error("tc_fc1: ep_index is not supported without tile images"); return PMB_ERR_INVALID; }
     tc::Fc1Epi epi{tab_act, tab_id, b->actions, b->actions_sb, b->filled, b->filled_sb, x_on, x_tg,
                    t0, nt, d->N, d->A, d->obs_last_action, (int64_t)d->B * d->N};
     return tc::launch_tc_gemm(P, epi, s);
@@ -1039,8 +1044,8 @@ int64_t tc_mixer_scratch_bytes(const pmb_dims* d) {
 // Column S of every real row holds 1.0 (the bias-gradient column of the hypernet weight-gradient GEMM; the packed
 // forward weights are zero there), everything else beyond S and all padding rows are zero.
 __global__ void __launch_bounds__(256)
-state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, int64_t BT, int T, int S, int n_chunks,
-                       uint8_t* __restrict__ img) {
+state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, const int64_t* __restrict__ ep_index, int64_t BT,
+                       int T, int S, int n_chunks, uint8_t* __restrict__ img) {
     // one thread per 16-byte chunk
     const int64_t total = ((BT + 127) / 128) * 128 * (int64_t)n_chunks * 8;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1056,7 +1061,7 @@ state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, int64_
     if (m < BT) {
         const int64_t b = m / T;
         const int t = (int)(m - b * T);
-        const float* src = state + b * state_sb + (int64_t)t * S + c * 64 + j * 8;
+        const float* src = state + ep_row(ep_index, b) * state_sb + (int64_t)t * S + c * 64 + j * 8;
         const int nv = S - (c * 64 + j * 8);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -1073,7 +1078,8 @@ int tc_state_to_images(const pmb_dims* d, const pmb_batch* b, uint8_t* img, cuda
     const int64_t BT = (int64_t)d->B * d->T;
     const int n_chunks = tc_state_chunks(d);
     const int64_t total = ((BT + 127) / 128) * 128 * (int64_t)n_chunks * 8;
-    state_to_images_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(b->state, b->state_sb, BT, d->T, d->S, n_chunks, img);
+    state_to_images_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(b->state, b->state_sb, b->ep_index, BT, d->T, d->S, n_chunks,
+                                                                                  img);
     PMB_LAUNCH_CHECK("state_to_images_kernel");
     return PMB_OK;
 }

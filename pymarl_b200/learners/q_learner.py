@@ -175,14 +175,23 @@ class QLearner:
         names = ["obs", "actions", "avail_actions", "reward", "terminated", "filled"]
         if a.mixer == "qmix":
             names.append("state")
-        for k in names:
-            t = batch[k]
-            fields[k] = t if t.is_cuda else t.to(dev, non_blocking=True)       # host batch: H2D here (run.py:214)
+        ep_index = None
+        if hasattr(batch, "ep_ids") and hasattr(batch, "buffer"):
+            # zero-copy replay sample (IndexedEpisodeBatch): the kernels read the buffer's episodes in place
+            ep_index = batch.ep_ids
+            for k in names:
+                fields[k] = batch.buffer.data.transition_data[k]
+        else:
+            for k in names:
+                t = batch[k]
+                fields[k] = t if t.is_cuda else t.to(dev, non_blocking=True)   # host batch: H2D here (run.py:214)
         obs = fields["obs"]
         B, T, N, O = obs.shape
+        if ep_index is not None:
+            B, T = batch.batch_size, batch.max_seq_length
         S = fields["state"].shape[-1] if "state" in fields else 1
         dims = self._layout_dims(B=B, T=T, O=O, S=S)
-        pb = _lib.make_batch(fields, need_state=(a.mixer == "qmix"), keep=keep)
+        pb = _lib.make_batch(fields, need_state=(a.mixer == "qmix"), keep=keep, ep_index=ep_index)
         need = self._ensure_workspace(dims, dev)
 
         do_sync = (episode_num - self.last_target_update_episode) / a.target_update_interval >= 1.0

@@ -521,3 +521,50 @@ def test_replay_sample_on_device_is_bit_exact():
     np.testing.assert_array_equal(bufs["cpu"][ids]["avail_actions"].numpy(), bufs["cuda"][ids]["avail_actions"].cpu().numpy())
     with pytest.raises(IndexError):
         bufs["cuda"][np.array([0, 32])]
+
+
+@pytest.mark.parametrize("mixer", ["qmix", "vdn"])
+def test_zero_copy_replay_sample_trains_identically(mixer):
+    """ReplayBuffer(zero_copy=True).sample returns episode ids + the buffer (IndexedEpisodeBatch); QLearner.train passes
+    the ids to the kernels (pmb_batch.ep_index) which read the buffer in place.  Same ids -> bit-identical step as
+    training on the gathered copy, including the [:, :max_t_filled] truncation of the reference's loop (run.py:207-215)."""
+    from cuda_utils import build_learner
+    from pymarl_b200 import ReplayBuffer, IndexedEpisodeBatch
+    from pymarl_b200.components.transforms import OneHot
+    from pymarl_b200.synthetic import make_scheme
+    shape = SMAC_SHAPES["2s3z"]
+    T = 24
+    scheme, groups = make_scheme(shape)
+    preprocess = {"actions": ("actions_onehot", [OneHot(out_dim=shape.n_actions)])}
+    fields = numpy_episode_fields(shape, 40, T, seed=6, ragged=True)
+    buf = ReplayBuffer(scheme, groups, 48, T, preprocess=preprocess, device="cuda")
+    for k, v in fields.items():
+        buf.data.transition_data[k][:40] = th.from_numpy(np.ascontiguousarray(v)).cuda()
+    buf.buffer_index, buf.episodes_in_buffer = 40, 40
+    args = default_args(shape, mixer=mixer, learner_log_interval=0, precision="bf16")
+    olr = _oracle_learner(shape, copy.copy(args), seed=3)
+    results = []
+    for zero_copy in (False, True):
+        learner, _ = build_learner(shape, copy.copy(args), olr.agent, olr.target_agent, olr.mixer_p, olr.target_mixer_p)
+        buf.zero_copy = zero_copy
+        np.random.seed(77)
+        batch = buf.sample(16)
+        assert isinstance(batch, IndexedEpisodeBatch) == zero_copy
+        max_t = int(batch.max_t_filled())
+        batch = batch[:, :max_t]
+        batch.to("cuda")                                # in place, like the reference's loop (run.py:214-215)
+        assert batch.max_seq_length == max_t and batch.batch_size == 16
+        learner.train(batch, 0, 0)
+        results.append((learner.stats(), learner._flat["p"].clone(), max_t))
+    (st_a, p_a, t_a), (st_b, p_b, t_b) = results
+    assert t_a == t_b
+    assert st_a == st_b
+    assert th.equal(p_a, p_b)
+    # a field asked of the indexed batch is the gathered field
+    buf.zero_copy = False
+    np.random.seed(77)
+    ref = buf.sample(16)
+    buf.zero_copy = True
+    np.random.seed(77)
+    idx = buf.sample(16)
+    assert th.equal(idx["obs"], ref["obs"])
