@@ -360,11 +360,25 @@ def test_tc_gemm_atb_matches_bf16_reference(m, c, k, ldd, lda):
     assert rel_err(bias.cpu().numpy(), dr.sum(0)) < 3e-5
 
 
+# shapes outside the SMAC table that take the less common kernel paths of the tensor-core tier:
+#   many_agents: N = 31 -> 17 raw-image column blocks (generic mixer-backward kernel), one-hot agent columns fold into
+#                the K padding of a 2-chunk obs image
+#   no_fold:     64 * ceil(O / 64) - O < N + 1 -> agent-id table in the fc1 epilogue, un-fused fc1/fc2 weight gradients
+EXTRA_SHAPES = {"many_agents": SmacShape("many_agents", 31, 70, 90, 12, 21),
+                "no_fold": SmacShape("no_fold", 10, 120, 64, 9, 21)}
+
+
+def _shape(name):
+    return SMAC_SHAPES[name] if name in SMAC_SHAPES else EXTRA_SHAPES[name]
+
+
 @pytest.mark.parametrize("shape_name,B,T,mixer", [("3m", 32, 60, "qmix"), ("2s3z", 40, 30, "qmix"),
-                                                   ("MMM2", 16, 20, "vdn"), ("27m_vs_30m", 8, 12, "qmix")])
+                                                   ("MMM2", 16, 20, "vdn"), ("27m_vs_30m", 8, 12, "qmix"),
+                                                   ("many_agents", 9, 14, "qmix"), ("no_fold", 21, 16, "qmix"),
+                                                   ("no_fold", 21, 16, None)])
 def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
     from cuda_utils import build_learner, to_batch, state_np
-    shape = SMAC_SHAPES[shape_name]
+    shape = _shape(shape_name)
     # clip disabled so .grad holds the raw (normalised) gradient.  RMSprop state is pre-warmed to a
     # constant on both sides: from a zero state the first update is +-lr/sqrt(1-alpha) * sign(g) for
     # every element, which turns bf16-level noise on near-zero gradients into full-size sign flips
