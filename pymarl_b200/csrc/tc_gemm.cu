@@ -514,10 +514,12 @@ int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
 //   4 epilogue warps : Fc1TiEpi (one-hot gathers, bias, ReLU, bf16 x tile images of both nets, ReLU bit mask).
 namespace fs {
 constexpr int MAX_CHUNKS = 5;
-constexpr int GROUP_ROWS = 16, GROUPS = BM / GROUP_ROWS;
+constexpr int GROUP_ROWS = 16, GROUPS = BM / GROUP_ROWS;     // (8 rows x 6 slots measured no better: 8.5 vs 8.2 ms)
 constexpr int N_SLOTS = 3;
-constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_PROD = 3, STORE_W = 8, FIRST_CONV_W = 9, N_CONV = 8;
-constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);       // 544
+constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_PROD = N_SLOTS, STORE_W = PROD_W + N_PROD, FIRST_CONV_W = STORE_W + 1, N_CONV = 8;
+constexpr int RPW = GROUP_ROWS / N_CONV;                     // rows of a group per converter warp
+constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);
+static_assert(RPW >= 1 && RPW * N_CONV == GROUP_ROWS, "group rows must divide over the converter warps");
 static_assert(N_PROD == N_SLOTS, "every producer warp owns one staging slot (parity waits are only safe one phase apart)");
 constexpr int N_FIX_LANES = 6;                              // lanes 1-3 head floats, 4-6 tail floats
 }  // namespace fs
@@ -676,13 +678,17 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 const int slot = git % N_SLOTS;
                 mbar_wait(&st_full[slot], (git / N_SLOTS) & 1);
                 const uint32_t sl = smem_u32(stage + slot * P.slot_bytes) + 8u * lane;
-                const int2 off2 = *reinterpret_cast<const int2*>(rowoff + slot * GROUP_ROWS + 2 * cw);
-                const int2 nn2 = *reinterpret_cast<const int2*>(rown + slot * GROUP_ROWS + 2 * cw);
-                float v0[2][MAX_CHUNKS], v1[2][MAX_CHUNKS];
+                int offs[RPW], nns[RPW];
+#pragma unroll
+                for (int rr = 0; rr < RPW; ++rr) {
+                    offs[rr] = rowoff[slot * GROUP_ROWS + RPW * cw + rr];
+                    nns[rr] = rown[slot * GROUP_ROWS + RPW * cw + rr];
+                }
+                float v0[RPW][MAX_CHUNKS], v1[RPW][MAX_CHUNKS];
                 {
 #pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {             // all 20 loads first
-                        const int off = rr ? off2.y : off2.x;
+                    for (int rr = 0; rr < RPW; ++rr) {           // all loads first
+                        const int off = offs[rr];
                         const uint32_t src = sl + (uint32_t)(off < 0 ? 0 : off);
                         const uint32_t m0 = off < 0 ? 0u : ok0, m1 = off < 0 ? 0u : ok1;
 #pragma unroll
@@ -693,11 +699,11 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                         }
                     }
                     // pack first (consumes every loaded value), release the staging slot, then write the A tile
-                    uint32_t pk[2][MAX_CHUNKS];
+                    uint32_t pk[RPW][MAX_CHUNKS];
 #pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const int off = rr ? off2.y : off2.x;
-                        const int nn = rr ? nn2.y : nn2.x;
+                    for (int rr = 0; rr < RPW; ++rr) {
+                        const int off = offs[rr];
+                        const int nn = nns[rr];
                         // one-hot(agent) and the bias column live in the K padding of the last chunk
                         const bool fold = P.fold_id && off >= 0;
                         const bool hit0 = fold && j_pad >= 0 && (j_pad == nn || j_pad == P.N);
@@ -715,8 +721,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     // the MMAs and the image store of the previous tile are done with the A tile
                     if (g == 0) mbar_wait(a_free, (ti & 1) ^ 1);
 #pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const uint32_t rt = (uint32_t)(g * GROUP_ROWS + 2 * cw + rr);
+                    for (int rr = 0; rr < RPW; ++rr) {
+                        const uint32_t rt = (uint32_t)(g * GROUP_ROWS + RPW * cw + rr);
                         const uint32_t dst = (a_base + rt * 128u) ^ ((rt & 7u) << 4);
 #pragma unroll
                         for (int c = 0; c < MAX_CHUNKS; ++c)
@@ -1063,10 +1069,18 @@ state_to_images_kernel(const float* __restrict__ state, int64_t state_sb, const 
         const int t = (int)(m - b * T);
         const float* src = state + ep_row(ep_index, b) * state_sb + (int64_t)t * S + c * 64 + j * 8;
         const int nv = S - (c * 64 + j * 8);
+        if (nv >= 8 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {        // the common case: four 8-byte loads
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (e < nv) f[e] = __ldg(src + e);
-            else if (e == nv) f[e] = 1.0f;
+            for (int e = 0; e < 4; ++e) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(src) + e);
+                f[2 * e] = v.x; f[2 * e + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (e < nv) f[e] = __ldg(src + e);
+                else if (e == nv) f[e] = 1.0f;
+            }
         }
     }
     *reinterpret_cast<uint4*>(img + (tile * n_chunks + c) * 16384 + tc::sw128_offset((uint32_t)r, (uint32_t)j)) =
