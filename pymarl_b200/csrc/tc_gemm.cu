@@ -521,7 +521,6 @@ constexpr int RPW = GROUP_ROWS / N_CONV;                     // rows of a group 
 constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);
 static_assert(RPW >= 1 && RPW * N_CONV == GROUP_ROWS, "group rows must divide over the converter warps");
 static_assert(N_PROD == N_SLOTS, "every producer warp owns one staging slot (parity waits are only safe one phase apart)");
-constexpr int N_FIX_LANES = 6;                              // lanes 1-3 head floats, 4-6 tail floats
 }  // namespace fs
 
 struct Fc1StreamParams {
@@ -578,7 +577,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
-        for (int i = 0; i < N_SLOTS; ++i) { mbar_init(&st_full[i], 1 + N_FIX_LANES); mbar_init(&st_empty[i], N_CONV); }
+        for (int i = 0; i < N_SLOTS; ++i) { mbar_init(&st_full[i], 1 + 32); mbar_init(&st_empty[i], N_CONV); }
         mbar_init(a_full, N_CONV); mbar_init(a_free, 2);
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], N_EPI); }
         fence_barrier_init();
@@ -599,62 +598,64 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             mbar_arrive_expect_tx(w_full, (uint32_t)tile_bytes);
             bulk_copy_g2s(w_s, P.Wp, (uint32_t)tile_bytes, w_full);
         }
+        // Lane i owns the i-th contiguous run of a group (one episode each) and computes its descriptor - global
+        // address, staging offset, head / interior / tail split - in closed form, in parallel with the other lanes
+        // and BEFORE the slot is free; once it is, every lane just issues its copies.  (The first version walked the
+        // runs serially after the wait: ~1.5 us of dependent integer code per group during which the slot sat empty,
+        // which bounded the stream at three slots per (walk + load + convert).)
         uint32_t git = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int64_t t = item / P.n_tiles, tile = item - t * P.n_tiles;
             for (int g = 0; g < GROUPS; ++g, ++git) {
                 const int slot = git % N_SLOTS;
                 if (slot != pw) continue;
-                mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
                 uint8_t* sl = stage + slot * P.slot_bytes;
                 int* ro = rowoff + slot * GROUP_ROWS;
                 int* rn = rown + slot * GROUP_ROWS;
                 const int64_t p0 = tile * BM + g * GROUP_ROWS;
-                uint32_t cur = 0, tx = 0;
-                int lr = 0;
-                while (lr < GROUP_ROWS) {                    // uniform across the warp
-                    const int64_t p = p0 + lr;
-                    if (p >= P.R) break;
-                    const int64_t b = (int64_t)((uint32_t)p / (uint32_t)P.N);     // B*N < 2^31 (validated on the host)
-                    const int n0 = (int)(p - b * P.N);
-                    int cnt = P.N - n0;
-                    if (cnt > GROUP_ROWS - lr) cnt = GROUP_ROWS - lr;
-                    if ((int64_t)cnt > P.R - p) cnt = (int)(P.R - p);
-                    const char* ga = reinterpret_cast<const char*>(P.obs + ep_row(P.ep_index, b) * P.obs_sb +
-                                                                   ((t + P.t0) * P.N + n0) * (int64_t)P.O);
-                    const uint32_t bytes = (uint32_t)cnt * P.O * 4u;
+                int rows_here = P.R - p0 < GROUP_ROWS ? (int)(P.R - p0) : GROUP_ROWS;     // rows of this group below R
+                if (rows_here < 0) rows_here = 0;
+                const uint32_t b0 = (uint32_t)p0 / (uint32_t)P.N;               // B*N < 2^31 (validated on the host)
+                const int n00 = (int)((uint32_t)p0 - b0 * (uint32_t)P.N);
+                int first_cnt = P.N - n00;
+                if (first_cnt > rows_here) first_cnt = rows_here;
+                // run `lane`: rows [lr, lr + cnt) of the group, agent index n0 .. of episode b0 + lane
+                const int lr = lane == 0 ? 0 : first_cnt + (lane - 1) * P.N;
+                int cnt = lane == 0 ? first_cnt : (rows_here - lr < P.N ? rows_here - lr : P.N);
+                if (cnt < 0) cnt = 0;
+                const int n0 = lane == 0 ? n00 : 0;
+                const char* ga = nullptr;
+                uint32_t bytes = 0, cur = 0, h_end = 0, t_beg = 0;
+                if (cnt > 0) {
+                    ga = reinterpret_cast<const char*>(P.obs + ep_row(P.ep_index, (int64_t)b0 + lane) * P.obs_sb +
+                                                       ((t + P.t0) * P.N + n0) * (int64_t)P.O);
+                    bytes = (uint32_t)cnt * P.O * 4u;
                     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
-                    cur = ((cur + 15u) & ~15u) + phase;
-                    if (lane < cnt) { ro[lr + lane] = (int)(cur + (uint32_t)lane * P.O * 4u); rn[lr + lane] = n0 + lane; }
+                    // staging offset: same 16-byte phase as the source; 32 bytes of slack per run keep runs disjoint
+                    cur = (((uint32_t)lr * P.O * 4u + 15u) & ~15u) + 32u * lane + phase;
                     // [ga, ga+bytes) = head (< 16 B) | 16-byte aligned interior | tail (< 16 B)
-                    uint32_t h_end = (16u - phase) & 15u;                      // bytes before the first aligned address
+                    h_end = (16u - phase) & 15u;
                     if (h_end > bytes) h_end = bytes;
-                    uint32_t t_beg = (phase + bytes) & ~15u;                   // offset (from ga - phase) of the last aligned address
+                    t_beg = (phase + bytes) & ~15u;
                     t_beg = t_beg > phase ? t_beg - phase : 0u;
                     if (t_beg < h_end) t_beg = h_end;
-                    if (t_beg > h_end) {
-                        if (lane == 0) bulk_copy_g2s(sl + cur + h_end, ga + h_end, t_beg - h_end, &st_full[slot]);
-                        tx += t_beg - h_end;
-                    }
-                    if (lane >= 1 && lane <= 3) {
-                        const uint32_t o = (uint32_t)(lane - 1) * 4u;
-                        if (o < h_end)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
-                    } else if (lane >= 4 && lane <= 6) {
-                        const uint32_t o = t_beg + (uint32_t)(lane - 4) * 4u;
-                        if (o < bytes)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
-                    }
-                    cur += bytes;
-                    lr += cnt;
                 }
-                if (lane >= lr && lane < GROUP_ROWS) ro[lane] = -1;           // rows beyond R: zeros
+                const uint32_t tx = __reduce_add_sync(0xffffffffu, t_beg - h_end);
+                mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
+                if (cnt > 0) {
+                    for (int k = 0; k < cnt; ++k) { ro[lr + k] = (int)(cur + (uint32_t)k * P.O * 4u); rn[lr + k] = n0 + k; }
+                    if (t_beg > h_end) bulk_copy_g2s(sl + cur + h_end, ga + h_end, t_beg - h_end, &st_full[slot]);
+                    for (uint32_t o = 0; o < h_end; o += 4)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
+                    for (uint32_t o = t_beg; o < bytes; o += 4)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
+                }
+                if (lane >= rows_here && lane < GROUP_ROWS) ro[lane] = -1;       // rows beyond R: zeros
+                // arrives when all earlier cp.async of this lane have landed (does not change the expected count)
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&st_full[slot])) : "memory");
                 __syncwarp();
                 if (lane == 0) {
                     if (tx) mbar_arrive_expect_tx(&st_full[slot], tx); else mbar_arrive(&st_full[slot]);
-                } else if (lane <= N_FIX_LANES) {
-                    // arrives when all earlier cp.async of this lane have landed (does not change the expected count)
-                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&st_full[slot])) : "memory");
                 }
             }
         }
@@ -991,7 +992,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
                          reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
                          d->obs_last_action, n_tiles, R, relu_mask};
         const int n_chunks = (d->O + tc::BK - 1) / tc::BK;
-        const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 512, 128);
+        const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 32 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
         const int64_t smem_need = 1024 + 2 * (int64_t)n_chunks * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes +
                                   2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
         if (n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
