@@ -541,6 +541,7 @@ struct Fc1StreamParams {
     uint8_t* x_on; uint8_t* x_tg;  // tile images [T][n_tiles][16 KB]
     uint32_t* relu_mask;           // [T][n_tiles][2][128]
     int use_act;
+    int l2_prefetch;               // 1: prefetch the next tile's runs into L2
     int n_nets;                    // 2: online + target (learner step), 1: online only (rollout step)
     int t0;                        // batch timestep of item t = 0 (rollout: the step index; obs is addressed at t0 + t)
 };
@@ -641,6 +642,29 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     if (t_beg < h_end) t_beg = h_end;
                 }
                 const uint32_t tx = __reduce_add_sync(0xffffffffu, t_beg - h_end);
+                // L2 prefetch of the same group of this CTA's NEXT tile: the staging ring is all the shared memory that is
+                // left (3 x 18 KB in flight per SM), so the copies should see L2 latency, not loaded-HBM latency
+                if (P.l2_prefetch && cnt > 0 && item + gridDim.x < n_items) {
+                    const int64_t item2 = item + gridDim.x;
+                    const int64_t t2 = item2 / P.n_tiles, tile2 = item2 - t2 * P.n_tiles;
+                    const int64_t q0 = tile2 * BM + g * GROUP_ROWS;
+                    int rows2 = P.R - q0 < GROUP_ROWS ? (int)(P.R - q0) : GROUP_ROWS;
+                    if (rows2 < 0) rows2 = 0;
+                    const uint32_t c0 = (uint32_t)q0 / (uint32_t)P.N;
+                    const int m00 = (int)((uint32_t)q0 - c0 * (uint32_t)P.N);
+                    int fc = P.N - m00;
+                    if (fc > rows2) fc = rows2;
+                    const int lr2 = lane == 0 ? 0 : fc + (lane - 1) * P.N;
+                    int cnt2 = lane == 0 ? fc : (rows2 - lr2 < P.N ? rows2 - lr2 : P.N);
+                    if (cnt2 > 0) {
+                        const char* gb = reinterpret_cast<const char*>(P.obs + ep_row(P.ep_index, (int64_t)c0 + lane) * P.obs_sb +
+                                                                       ((t2 + P.t0) * P.N + (lane == 0 ? m00 : 0)) * (int64_t)P.O);
+                        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(gb) + 15) & ~(uintptr_t)15;
+                        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(gb) + (uint64_t)cnt2 * P.O * 4) & ~(uintptr_t)15;
+                        if (a1 > a0)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+                    }
+                }
                 mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
                 if (cnt > 0) {
                     for (int k = 0; k < cnt; ++k) { ro[lr + k] = (int)(cur + (uint32_t)k * P.O * 4u); rn[lr + k] = n0 + k; }
@@ -1011,6 +1035,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             Q.x_on = reinterpret_cast<uint8_t*>(x_on); Q.x_tg = reinterpret_cast<uint8_t*>(x_tg);
             Q.relu_mask = relu_mask; Q.use_act = d->obs_last_action;
             Q.n_nets = x_tg ? 2 : 1; Q.t0 = t0;
+            Q.l2_prefetch = 1;
             PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
             const int64_t n_items = (int64_t)nt * n_tiles;
             const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
