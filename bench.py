@@ -251,6 +251,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=0)
+    ap.add_argument("--action-rng", default="philox", choices=["philox", "torch"],
+                    help="select_actions config: where the epsilon-greedy draws come from")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16 = tcgen05 tensor-core tier (fp32 accumulate, parity 1e-2); fp32 = CUDA-core tier (parity 1e-5)")
     a = ap.parse_args()
@@ -467,7 +469,10 @@ def rollout_bench(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    args = default_args(shape, mixer="qmix", device="cuda", use_cuda=True, precision=a.precision)
+    # action_rng="philox": the epsilon-greedy draws come from the kernel's own Philox stream (one fused call per step);
+    # the default "torch" mode replays the reference's generator order for bit-identical actions and costs two torch
+    # RNG launches + 190 MB of extra traffic per step
+    args = default_args(shape, mixer="qmix", device="cuda", use_cuda=True, precision=a.precision, action_rng=a.action_rng)
     th.manual_seed(7)
     scheme, groups = make_scheme(shape)
     scheme["actions_onehot"] = {"vshape": (A,), "dtype": th.float32, "group": "agents"}
@@ -537,7 +542,7 @@ def rollout_bench(a):
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if a.precision == "fp32" else "bf16 (fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": "BasicMAC.select_actions step, 27m_vs_30m shapes", "envs_per_gpu": envs, "n_agents": N,
-                           "obs": O, "n_actions": A, "parallelism": "dp%d" % world,
+                           "obs": O, "n_actions": A, "parallelism": "dp%d" % world, "action_rng": a.action_rng,
                            "l2_policy": "obs of 4 timesteps (%.1f GB) cycled, larger than L2" % (fields["obs"].numel() * 4 / 1e9)},
                 "roofline": {"kernel": "select_actions_step (all launches)", "bound": "hbm", "achieved": ach,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,

@@ -69,7 +69,7 @@ class BasicMAC:
         b = _lib.make_batch(fields, need_state=False, keep=keep)
         return b, t_local, T_local
 
-    def _run_step(self, ep_batch, t, epsilon=None, u=None, expo=None, seed=0, offset=0, want_actions=False):
+    def _run_step(self, ep_batch, t, epsilon=None, u=None, expo=None, seed=0, offset=0, want_actions=False, want_q=True):
         dev = self._device()
         _lib.require_cuda(self.agent.fc1.weight, "agent parameters")
         keep = []
@@ -89,7 +89,7 @@ class BasicMAC:
         need = _lib.lib().pmb_select_actions_workspace_bytes(C.byref(dims))
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
             self._scratch = th.empty(need, dtype=th.uint8, device=dev)
-        q = th.empty(B, N, A, dtype=th.float32, device=dev)
+        q = th.empty(B, N, A, dtype=th.float32, device=dev) if (want_q or not want_actions) else None
         actions = th.empty(B, N, dtype=th.int64, device=dev) if want_actions else None
         _lib.check(_lib.lib().pmb_select_actions_step(
             C.byref(dims), C.byref(batch), t_local, flat, _lib.ptr(hs), C.c_float(epsilon or 0.0), _lib.ptr(u),
@@ -108,7 +108,7 @@ class BasicMAC:
             sel.epsilon = 0.0 if test_mode else sel.schedule.eval(t_env)
             seed, offset = sel.next_philox()
             _, actions = self._run_step(ep_batch, t_ep, epsilon=sel.epsilon, seed=seed, offset=offset,
-                                        want_actions=True)
+                                        want_actions=True, want_q=False)
             return actions
         q, _ = self._run_step(ep_batch, t_ep)
         avail = ep_batch["avail_actions"][:, t_ep]

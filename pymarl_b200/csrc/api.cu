@@ -531,7 +531,12 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
         fp.b_ih = ap.b_ih; fp.b_hh = ap.b_hh; fp.b2 = ap.fc2_b;
         fp.x_ti = x_ti; fp.h0 = hidden; fp.h_ti = nullptr; fp.g_ti = nullptr; fp.q = q; fp.h_last = hidden;
         fp.R = R; fp.nt = 1; fp.A = d->A; fp.n_tiles = n_tiles;
+        // epsilon-greedy fused into the q epilogue (no q round trip through HBM); q itself only when the caller wants it
+        fp.avail = b->avail + (int64_t)t * d->N * d->A; fp.avail_sb = b->avail_sb; fp.N = d->N; fp.epsilon = epsilon;
+        fp.u = u; fp.expo = expo; fp.seed = seed; fp.offset = offset; fp.actions_out = actions_out;
+        if (actions_out && !q_out) fp.q = nullptr;
         if ((rc = tc_gru_fwd(fp, s))) return rc;
+        return PMB_OK;
     } else {
         rc = fc1_fwd(d, b, t, 1, ap, x, s);
         if (rc) return rc;

@@ -41,6 +41,20 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// Philox4x32-10 and the (0, 1] mapping: identical to select.cu (the fused selection must draw the same numbers)
+__device__ __forceinline__ uint4 gf_philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float gf_u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+
 // 16 fp32 values (columns 16c .. 16c+15 of row r) -> two 16-byte chunks of a tile image
 __device__ __forceinline__ void store_row16(uint8_t* tile, uint32_t r, int c16, const float (&f)[16]) {
     uint4 a = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -257,28 +271,101 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
                 // q = fc2(h)
                 mbar_wait(q_full, it & 1);
                 tc_fence_after();
-                float* qo = P.q + ((int64_t)t * P.R + row) * P.A;
+                float* qo = P.q ? P.q + ((int64_t)t * P.R + row) * P.A : nullptr;
                 const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
+                const bool select = P.actions_out != nullptr && t == P.nt - 1 && valid;
+                const int32_t* av = nullptr;
+                if (select) {
+                    const int64_t bb = (int64_t)((uint32_t)row / (uint32_t)P.N);
+                    av = P.avail + bb * P.avail_sb + (row - bb * P.N) * P.A;
+                }
+                const bool av_vec = (P.A & 3) == 0 && (P.avail_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
+                float best = -INFINITY;
+                int bidx = 0x7fffffff, cnt = 0;
+                unsigned long long okmask = 0ull;
                 for (int c0 = 0; c0 < A_pad; c0 += 16) {
                     uint32_t aq[16];
                     tmem_ld_32x16(tlane + c0, aq);
                     tmem_wait_ld();
                     if (valid) {
-                        if (q_vec) {
+                        float qv[16];
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4)
-                                if (c0 + 4 * j4 < P.A)
-                                    *reinterpret_cast<float4*>(qo + c0 + 4 * j4) = make_float4(
-                                        __uint_as_float(aq[4 * j4]) + bias[256 + c0 + 4 * j4],
-                                        __uint_as_float(aq[4 * j4 + 1]) + bias[256 + c0 + 4 * j4 + 1],
-                                        __uint_as_float(aq[4 * j4 + 2]) + bias[256 + c0 + 4 * j4 + 2],
-                                        __uint_as_float(aq[4 * j4 + 3]) + bias[256 + c0 + 4 * j4 + 3]);
-                        } else {
+                        for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
+                        if (qo) {
+                            if (q_vec) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < P.A) qo[c0 + j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
+                                for (int j4 = 0; j4 < 4; ++j4)
+                                    if (c0 + 4 * j4 < P.A)
+                                        *reinterpret_cast<float4*>(qo + c0 + 4 * j4) =
+                                            make_float4(qv[4 * j4], qv[4 * j4 + 1], qv[4 * j4 + 2], qv[4 * j4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < P.A) qo[c0 + j] = qv[j];
+                            }
+                        }
+                        if (select) {
+                            // this chunk's 16 avail flags: four 16-byte loads when the layout allows
+                            int avj[16];
+                            if (av_vec && c0 + 16 <= P.A) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const int4 w4 = __ldg(reinterpret_cast<const int4*>(av + c0) + j4);
+                                    avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? __ldg(av + c0 + j) : 0;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int a = c0 + j;
+                                if (a < P.A) {
+                                    const bool ok = avj[j] != 0;
+                                    cnt += ok ? 1 : 0;
+                                    okmask |= (unsigned long long)(ok ? 1 : 0) << a;
+                                    const float v = ok ? qv[j] : -INFINITY;
+                                    if (v > best) { best = v; bidx = a; }          // ascending a, strict >: lowest index wins
+                                }
+                            }
                         }
                     }
+                }
+                if (select) {
+                    if (bidx == 0x7fffffff) bidx = 0;                              // all -inf / NaN: first index
+                    // Categorical(avail.float()).sample() == argmax_a (avail[a] / cnt) / Exp(1)[a]
+                    const float prob = __fdiv_rn(1.0f, (float)cnt);
+                    float rbest = -INFINITY;
+                    int ridx = 0x7fffffff;
+                    uint4 r4 = make_uint4(0, 0, 0, 0);
+                    for (int a = 0; a < P.A; ++a) {
+                        float e;
+                        if (P.expo) {
+                            e = __ldg(P.expo + row * P.A + a);
+                        } else {
+                            if ((a & 3) == 0)
+                                r4 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
+                                                                 (uint32_t)(1 + a / 4) | ((uint32_t)(row >> 32) << 16)),
+                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                            const uint32_t w = (a & 3) == 0 ? r4.x : (a & 3) == 1 ? r4.y : (a & 3) == 2 ? r4.z : r4.w;
+                            e = -logf(gf_u01(w));
+                        }
+                        const float ratio = __fdiv_rn(((okmask >> a) & 1ull) ? prob : 0.0f, e);
+                        if (ratio > rbest) { rbest = ratio; ridx = a; }
+                    }
+                    if (ridx == 0x7fffffff) ridx = 0;
+                    float uu;
+                    if (P.u) {
+                        uu = __ldg(P.u + row);
+                    } else {
+                        const uint4 q4 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
+                                                                     ((uint32_t)(row >> 32) << 16)),
+                                                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                        uu = 1.0f - gf_u01(q4.x);                  // [0, 1)
+                    }
+                    int pick = (cnt > 0 && uu < P.epsilon) ? ridx : bidx;
+                    if (pick >= P.A) pick = 0;
+                    P.actions_out[row] = pick;
                 }
                 tc_fence_before();
                 __syncwarp();

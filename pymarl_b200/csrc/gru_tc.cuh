@@ -21,6 +21,16 @@ struct GruFwdParams {
     float* h_last;                   // fp32 [R][64] or null
     int64_t R;
     int nt, A, n_tiles;
+    // optional fused epsilon-greedy selection on the q of the LAST step (components/action_selectors.py:44-62; same
+    // arithmetic and Philox indexing as epsilon_greedy_kernel in select.cu): actions_out == nullptr disables it
+    const int32_t* avail;            // already offset to the step: row (b, n) at avail + b*avail_sb + n*A
+    int64_t avail_sb;
+    int N;
+    float epsilon;
+    const float* u;                  // injected draws [R] / [R][A], or null -> Philox(seed, offset)
+    const float* expo;
+    uint64_t seed, offset;
+    int64_t* actions_out;            // [R]
 };
 
 

@@ -992,15 +992,28 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(scratch);
     float* tab_act = reinterpret_cast<float*>(static_cast<char*>(scratch) + wp_bytes);
     float* tab_id = reinterpret_cast<float*>(static_cast<char*>(scratch) + wp_bytes + ta_bytes);
-    const float* ptrs[2] = {on.fc1_w, tg.fc1_w};
-    int rows[2] = {64, 64}, lds[2] = {D_in, D_in};
-    int rc = tc_pack_w(ptrs, rows, lds, 2, d->O, wp, s);
-    if (rc) return rc;
-    int n_tab = 2 * (d->A + d->N) * 64;
-    fc1_tables_kernel<<<(unsigned)ceil_div(n_tab, 256), 256, 0, s>>>(on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A,
-                                                                     d->N, D_in, d->obs_last_action, d->obs_agent_id,
-                                                                     tab_act, tab_id);
-    PMB_LAUNCH_CHECK("fc1_tables_kernel");
+    // the streaming kernel packs its own W (fc1_stream_pack_kernel) and needs the agent-id table only when the one-hot
+    // columns do not fit the K padding
+    const int n_chunks_s = (d->O + tc::BK - 1) / tc::BK;
+    const int slot_bytes_s = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 32 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
+    const int64_t smem_need_s = 1024 + 2 * (int64_t)n_chunks_s * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes_s +
+                                2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
+    const bool use_stream = tile_images && n_chunks_s <= tc::fs::MAX_CHUNKS && smem_need_s <= 232448;
+    const bool fold_id_s = n_chunks_s * tc::BK - d->O >= d->N + 1;
+    int rc = PMB_OK;
+    if (!use_stream) {
+        const float* ptrs[2] = {on.fc1_w, tg.fc1_w};
+        int rows[2] = {64, 64}, lds[2] = {D_in, D_in};
+        rc = tc_pack_w(ptrs, rows, lds, 2, d->O, wp, s);
+        if (rc) return rc;
+    }
+    if (!use_stream || !fold_id_s) {
+        int n_tab = 2 * (d->A + d->N) * 64;
+        fc1_tables_kernel<<<(unsigned)ceil_div(n_tab, 256), 256, 0, s>>>(on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A,
+                                                                         d->N, D_in, d->obs_last_action, d->obs_agent_id,
+                                                                         tab_act, tab_id);
+        PMB_LAUNCH_CHECK("fc1_tables_kernel");
+    }
     const int64_t M = (int64_t)d->B * nt * d->N;
     RowMap map{b->obs_sb, (int64_t)d->N * d->O, (int64_t)d->O, nt, d->N};
     tc::GemmParams P{b->obs + (int64_t)t0 * d->N * d->O, map, M, d->O, (d->O + tc::BK - 1) / tc::BK, wp, 128,

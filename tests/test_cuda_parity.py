@@ -582,3 +582,36 @@ def test_zero_copy_replay_sample_trains_identically(mixer):
     np.random.seed(77)
     idx = buf.sample(16)
     assert th.equal(idx["obs"], ref["obs"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_rollout_selection_equals_separate_kernel(precision):
+    """pmb_select_actions_step with the epsilon-greedy selection fused into the step (Philox draws inside the kernel)
+    picks exactly the actions that pmb_epsilon_greedy picks from the step's Q tensor with the same (seed, offset)."""
+    import ctypes as C
+    from cuda_utils import to_batch
+    from pymarl_b200 import mac_REGISTRY, _lib
+    from pymarl_b200.synthetic import make_scheme
+    shape = SMAC_SHAPES["2s3z"]
+    args = default_args(shape, device="cuda", precision=precision, action_rng="philox")
+    scheme, groups = make_scheme(shape)
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    mac.cuda()
+    B = 53
+    fields = numpy_episode_fields(shape, B, 4, seed=11, ragged=False)
+    batch = to_batch(shape, fields)
+    mac.init_hidden(B)
+    for t, eps in ((0, 0.0), (1, 0.5), (2, 1.0)):
+        q, acts = mac._run_step(batch, t, epsilon=eps, seed=1234, offset=7 + t, want_actions=True, want_q=True)
+        avail = batch["avail_actions"][:, t].contiguous()
+        ref = th.empty(B, shape.n_agents, dtype=th.int64, device="cuda")
+        _lib.check(_lib.lib().pmb_epsilon_greedy(B * shape.n_agents, shape.n_actions, _lib.ptr(q.contiguous()), _lib.ptr(avail),
+                                                 C.c_float(eps), None, None, 1234, 7 + t, _lib.ptr(ref), _lib.stream_ptr("cuda")),
+                   "pmb_epsilon_greedy")
+        assert th.equal(acts, ref), (precision, t)
+        picked = th.gather(avail, 2, acts.unsqueeze(-1))
+        assert bool((picked != 0).all())                 # only available actions are ever selected
+    # the public call (no Q round trip) gives the same actions as the step that also returns Q
+    mac.init_hidden(B)
+    a1 = mac.select_actions(batch, 1, t_env=0)
+    assert a1.shape == (B, shape.n_agents) and a1.dtype == th.int64
