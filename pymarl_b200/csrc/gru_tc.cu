@@ -23,7 +23,13 @@ namespace tc {
 constexpr int TILE_ROWS = 128;
 constexpr int TILE_BYTES = TILE_ROWS * 128;      // 16 KB
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 : one MUFU op instead of ex2 + rcp (same form as gru_fwd2 in gru_tc2.cu, so the
+// rollout step and the learner's unroll round identically)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(0.5f * x));
+    return fmaf(0.5f, y, 0.5f);
+}
 __device__ __forceinline__ float fast_tanh(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -333,35 +339,34 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
                 }
                 if (select) {
                     if (bidx == 0x7fffffff) bidx = 0;                              // all -inf / NaN: first index
-                    // Categorical(avail.float()).sample() == argmax_a (avail[a] / cnt) / Exp(1)[a]
-                    const float prob = __fdiv_rn(1.0f, (float)cnt);
-                    float rbest = -INFINITY;
-                    int ridx = 0x7fffffff;
-                    uint4 r4 = make_uint4(0, 0, 0, 0);
-                    for (int a = 0; a < P.A; ++a) {
-                        float e;
-                        if (P.expo) {
-                            e = __ldg(P.expo + row * P.A + a);
-                        } else {
-                            if ((a & 3) == 0)
-                                r4 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
-                                                                 (uint32_t)(1 + a / 4) | ((uint32_t)(row >> 32) << 16)),
-                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-                            const uint32_t w = (a & 3) == 0 ? r4.x : (a & 3) == 1 ? r4.y : (a & 3) == 2 ? r4.z : r4.w;
-                            e = -logf(gf_u01(w));
-                        }
-                        const float ratio = __fdiv_rn(((okmask >> a) & 1ull) ? prob : 0.0f, e);
-                        if (ratio > rbest) { rbest = ratio; ridx = a; }
-                    }
-                    if (ridx == 0x7fffffff) ridx = 0;
+                    int ridx;
                     float uu;
-                    if (P.u) {
+                    if (P.expo) {
+                        // reference arithmetic with injected draws: argmax_a (avail[a] / cnt) / Exp(1)[a]
+                        const float prob = __fdiv_rn(1.0f, (float)cnt);
+                        float rbest = -INFINITY;
+                        ridx = 0x7fffffff;
+                        for (int a = 0; a < P.A; ++a) {
+                            const float ratio = __fdiv_rn(((okmask >> a) & 1ull) ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
+                            if (ratio > rbest) { rbest = ratio; ridx = a; }
+                        }
+                        if (ridx == 0x7fffffff) ridx = 0;
                         uu = __ldg(P.u + row);
                     } else {
-                        const uint4 q4 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
+                        // Philox mode (same arithmetic as epsilon_greedy_kernel): word x -> epsilon test, word y -> rank
+                        const uint4 r0 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
                                                                      ((uint32_t)(row >> 32) << 16)),
                                                           make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-                        uu = 1.0f - gf_u01(q4.x);                  // [0, 1)
+                        uu = 1.0f - gf_u01(r0.x);                  // [0, 1)
+                        int k = (int)((1.0f - gf_u01(r0.y)) * (float)cnt);
+                        if (k >= cnt) k = cnt - 1;
+                        ridx = 0;
+                        int seen = 0;
+                        for (int a = 0; a < P.A; ++a) {
+                            const bool ok = (okmask >> a) & 1ull;
+                            if (ok && seen == k) ridx = a;
+                            seen += ok ? 1 : 0;
+                        }
                     }
                     int pick = (cnt > 0 && uu < P.epsilon) ? ridx : bidx;
                     if (pick >= P.A) pick = 0;

@@ -110,37 +110,42 @@ epsilon_greedy_kernel(int64_t rows, int N, int A, const float* __restrict__ q, c
     for (int o = GL / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     group_argmax(best, bidx);
 
-    // Categorical(avail.float()).sample() == argmax_a (avail[a] / cnt) / Exp(1)[a]
-    const float prob = __fdiv_rn(1.0f, (float)cnt);
-    float rbest = -INFINITY;
-    int ridx = 0x7fffffff;
-    for (int a = lane; a < A; a += GL) {
-        bool ok = __ldg(av + a) != 0;
-        float e;
-        if (expo) {
-            e = __ldg(expo + row * A + a);
-        } else {
-            uint4 r4 = philox4x32_10(make_uint4((uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)row,
-                                                (uint32_t)(1 + a / 4) | ((uint32_t)(row >> 32) << 16)),
-                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            uint32_t w = (a & 3) == 0 ? r4.x : (a & 3) == 1 ? r4.y : (a & 3) == 2 ? r4.z : r4.w;
-            e = -logf(u01(w));
+    int ridx;
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    if (expo) {
+        // reference arithmetic with injected draws: Categorical(avail.float()).sample() == argmax_a (avail[a] / cnt) / Exp(1)[a]
+        const float prob = __fdiv_rn(1.0f, (float)cnt);
+        float rbest = -INFINITY;
+        ridx = 0x7fffffff;
+        for (int a = lane; a < A; a += GL) {
+            bool ok = __ldg(av + a) != 0;
+            float ratio = __fdiv_rn(ok ? prob : 0.0f, __ldg(expo + row * A + a));
+            if (ratio > rbest) { rbest = ratio; ridx = a; }
         }
-        float ratio = __fdiv_rn(ok ? prob : 0.0f, e);
-        if (ratio > rbest) { rbest = ratio; ridx = a; }
+        if (ridx == 0x7fffffff) ridx = lane < A ? lane : 0x7ffffffe;
+        group_argmax(rbest, ridx);
+    } else {
+        // Philox mode: the same distribution (uniform over the available actions) from ONE counter block per row:
+        // word x -> the epsilon test, word y -> the rank k of the chosen action among the available ones
+        r0 = philox4x32_10(make_uint4((uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)row, ((uint32_t)(row >> 32) << 16)),
+                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        int k = (int)((1.0f - u01(r0.y)) * (float)cnt);
+        if (k >= cnt) k = cnt - 1;
+        ridx = 0;
+        int seen = 0;
+        for (int a = 0; a < A; ++a) {                  // every lane walks the whole row: A is small, the loads hit L1
+            const bool ok = __ldg(av + a) != 0;
+            if (ok && seen == k) ridx = a;
+            seen += ok ? 1 : 0;
+        }
     }
-    if (ridx == 0x7fffffff) ridx = lane < A ? lane : 0x7ffffffe;
-    group_argmax(rbest, ridx);
 
     if (active && lane == 0) {
         float uu;
         if (u) {
             uu = __ldg(u + row);
         } else {
-            uint4 r4 = philox4x32_10(make_uint4((uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)row,
-                                                ((uint32_t)(row >> 32) << 16)),
-                                     make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            uu = 1.0f - u01(r4.x);                 // [0, 1)
+            uu = 1.0f - u01(r0.x);                 // [0, 1)
         }
         int pick = (cnt > 0 && uu < epsilon) ? ridx : bidx;
         if (pick >= A) pick = 0;
