@@ -6,6 +6,7 @@ Tolerances (BASELINE.json north_star / SURVEY.md section 8c): integer outputs bi
 fp32 tier: Q, Q_tot, loss, grad_norm, gradients and post-update parameters within 1e-5
 norm-wise relative error (max|a-b| / max|b|)."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -615,3 +616,15 @@ def test_fused_rollout_selection_equals_separate_kernel(precision):
     mac.init_hidden(B)
     a1 = mac.select_actions(batch, 1, t_env=0)
     assert a1.shape == (B, shape.n_agents) and a1.dtype == th.int64
+
+
+def test_shape_sweep_both_tiers():
+    """tools/shape_sweep.py: the learner step against the oracle on 8 hand-picked edge shapes (N = 1 and 64, O = 3, 64,
+    320 and 321, S + 1 a multiple of 64, A = 2 and 64, B = 1 and 130, T = 2) and 6 random ones, on both precision tiers:
+    statistics and post-update parameters within the tier's tolerance."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "shape_sweep.py"), "6", "5"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
