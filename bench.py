@@ -77,10 +77,10 @@ def phase_work(name, B, T, N, O, S, A, H, E, mixer):
         return 2.0 * BT * ks * C, BT * (ks * 2 + kc * 2 + N * f4 + f4)
     if name == "mixer_bwd" and mixer == "qmix":   # mix backward on the raw images + weight-gradient GEMM over both images
         return 2.0 * BT * ks * C, BT * (2 * kc * 2 + kc * 2 + ks * 2 + 2 * N * f4)
-    if name == "gru_unroll_bwd_tc":            # 4 gate tiles + h in; 3 gate-gradient tiles + dpre1 out (+ weight_hh in TMEM)
-        return 2.0 * rows * H * 9 * H, rows * (640 + 512 + 8)
-    if name == "dW_rnn_tc":                    # 3 gate-gradient tiles + x
-        return 2.0 * rows * H * 3 * H, rows * (384 + 128)
+    if name == "gru_unroll_bwd_tc":            # 4 gate tiles + h + x in; dpre1 out; all rnn.* gradients in TMEM
+        return 2.0 * rows * H * (6 * H + 8 * H), rows * (640 + 128 + 128 + 8)
+    if name == "dW_rnn_tc":                    # reduction of the per-tile partials
+        return 0.0, -(-(B * N) // 128) * (2 * 192 * 64 + 256) * f4
     if name == "dW_fc1_fc2_tc":
         return 2.0 * rows * H * (ko + H + 2 * H), rows * (128 + 128 + ko * 2 + 16)
     if name.startswith("fc1_fwd"):

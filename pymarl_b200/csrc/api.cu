@@ -192,7 +192,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
     if (d->precision == PMB_PREC_BF16) {
         int64_t f = tc_fc1_scratch_bytes(d);
         if (f > sc) sc = f;
-        int64_t g = 131072 + tc_gru_dw_scratch_bytes() + tc_gru_whh_partial_bytes((int)ceil_div((int64_t)d->B * d->N, 128));
+        int64_t g = 131072 + tc_gru_bwd2_partial_bytes((int)ceil_div((int64_t)d->B * d->N, 128));
         if (g > sc) sc = g;
         int64_t a2 = tc_atb_ti_scratch_bytes(d->T, (int)ceil_div((int64_t)d->B * d->N, 128), d->O);
         if (a2 > sc) sc = a2;
@@ -682,15 +682,13 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         AgentGrads gr = agent_grads(d, flat_g);
         PHASE(s, "gru_unroll_bwd_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
-        char* sc2 = reinterpret_cast<char*>(v.scratch) + 131072;
-        float* whh_part = reinterpret_cast<float*>(sc2 + tc_gru_dw_scratch_bytes());
-        if ((rc = tc_gru_bwd2(reinterpret_cast<const __nv_bfloat16*>(gru_img),
-                              reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576), on.fc2_w, h_ti, g_ti, x_tg_ti,
+        float* rnn_part = reinterpret_cast<float*>(reinterpret_cast<char*>(v.scratch) + 131072);
+        auto img = [&](int64_t off) { return reinterpret_cast<const __nv_bfloat16*>(gru_img + off); };
+        if ((rc = tc_gru_bwd2(img(0), img(24576), img(49152), x_on_ti, h_ti, g_ti, x_tg_ti,
                               reinterpret_cast<const uint32_t*>(v.relu_mask), v.d_chosen, b->actions, b->actions_sb, b->ep_index,
-                              R, d->T, d->N, d->A, n_tiles, whh_part, s))) return rc;
+                              R, d->T, d->N, d->A, n_tiles, rnn_part, s))) return rc;
         PHASE(s, "dW_rnn_tc");
-        if ((rc = tc_gru_whh_reduce(whh_part, n_tiles, gr.w_hh, gr.b_hh, s))) return rc;
-        if ((rc = tc_gru_dw(g_ti, x_on_ti, d->T, n_tiles, gr.w_ih, gr.b_ih, gr.b_hh, sc2, tc_gru_dw_scratch_bytes(), s))) return rc;
+        if ((rc = tc_gru_bwd2_reduce(rnn_part, n_tiles, gr.w_ih, gr.w_hh, gr.b_ih, gr.b_hh, s))) return rc;
         if (fused_dw) {
             PHASE(s, "dW_fc1_fc2_tc");
             if ((rc = tc_agent_dw(d, b, x_tg_ti, h_ti, obs_ti, v.d_chosen, n_tiles, gr.fc1_w, gr.fc1_b, gr.fc2_w, gr.fc2_b,

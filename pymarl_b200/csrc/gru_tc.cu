@@ -11,8 +11,8 @@
 //                epilogue thread) and in a bf16 operand tile.  Per step: 16 tcgen05.mma for the gates (r|z fused over
 //                [x|h], n input part, n hidden part), gate math out of TMEM, 4 mma for fc2, q out of TMEM.
 //                2 CTAs per SM.  (The learner step uses gru_fwd2 / gru_bwd2 / q_select in gru_tc2.cu.)
-//   gru_dw_tc  : rnn.weight_ih / weight_hh / biases: sum over (t, tile) of [dg]^T . [x | h | 1] with
-//                every operand bulk-copied (no conversion) - a pure HBM-bandwidth kernel.
+//   agent_dw_tc: fc1 / fc2 weight gradients as one image-fed GEMM kernel.  (The rnn.* gradients are accumulated
+//                inside gru_bwd2, gru_tc2.cu.)
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "gru_tc.cuh"
@@ -387,160 +387,6 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
 }
 
 // ------------------------------------------------------------------------------------------
-// rnn.weight_ih / bias_ih gradients from tile images (pure bulk-copy + MMA).  rnn.weight_hh is accumulated inside
-// gru_bwd2 (gru_tc2.cu), where the gate gradients and h_{t-1} already are in shared memory.
-// ------------------------------------------------------------------------------------------
-namespace gd {
-constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;                   // da_r | da_z | da_n | x
-constexpr int ONES = STAGES * STAGE_BYTES;                    // static all-ones block (16 KB)
-constexpr int BARS = ONES + TILE_BYTES;
-constexpr int SMEM_BYTES = 1024 + BARS + 128;
-constexpr int THREADS = 192;
-constexpr int PARTIAL_FLOATS = 192 * 64 + 192;               // dW_ih | db_ih
-}  // namespace gd
-
-struct GruDwParams {
-    const uint8_t* g_ti;             // [T][n_tiles][4][16 KB]  da_r, da_z, da_n, (4th tile unused)
-    const uint8_t* x_ti;             // [T][n_tiles][16 KB]
-    float* partial;                  // [grid][PARTIAL_FLOATS]
-    int64_t n_items;                 // T * n_tiles
-    int64_t items_per_cta;
-};
-
-__global__ void __launch_bounds__(gd::THREADS, 1) gru_dw_tc_kernel(GruDwParams P) {
-    using namespace gd;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
-    uint64_t* full = bars;               // [STAGES]
-    uint64_t* empty = bars + STAGES;     // [STAGES]
-    uint64_t* done = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1);
-        fence_barrier_init();
-    }
-    if (warp == 4) tmem_alloc(tmem_slot, 256);
-    // the ones block: bf16 1.0 everywhere (only the first 16 columns are read)
-    for (int i = threadIdx.x; i < TILE_BYTES / 16; i += THREADS)
-        reinterpret_cast<uint4*>(smem + ONES)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int64_t beg = (int64_t)blockIdx.x * P.items_per_cta;
-    const int64_t end = beg + P.items_per_cta < P.n_items ? beg + P.items_per_cta : P.n_items;
-    const int64_t n_my = end > beg ? end - beg : 0;
-
-    if (warp == 5) {
-        if (lane == 0) {
-            for (int64_t i = 0; i < n_my; ++i) {
-                const int s = (int)(i % STAGES);
-                const int64_t item = beg + i;                 // item = t * n_tiles + tile (same index in both buffers)
-                mbar_wait(&empty[s], (uint32_t)(((i / STAGES) & 1) ^ 1));
-                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                uint8_t* st = smem + s * STAGE_BYTES;
-                bulk_copy_g2s(st, P.g_ti + item * 4 * TILE_BYTES, 3 * TILE_BYTES, &full[s]);
-                bulk_copy_g2s(st + 3 * TILE_BYTES, P.x_ti + item * TILE_BYTES, TILE_BYTES, &full[s]);
-            }
-        }
-    } else if (warp == 4) {
-        if (lane == 0 && n_my > 0) {
-            const uint32_t id64 = umma_idesc_bf16(128, 64, 1, 1), id16 = umma_idesc_bf16(128, 16, 1, 1);
-            const uint32_t ones = smem_u32(smem + ONES);
-            for (int64_t i = 0; i < n_my; ++i) {
-                const int s = (int)(i % STAGES);
-                mbar_wait(&full[s], (uint32_t)((i / STAGES) & 1));
-                tc_fence_after();
-                const uint32_t dg = smem_u32(smem + s * STAGE_BYTES), xt = dg + 3 * TILE_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {               // 128 rows = 8 x (K = 16)
-                    const uint32_t acc = (i | kk) != 0;
-                    const uint64_t a_rz = umma_desc_sw128(dg + kk * 2048, TILE_BYTES, 1024);
-                    // [da_n | x]: the second block is not a gradient, its accumulator rows (64..127) are ignored
-                    const uint64_t a_n = umma_desc_sw128(dg + 2 * TILE_BYTES + kk * 2048, TILE_BYTES, 1024);
-                    const uint64_t b_x = umma_desc_sw128(xt + kk * 2048, TILE_BYTES, 1024);
-                    const uint64_t b_1 = umma_desc_sw128(ones + kk * 2048, TILE_BYTES, 1024);
-                    umma_bf16(tmem_base, a_rz, b_x, id64, acc);              // [r|z]^T x
-                    umma_bf16(tmem_base + 64, a_n, b_x, id64, acc);          // [n|.]^T x
-                    umma_bf16(tmem_base + 128, a_rz, b_1, id16, acc);        // column sums
-                    umma_bf16(tmem_base + 144, a_n, b_1, id16, acc);
-                }
-                umma_commit(&empty[s]);
-            }
-            umma_commit(done);
-        }
-    } else {
-        // epilogue: row c of the accumulators = gate column (warp*32 + lane) of the [r|z] resp. [n|.] pair
-        float* out = P.partial + (int64_t)blockIdx.x * PARTIAL_FLOATS;
-        float* dwih = out, *dbih = out + 192 * 64;
-        const int c = warp * 32 + lane;                       // 0..127
-        if (n_my > 0) {
-            mbar_wait(done, 0);
-            tc_fence_after();
-            const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int g = 0; g < 64; g += 32) {
-                uint32_t v1[32], v2[32];
-                tmem_ld_32x32(tl + g, v1);
-                tmem_ld_32x32(tl + 64 + g, v2);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    dwih[c * 64 + g + j] = __uint_as_float(v1[j]);                       // rows r, z
-                    if (c < 64) dwih[(128 + c) * 64 + g + j] = __uint_as_float(v2[j]);   // rows n
-                }
-            }
-            uint32_t b1[16], b2[16];
-            tmem_ld_32x16(tl + 128, b1);
-            tmem_ld_32x16(tl + 144, b2);
-            tmem_wait_ld();
-            dbih[c] = __uint_as_float(b1[0]);
-            if (c < 64) dbih[128 + c] = __uint_as_float(b2[0]);
-        } else {
-            for (int i = threadIdx.x; i < PARTIAL_FLOATS; i += 128) out[i] = 0.f;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
-    }
-}
-
-// w_ih, b_ih from the gru_dw partials; b_hh[r, z] = b_ih[r, z] (the same column sums)
-__global__ void gru_dw_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ w_ih,
-                                     float* __restrict__ b_ih, float* __restrict__ b_hh) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= gd::PARTIAL_FLOATS) return;
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * gd::PARTIAL_FLOATS + i];
-    if (i < 192 * 64) w_ih[i] = s;
-    else {
-        const int k = i - 192 * 64;
-        b_ih[k] = s;
-        if (k < 128) b_hh[k] = s;
-    }
-}
-
-// w_hh and b_hh[n] from the per-tile partials of gru_bwd2: [n_tiles][192*64 + 64], summed in tile order
-__global__ void gru_whh_reduce_kernel(const float* __restrict__ partial, int n_part, float* __restrict__ w_hh,
-                                      float* __restrict__ b_hh) {
-    constexpr int PF = 192 * 64 + 64;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= PF) return;
-    float s = 0.f;
-    for (int c = 0; c < n_part; ++c) s += partial[(int64_t)c * PF + i];
-    if (i < 192 * 64) w_hh[i] = s;
-    else b_hh[128 + (i - 192 * 64)] = s;
-}
-
-// ------------------------------------------------------------------------------------------
 // fc1 / fc2 weight gradients from tile images, one-hot operands generated on the fly.
 //   item = (t, tile, half): 64 rows.  A1 = [dpre1 | Q1], A2 = [P1 | (ignored)] (MN-major, M = 128), where
 //     Q1[row, a]  = dq[row]        if a == action[row]          (-> fc2.weight / fc2.bias)
@@ -793,32 +639,6 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
     return PMB_OK;
 }
 
-int64_t tc_gru_dw_scratch_bytes() { return align_up((int64_t)148 * 2 * tc::gd::PARTIAL_FLOATS * 4, 256); }
-
-int tc_gru_dw(const uint8_t* g_ti, const uint8_t* x_ti, int T, int n_tiles, float* w_ih, float* b_ih, float* b_hh,
-              void* scratch, int64_t scratch_bytes, cudaStream_t s) {
-    tc::GruDwParams P;
-    P.g_ti = g_ti; P.x_ti = x_ti;
-    P.n_items = (int64_t)T * n_tiles;
-    int grid = (int)(P.n_items < sm_count() ? P.n_items : sm_count());
-    if ((int64_t)grid * tc::gd::PARTIAL_FLOATS * 4 > scratch_bytes) { set_error("tc_gru_dw: scratch too small"); return PMB_ERR_WORKSPACE; }
-    P.items_per_cta = ceil_div(P.n_items, grid);
-    P.partial = static_cast<float*>(scratch);
-    PMB_CUDA(cudaFuncSetAttribute(tc::gru_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gd::SMEM_BYTES));
-    tc::gru_dw_tc_kernel<<<grid, tc::gd::THREADS, tc::gd::SMEM_BYTES, s>>>(P);
-    PMB_LAUNCH_CHECK("gru_dw_tc_kernel");
-    tc::gru_dw_reduce_kernel<<<(unsigned)ceil_div(tc::gd::PARTIAL_FLOATS, 256), 256, 0, s>>>(P.partial, grid, w_ih, b_ih, b_hh);
-    PMB_LAUNCH_CHECK("gru_dw_reduce_kernel");
-    return PMB_OK;
-}
-
-int64_t tc_gru_whh_partial_bytes(int n_tiles) { return align_up((int64_t)n_tiles * (192 * 64 + 64) * 4, 256); }
-
-int tc_gru_whh_reduce(const float* partial, int n_tiles, float* w_hh, float* b_hh, cudaStream_t s) {
-    tc::gru_whh_reduce_kernel<<<(unsigned)ceil_div(192 * 64 + 64, 256), 256, 0, s>>>(partial, n_tiles, w_hh, b_hh);
-    PMB_LAUNCH_CHECK("gru_whh_reduce_kernel");
-    return PMB_OK;
-}
 
 int64_t tc_agent_dw_scratch_bytes() { return align_up((int64_t)148 * 2 * tc::ad::PARTIAL_FLOATS * 4, 256); }
 

@@ -37,11 +37,6 @@ struct GruFwdParams {
 }  // namespace tc
 
 int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s);
-int64_t tc_gru_dw_scratch_bytes();
-int tc_gru_dw(const uint8_t* g_ti, const uint8_t* x_ti, int T, int n_tiles, float* w_ih, float* b_ih, float* b_hh,
-              void* scratch, int64_t scratch_bytes, cudaStream_t s);
-int64_t tc_gru_whh_partial_bytes(int n_tiles);
-int tc_gru_whh_reduce(const float* partial, int n_tiles, float* w_hh, float* b_hh, cudaStream_t s);
 int64_t tc_agent_dw_scratch_bytes();
 int tc_agent_dw(const pmb_dims* d, const pmb_batch* b, const uint8_t* dpre1_ti, const uint8_t* h_ti, const uint8_t* obs_ti,
                 const float* d_chosen, int n_tiles, float* fc1_w, float* fc1_b, float* fc2_w, float* fc2_b, void* scratch,
@@ -51,10 +46,12 @@ int tc_gru_fwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, co
 int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_on_img, const __nv_bfloat16* w2_tg_img,
                 const float* b2_on, const float* b2_tg, const uint8_t* h_on_ti, const uint8_t* h_tg_ti, int n_tiles,
                 float* chosen, float* tmax, float* q_on_out, float* q_tg_out, cudaStream_t s);
-int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* fc2_w, const uint8_t* h_ti,
-                uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask, const float* d_chosen, const int64_t* actions,
-                int64_t actions_sb, const int64_t* ep_index, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial,
-                cudaStream_t s);
+int64_t tc_gru_bwd2_partial_bytes(int n_tiles);
+int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const __nv_bfloat16* w2_img,
+                const uint8_t* x_ti, const uint8_t* h_ti, const uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask,
+                const float* d_chosen, const int64_t* actions, int64_t actions_sb, const int64_t* ep_index, int64_t R, int T,
+                int N, int A, int n_tiles, float* partial, cudaStream_t s);
+int tc_gru_bwd2_reduce(const float* partial, int n_tiles, float* w_ih, float* w_hh, float* b_ih, float* b_hh, cudaStream_t s);
 int tc_ti_zero_pad(uint8_t* buf, int n_t, int n_tiles, int64_t R, cudaStream_t s);
 
 }  // namespace pmb

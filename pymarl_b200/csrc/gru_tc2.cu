@@ -516,71 +516,81 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
 // ------------------------------------------------------------------------------------------
 // backward recurrence (BPTT), one tile per CTA, double-buffered bulk-copied inputs
 // ------------------------------------------------------------------------------------------
-//   stage buffer (80 KB): [r | z | n | hn | h_prev] tile images of step t, brought in by two bulk copies.  The gate
-//   gradients are written IN PLACE (dr -> r, dz -> z, dn -> n, dn*r -> hn: every thread overwrites exactly the
-//   elements it has just read), are the K-major A operands of the 24 tcgen05.mma (dx = dg . W_ih, dh_rec = dg' . W_hh;
-//   B = the weight images read MN-major) and leave as ONE 64 KB bulk store into the gate stash (gru_dw reads them);
-//   the h_prev slot is reused as the staging tile of dpre1 = relu'(x) dx.  dh stays in fp32 registers.
-//   rnn.weight_hh is accumulated HERE (the gate gradients and h_{t-1} are in shared memory anyway): 16 more
-//   tcgen05.mma per step, [da_r|da_z]^T h_{t-1} and [da_n|da_n r]^T h_{t-1} with both operands read MN-major, into 128
-//   TMEM columns that live for the whole kernel; sum(da_n r) (bias_hh[n]) in fp32 registers.  Only three gradient tiles
-//   (da_r, da_z, da_n) go back to the stash for gru_dw_tc (rnn.weight_ih).
+//   stage buffer (80 KB): [r | z | n | hn | h_prev] tile images of step t, brought in by two bulk copies; x_t in a
+//   sixth, single-buffered slot (refilled as soon as the step's MMAs have completed, prefetched into L2 a step ahead).
+//   The gate gradients are written IN PLACE (dr -> r, dz -> z, dn -> n, dn*r -> hn: every thread overwrites exactly
+//   the elements it has just read) and are (a) the K-major A operands of 24 tcgen05.mma (dx = dg . W_ih, dh_rec =
+//   dg' . W_hh; B = the weight images read MN-major), (b) the MN-major A operands of the weight-gradient MMAs
+//   [da_r|da_z]^T [x|h_prev] and [da_n|da_n r]^T [x|h_prev] (N = 128: the x slot and the h_prev slot as two 64-column
+//   blocks of one B operand) and of the bias column sums (B = a block of ones), accumulated over the whole kernel in
+//   288 TMEM columns.  They never go to HBM; the only store per step is dpre1 = relu'(x) dx, staged in the h_prev
+//   slot.  dh stays in fp32 registers; the fc2.weight row of the step's action comes out of the bf16 image in global
+//   memory (L1), fetched one step ahead.
 namespace b2 {
+// 227 KB of shared memory, to the byte: both weight images (48 KB), ONE x slot (16 KB), two 5-tile stages (160 KB), a
+// 2 KB block of ones (bias column sums on the tensor core) and the barriers.  There is no room for the usual 1 KB of
+// alignment slack: the kernel has no static shared memory, so the dynamic window starts 1024-aligned (checked, traps).
 constexpr int WIH = 0, WHH = 24576;
-constexpr int BUF = 49152;                         // [2][5][16 KB]
+constexpr int XS = 49152;                          // x_t tile (single slot: only the weight-gradient MMAs read it)
+constexpr int BUF = XS + TILE_BYTES2;              // [2][5][16 KB]   r | z | n | hn | h_prev
 constexpr int BUF_BYTES = 5 * TILE_BYTES2;
-constexpr int W2T = BUF + 2 * BUF_BYTES;           // fc2.weight as bf16 [A][72] (row stride 144 B)
-constexpr int W2T_STRIDE = 144;
-constexpr int W2T_BYTES = 64 * W2T_STRIDE;         // A <= 64
-constexpr int BARS = W2T + W2T_BYTES;
-constexpr int SMEM_BYTES = 1024 + BARS + 256;
+constexpr int ONES = BUF + 2 * BUF_BYTES;          // bf16 1.0, 16 rows x 128 B
+constexpr int BARS = ONES + 2048;
+constexpr int SMEM_BYTES = BARS + 128;
 constexpr int N_EPI_WARPS = 8, MMA_WARP = 8, IO_WARP = 9;
 constexpr int THREADS = 320;
+// per-tile partial: weight_ih [192][64] | weight_hh [192][64] | bias r,z (ih = hh) [128] | bias_ih n [64] | bias_hh n [64]
+constexpr int PARTIAL_FLOATS = 2 * 192 * 64 + 256;
+static_assert(SMEM_BYTES <= 232448, "gru_bwd2 shared memory");
 }  // namespace b2
 
 struct GruBwd2Params {
     const __nv_bfloat16* w_ih_img;
     const __nv_bfloat16* w_hh_img;
-    const float* fc2_w;              // fp32 [A][64]
+    const uint8_t* w2_img;           // fc2.weight image: row a at a * 128 B, 16-byte chunk j at (j ^ (a & 7))
+    const uint8_t* x_ti;             // [T][n_tiles][16 KB]       x_t = relu(fc1), the GRU input (weight_ih gradient operand)
     const uint8_t* h_ti;             // [(T+1)][n_tiles][16 KB]   slot t = h_{t-1}
-    uint8_t* g_ti;                   // [T][n_tiles][4][16 KB]: in (r, z, n, hn) -> out (da_r, da_z, da_n, da_n*r)
+    const uint8_t* g_ti;             // [T][n_tiles][4][16 KB]    r, z, n, hn of the forward pass
     uint8_t* dpre1_ti;               // [T][n_tiles][16 KB]
     const uint32_t* relu_mask;       // [T][n_tiles][2][128]: bit j of word (half, row) = fc1 output column 32*half + j > 0
     const float* d_chosen;           // [B][T-1][N]
     const int64_t* actions; int64_t actions_sb;
     const int64_t* ep_index;         // optional batch row -> buffer episode
-    float* whh_partial;              // [n_tiles][192*64 + 64]: this tile's rnn.weight_hh gradient and sum of da_n*r
+    float* partial;                  // [n_tiles][b2::PARTIAL_FLOATS]
     int64_t R;
     int T, N, A, n_tiles;
 };
 
+// BPTT through the GRU over one 128-row tile, fused with ALL recurrent weight gradients: per step the gate gradients
+// are written in place over the stashed gates and feed (a) 24 MMAs for dx and the recurrent part of dh_prev, (b) 16
+// MMAs [da_r|da_z]^T [x|h_prev] and [da_n|da_n r]^T [x|h_prev] (M = 128 gate columns, N = 128, K = the tile's 128 rows)
+// whose TMEM accumulators live for the whole kernel, (c) 16 N=16 MMAs against a block of ones for the bias column sums.
+// The gate gradients never reach HBM.
 __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params P) {
     using namespace b2;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
     uint64_t* w_full = bars;
     uint64_t* in_full = bars + 1;            // [2]  stage buffer landed
-    uint64_t* dg_ready = bars + 3;           // gate gradients written (8 warps)
-    uint64_t* mma_done = bars + 4;
-    uint64_t* dp_ready = bars + 5;           // dpre1 staged (8 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* x_full = bars + 3;             // x slot landed
+    uint64_t* dg_ready = bars + 4;           // gate gradients written (8 warps)
+    uint64_t* mma_done = bars + 5;
+    uint64_t* dp_ready = bars + 6;           // dpre1 staged (8 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
-        mbar_init(&in_full[0], 1); mbar_init(&in_full[1], 1);
+        mbar_init(&in_full[0], 1); mbar_init(&in_full[1], 1); mbar_init(x_full, 1);
         mbar_init(dg_ready, N_EPI_WARPS); mbar_init(mma_done, 1); mbar_init(dp_ready, N_EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 256);
-    // fc2.weight table (bf16, padded rows)
-    for (int i = threadIdx.x; i < P.A * 32; i += THREADS) {
-        const int a = i >> 5, c = (i & 31) * 2;
-        *reinterpret_cast<uint32_t*>(smem + W2T + a * W2T_STRIDE + c * 2) =
-            pack_bf16x2(P.fc2_w[a * 64 + c], P.fc2_w[a * 64 + c + 1]);
-    }
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < 128)
+        reinterpret_cast<uint4*>(smem + ONES)[threadIdx.x] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -590,9 +600,6 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
     const int q4 = warp & 3, ch = (warp >> 2) & 1;
     const uint32_t r = (uint32_t)(q4 * 32 + lane);
     const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + 32 * ch;
-    float bsum[32];                                            // sum over steps of da_n * r of this row / these columns
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bsum[j] = 0.f;
 
     if (warp == IO_WARP) {
         if (lane == 0) {
@@ -607,16 +614,23 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                 bulk_copy_g2s(buf, P.g_ti + tt * 4 * TILE_BYTES2, 4 * TILE_BYTES2, &in_full[i & 1]);
                 bulk_copy_g2s(buf + 4 * TILE_BYTES2, P.h_ti + tt * TILE_BYTES2, TILE_BYTES2, &in_full[i & 1]);
             };
+            auto load_x = [&](int i) {
+                const int64_t tt = (int64_t)(P.T - 1 - i) * P.n_tiles + tile;
+                mbar_arrive_expect_tx(x_full, TILE_BYTES2);
+                bulk_copy_g2s(smem + XS, P.x_ti + tt * TILE_BYTES2, TILE_BYTES2, x_full);
+                if (i + 1 < P.T)                                // the next one comes out of L2
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.x_ti + (tt - P.n_tiles) * TILE_BYTES2),
+                                 "r"((uint32_t)TILE_BYTES2) : "memory");
+            };
             load(0);
+            load_x(0);
             if (P.T > 1) load(1);
             for (int i = 0; i < P.T; ++i) {
-                const int t = P.T - 1 - i;
-                const int64_t tt = (int64_t)t * P.n_tiles + tile;
+                const int64_t tt = (int64_t)(P.T - 1 - i) * P.n_tiles + tile;
                 uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
-                mbar_wait(dg_ready, (uint32_t)(i & 1));
-                bulk_copy_s2g(P.g_ti + tt * 4 * TILE_BYTES2, buf, 3 * TILE_BYTES2);      // da_r, da_z, da_n for gru_dw_tc
-                bulk_commit_group();
-                mbar_wait(dp_ready, (uint32_t)(i & 1));        // implies the MMAs of this step have completed
+                mbar_wait(mma_done, (uint32_t)(i & 1));         // the x slot is free: refill it first (shortest window)
+                if (i + 1 < P.T) load_x(i + 1);
+                mbar_wait(dp_ready, (uint32_t)(i & 1));
                 bulk_copy_s2g(P.dpre1_ti + tt * TILE_BYTES2, buf + 4 * TILE_BYTES2, TILE_BYTES2);
                 bulk_commit_group();
                 bulk_wait_group_read<0>();                     // buffer i & 1 is free again
@@ -627,11 +641,15 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
+            const uint32_t xs = smem_u32(smem + XS), ones = smem_u32(smem + ONES);
             const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);          // A K-major, B MN-major
-            const uint32_t idesc_dw = umma_idesc_bf16(128, 64, 1, 1);       // both MN-major: reduction over the 128 rows
+            const uint32_t idesc_dw = umma_idesc_bf16(128, 128, 1, 1);      // both MN-major: reduction over the 128 rows
+            const uint32_t idesc_b = umma_idesc_bf16(128, 16, 1, 1);
+            const uint64_t b_one = umma_desc_sw128(ones, TILE_BYTES2, 1024);
             mbar_wait(w_full, 0);
             for (int i = 0; i < P.T; ++i) {
                 const uint32_t dg = smem_u32(smem + BUF + (i & 1) * BUF_BYTES);
+                const uint32_t xh_lbo = dg + 4 * TILE_BYTES2 - xs;          // [x | h_prev]: two 64-column blocks this far apart
                 mbar_wait(dg_ready, (uint32_t)(i & 1));
                 tc_fence_after();
                 // dx = da_r W_ir + da_z W_iz + da_n W_in
@@ -648,14 +666,20 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16(tmem_base + 64, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES2 + kk * 32, 16, 1024),
                                   umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
-                // rnn.weight_hh += [da_r|da_z]^T h_prev  and  [da_n|da_n r]^T h_prev  (accumulated over all steps)
+                // weight gradients, accumulated over all steps: [da_r|da_z]^T [x|h_prev], [da_n|da_n r]^T [x|h_prev], and
+                // the column sums of the four gate-gradient tiles (biases)
+                mbar_wait(x_full, (uint32_t)(i & 1));
+                tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint32_t acc = (i | kk) != 0;
-                    const uint64_t b_h = umma_desc_sw128(dg + 4 * TILE_BYTES2 + kk * 2048, TILE_BYTES2, 1024);
-                    umma_bf16(tmem_base + 128, umma_desc_sw128(dg + kk * 2048, TILE_BYTES2, 1024), b_h, idesc_dw, acc);
-                    umma_bf16(tmem_base + 192, umma_desc_sw128(dg + 2 * TILE_BYTES2 + kk * 2048, TILE_BYTES2, 1024), b_h,
-                              idesc_dw, acc);
+                    const uint64_t b_xh = umma_desc_sw128(xs + kk * 2048, xh_lbo, 1024);
+                    const uint64_t a_rz = umma_desc_sw128(dg + kk * 2048, TILE_BYTES2, 1024);
+                    const uint64_t a_n = umma_desc_sw128(dg + 2 * TILE_BYTES2 + kk * 2048, TILE_BYTES2, 1024);
+                    umma_bf16(tmem_base + 128, a_rz, b_xh, idesc_dw, acc);
+                    umma_bf16(tmem_base + 256, a_n, b_xh, idesc_dw, acc);
+                    umma_bf16(tmem_base + 384, a_rz, b_one, idesc_b, acc);
+                    umma_bf16(tmem_base + 400, a_n, b_one, idesc_b, acc);
                 }
                 umma_commit(mma_done);
             }
@@ -669,27 +693,33 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
         float dh[32], zk[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) dh[j] = 0.f;
-        // per-step scalars, fetched one step ahead
+        // per-step scalars and the fc2.weight row of the step's action (32 bf16 of this warp's column half), fetched one
+        // step ahead
         auto fetch_dq = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n) : 0.f; };
         const int64_t be = ep_row(P.ep_index, b);
         auto fetch_a = [&](int t) { return (valid && t >= 0 && t < P.T - 1) ? (int)__ldg(P.actions + be * P.actions_sb + (int64_t)t * P.N + n) : 0; };
         auto fetch_m = [&](int t) { return t >= 0 ? __ldg(P.relu_mask + (((int64_t)t * P.n_tiles + tile) * 2 + ch) * 128 + r) : 0u; };
+        auto fetch_w2 = [&](int a, uint4 (&w)[4]) {
+            const uint8_t* wr = P.w2_img + a * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                w[c] = __ldg(reinterpret_cast<const uint4*>(wr + (((uint32_t)(4 * ch + c) ^ ((uint32_t)a & 7u)) << 4)));
+        };
         float dq = fetch_dq(P.T - 1);
-        int act = fetch_a(P.T - 1);
         uint32_t xm = fetch_m(P.T - 1);
+        uint4 w2[4];
+        fetch_w2(fetch_a(P.T - 1), w2);
+        int act_n = fetch_a(P.T - 2);
         for (int i = 0; i < P.T; ++i) {
             const int t = P.T - 1 - i;
             uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
             const float dq_n = fetch_dq(t - 1);
-            const int act_n = fetch_a(t - 1);
             const uint32_t xm_n = fetch_m(t - 1);
             // chosen-action gradient enters through fc2: dh += dq * fc2_w[a, :]
             if (dq != 0.f) {
-                const uint8_t* wr = smem + W2T + act * W2T_STRIDE + 64 * ch;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const uint4 w = *reinterpret_cast<const uint4*>(wr + 16 * c);
-                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                    const uint32_t ww[4] = {w2[c].x, w2[c].y, w2[c].z, w2[c].w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         dh[8 * c + 2 * k] = fmaf(dq, __uint_as_float(ww[k] << 16), dh[8 * c + 2 * k]);
@@ -697,6 +727,8 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                     }
                 }
             }
+            fetch_w2(act_n, w2);                                // row for step i + 1 (L1-resident table)
+            act_n = fetch_a(t - 2);
             mbar_wait(&in_full[i & 1], (uint32_t)((i >> 1) & 1));
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                       // 4 chunks of 8 columns
@@ -727,7 +759,6 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                         dz2[e] = d * (fhp - fn) * fz * (1.f - fz);
                         dn2[e] = da_n;
                         dnr2[e] = da_n * fr;
-                        bsum[jj] += dnr2[e];
                         zk[jj] = fz;
                     }
                     o_r[k] = pack_bf16x2(dr2[0], dr2[1]); o_z[k] = pack_bf16x2(dz2[0], dz2[1]);
@@ -763,51 +794,80 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(dp_ready);
-            dq = dq_n; act = act_n; xm = xm_n;
+            dq = dq_n; xm = xm_n;
         }
     }
     // ---- end of the tile: every role is done (all MMAs complete, the IO thread has drained its bulk stores) ----
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    float* part = P.whh_partial + (int64_t)tile * (192 * 64 + 64);
-    float* red = reinterpret_cast<float*>(smem + BUF);        // [128 rows][64] fp32: the stage buffers are free now
     if (warp < N_EPI_WARPS) {
-        // weight_hh partial out of TMEM: accumulator row = gate column, accumulator column = h_{t-1} column
+        // accumulator row = gate column (r < 64: first gate of the pair, else the second), accumulator columns 0..63 =
+        // x columns (weight_ih), 64..127 = h_{t-1} columns (weight_hh): warp half ch takes the x resp. the h block
+        float* part = P.partial + (int64_t)tile * PARTIAL_FLOATS;
+        float* w = part + (ch ? 192 * 64 : 0);
+        const uint32_t tl = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const bool n_row = ch == 0 ? r < 64 : r >= 64;           // [da_n]^T x  resp.  [da_n r]^T h_prev
+        float* o1 = w + (int64_t)r * 64;                          // rows r (0..63), z (64..127)
+        float* o2 = w + (int64_t)(128 + (r & 63)) * 64;           // rows n
 #pragma unroll
-        for (int sc = 0; sc < 2; ++sc) {
+        for (int sc = 0; sc < 4; ++sc) {
             uint32_t a1[16], a2[16];
-            ld_tmem_16(tlane + 128 + 16 * sc, a1);
-            ld_tmem_16(tlane + 192 + 16 * sc, a2);
+            ld_tmem_16(tl + 128 + 64 * ch + 16 * sc, a1);
+            ld_tmem_16(tl + 256 + 64 * ch + 16 * sc, a2);
             tmem_wait_ld();
-            float* o1 = part + (int64_t)r * 64 + 32 * ch + 16 * sc;                    // rows r (0..63), z (64..127)
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-                *reinterpret_cast<float4*>(o1 + 4 * j4) =
+            for (int j4 = 0; j4 < 4; ++j4) {
+                *reinterpret_cast<float4*>(o1 + 16 * sc + 4 * j4) =
                     make_float4(__uint_as_float(a1[4 * j4]), __uint_as_float(a1[4 * j4 + 1]), __uint_as_float(a1[4 * j4 + 2]),
                                 __uint_as_float(a1[4 * j4 + 3]));
-            if (r >= 64) {                                                              // rows n: the da_n*r half
-                float* o2 = part + (int64_t)(128 + r - 64) * 64 + 32 * ch + 16 * sc;
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4)
-                    *reinterpret_cast<float4*>(o2 + 4 * j4) =
+                if (n_row)
+                    *reinterpret_cast<float4*>(o2 + 16 * sc + 4 * j4) =
                         make_float4(__uint_as_float(a2[4 * j4]), __uint_as_float(a2[4 * j4 + 1]),
                                     __uint_as_float(a2[4 * j4 + 2]), __uint_as_float(a2[4 * j4 + 3]));
             }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) red[r * 64 + 32 * ch + j] = bsum[j];
+        if (ch == 0) {
+            uint32_t b1[8], b2_[8];
+            ld_tmem_8(tl + 384, b1);
+            ld_tmem_8(tl + 400, b2_);
+            tmem_wait_ld();
+            float* bias = part + 2 * 192 * 64;
+            bias[r] = __uint_as_float(b1[0]);                     // r, z: bias_ih = bias_hh
+            bias[128 + r] = __uint_as_float(b2_[0]);              // 128..191 bias_ih[n], 192..255 bias_hh[n]
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 64) {                                    // bias_hh[n] partial: column sums in row order
-        float sacc = 0.f;
-        for (int rr = 0; rr < 128; ++rr) sacc += red[rr * 64 + threadIdx.x];
-        part[192 * 64 + threadIdx.x] = sacc;
-    }
     if (warp == MMA_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// rnn gradients from the per-tile partials of gru_bwd2, summed in tile order
+__global__ void gru_bwd2_reduce_kernel(const float* __restrict__ partial, int n_part, float* __restrict__ w_ih,
+                                       float* __restrict__ w_hh, float* __restrict__ b_ih, float* __restrict__ b_hh) {
+    constexpr int PF = b2::PARTIAL_FLOATS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PF) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= n_part; c += 4) {
+        s0 += partial[(int64_t)c * PF + i];
+        s1 += partial[(int64_t)(c + 1) * PF + i];
+        s2 += partial[(int64_t)(c + 2) * PF + i];
+        s3 += partial[(int64_t)(c + 3) * PF + i];
+    }
+    for (; c < n_part; ++c) s0 += partial[(int64_t)c * PF + i];
+    const float s = (s0 + s1) + (s2 + s3);
+    if (i < 192 * 64) w_ih[i] = s;
+    else if (i < 2 * 192 * 64) w_hh[i - 192 * 64] = s;
+    else {
+        const int k = i - 2 * 192 * 64;
+        if (k < 128) { b_ih[k] = s; b_hh[k] = s; }
+        else if (k < 192) b_ih[k] = s;
+        else b_hh[k - 64] = s;
     }
 }
 
@@ -843,18 +903,31 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
     return PMB_OK;
 }
 
-int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* fc2_w, const uint8_t* h_ti,
-                uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask, const float* d_chosen, const int64_t* actions,
-                int64_t actions_sb, const int64_t* ep_index, int64_t R, int T, int N, int A, int n_tiles, float* whh_partial,
-                cudaStream_t s) {
+int64_t tc_gru_bwd2_partial_bytes(int n_tiles) {
+    return align_up((int64_t)n_tiles * tc::b2::PARTIAL_FLOATS * 4, 256);
+}
+
+int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const __nv_bfloat16* w2_img,
+                const uint8_t* x_ti, const uint8_t* h_ti, const uint8_t* g_ti, uint8_t* dpre1_ti, const uint32_t* relu_mask,
+                const float* d_chosen, const int64_t* actions, int64_t actions_sb, const int64_t* ep_index, int64_t R, int T,
+                int N, int A, int n_tiles, float* partial, cudaStream_t s) {
     tc::GruBwd2Params P;
-    P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.fc2_w = fc2_w; P.h_ti = h_ti; P.g_ti = g_ti; P.dpre1_ti = dpre1_ti;
+    P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.w2_img = reinterpret_cast<const uint8_t*>(w2_img);
+    P.x_ti = x_ti; P.h_ti = h_ti; P.g_ti = g_ti; P.dpre1_ti = dpre1_ti;
     P.relu_mask = relu_mask; P.d_chosen = d_chosen; P.actions = actions; P.actions_sb = actions_sb;
-    P.whh_partial = whh_partial; P.ep_index = ep_index;
+    P.partial = partial; P.ep_index = ep_index;
     P.R = R; P.T = T; P.N = N; P.A = A; P.n_tiles = n_tiles;
     PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::b2::SMEM_BYTES));
     tc::gru_bwd2_kernel<<<n_tiles, tc::b2::THREADS, tc::b2::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("gru_bwd2_kernel");
+    return PMB_OK;
+}
+
+// rnn.weight_ih / weight_hh / bias_ih / bias_hh gradients out of the partials
+int tc_gru_bwd2_reduce(const float* partial, int n_tiles, float* w_ih, float* w_hh, float* b_ih, float* b_hh, cudaStream_t s) {
+    tc::gru_bwd2_reduce_kernel<<<(unsigned)ceil_div(tc::b2::PARTIAL_FLOATS, 128), 128, 0, s>>>(partial, n_tiles, w_ih, w_hh,
+                                                                                               b_ih, b_hh);
+    PMB_LAUNCH_CHECK("gru_bwd2_reduce_kernel");
     return PMB_OK;
 }
 
