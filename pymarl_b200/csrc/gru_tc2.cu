@@ -526,6 +526,9 @@ __global__ void __launch_bounds__(qs::THREADS, 2) q_select_kernel(QSelectParams 
 //   288 TMEM columns.  They never go to HBM; the only store per step is dpre1 = relu'(x) dx, staged in the h_prev
 //   slot.  dh stays in fp32 registers; the fc2.weight row of the step's action comes out of the bf16 image in global
 //   memory (L1), fetched one step ahead.
+__device__ __forceinline__ uint32_t (&ax_lo(uint32_t (&v)[32]))[16] { return *reinterpret_cast<uint32_t (*)[16]>(&v[0]); }
+__device__ __forceinline__ uint32_t (&ax_hi(uint32_t (&v)[32]))[16] { return *reinterpret_cast<uint32_t (*)[16]>(&v[16]); }
+
 namespace b2 {
 // 227 KB of shared memory, to the byte: both weight images (48 KB), ONE x slot (16 KB), two 5-tile stages (160 KB), a
 // 2 KB block of ones (bias column sums on the tensor core) and the barriers.  There is no room for the usual 1 KB of
@@ -577,7 +580,9 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
     uint64_t* dg_ready = bars + 4;           // gate gradients written (8 warps)
     uint64_t* mma_done = bars + 5;
     uint64_t* dp_ready = bars + 6;           // dpre1 staged (8 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* ld_done = bars + 7;            // dx / dh_rec read out of TMEM (8 warps)
+    uint64_t* dw_done = bars + 8;            // weight-gradient MMAs of the step complete: its six tiles are dead
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
@@ -585,6 +590,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
         mbar_init(w_full, 1);
         mbar_init(&in_full[0], 1); mbar_init(&in_full[1], 1); mbar_init(x_full, 1);
         mbar_init(dg_ready, N_EPI_WARPS); mbar_init(mma_done, 1); mbar_init(dp_ready, N_EPI_WARPS);
+        mbar_init(ld_done, N_EPI_WARPS); mbar_init(dw_done, 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -622,13 +628,22 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.x_ti + (tt - P.n_tiles) * TILE_BYTES2),
                                  "r"((uint32_t)TILE_BYTES2) : "memory");
             };
+            auto prefetch = [&](int i) {                        // stage i into L2: its buffer frees late, the copy must be short
+                const int64_t tt = (int64_t)(P.T - 1 - i) * P.n_tiles + tile;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.g_ti + tt * 4 * TILE_BYTES2),
+                             "r"((uint32_t)(4 * TILE_BYTES2)) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.h_ti + tt * TILE_BYTES2),
+                             "r"((uint32_t)TILE_BYTES2) : "memory");
+            };
             load(0);
             load_x(0);
             if (P.T > 1) load(1);
+            if (P.T > 2) prefetch(2);
             for (int i = 0; i < P.T; ++i) {
+                if (i + 3 < P.T) prefetch(i + 3);
                 const int64_t tt = (int64_t)(P.T - 1 - i) * P.n_tiles + tile;
                 uint8_t* buf = smem + BUF + (i & 1) * BUF_BYTES;
-                mbar_wait(mma_done, (uint32_t)(i & 1));         // the x slot is free: refill it first (shortest window)
+                mbar_wait(dw_done, (uint32_t)(i & 1));          // the x slot is free: refill it first
                 if (i + 1 < P.T) load_x(i + 1);
                 mbar_wait(dp_ready, (uint32_t)(i & 1));
                 bulk_copy_s2g(P.dpre1_ti + tt * TILE_BYTES2, buf + 4 * TILE_BYTES2, TILE_BYTES2);
@@ -666,9 +681,12 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16(tmem_base + 64, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES2 + kk * 32, 16, 1024),
                                   umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                umma_commit(mma_done);
                 // weight gradients, accumulated over all steps: [da_r|da_z]^T [x|h_prev], [da_n|da_n r]^T [x|h_prev], and
-                // the column sums of the four gate-gradient tiles (biases)
+                // the column sums of the four gate-gradient tiles (biases).  Off the dh chain: issued once the epilogue has
+                // read dx / dh_rec out of TMEM, they run while it does the gate-gradient math of the next step.
                 mbar_wait(x_full, (uint32_t)(i & 1));
+                mbar_wait(ld_done, (uint32_t)(i & 1));
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
@@ -681,7 +699,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                     umma_bf16(tmem_base + 384, a_rz, b_one, idesc_b, acc);
                     umma_bf16(tmem_base + 400, a_n, b_one, idesc_b, acc);
                 }
-                umma_commit(mma_done);
+                umma_commit(dw_done);
             }
         }
     } else {
@@ -708,6 +726,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
         float dq = fetch_dq(P.T - 1);
         uint32_t xm = fetch_m(P.T - 1);
         uint4 w2[4];
+        uint32_t dpk[16];                                       // dpre1 of the previous step (bf16 pairs), staged late
         fetch_w2(fetch_a(P.T - 1), w2);
         int act_n = fetch_a(P.T - 2);
         for (int i = 0; i < P.T; ++i) {
@@ -773,27 +792,43 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
             __syncwarp();
             if (lane == 0) mbar_arrive(dg_ready);
 
+            // dpre1 of the previous step goes to its h_prev slot now: the weight-gradient MMAs that read the slot ran
+            // during the math above
+            auto stage_dp = [&](int ip) {
+                uint8_t* hp = smem + BUF + (ip & 1) * BUF_BYTES + 4 * TILE_BYTES2;
+                mbar_wait(dw_done, (uint32_t)(ip & 1));
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(hp + sw128_offset(r, (uint32_t)(4 * ch + c))) =
+                        make_uint4(dpk[4 * c], dpk[4 * c + 1], dpk[4 * c + 2], dpk[4 * c + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dp_ready);
+            };
+            if (i > 0) stage_dp(i - 1);
+
             mbar_wait(mma_done, (uint32_t)(i & 1));
             tc_fence_after();
-#pragma unroll
-            for (int sc = 0; sc < 2; ++sc) {
-                uint32_t ax[16], ah[16];
-                ld_tmem_16(tlane + 16 * sc, ax);
-                ld_tmem_16(tlane + 64 + 16 * sc, ah);
+            {
+                uint32_t ax[32], ah[32];
+                ld_tmem_16(tlane, ax_lo(ax));
+                ld_tmem_16(tlane + 16, ax_hi(ax));
+                ld_tmem_16(tlane + 64, ax_lo(ah));
+                ld_tmem_16(tlane + 80, ax_hi(ah));
                 tmem_wait_ld();
-                float dp[16];
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ld_done);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int jj = 16 * sc + j;
-                    dp[j] = (xm >> jj) & 1u ? __uint_as_float(ax[j]) : 0.f;
-                    dh[jj] = fmaf(dh[jj], zk[jj], __uint_as_float(ah[j]));
+                for (int j = 0; j < 32; j += 2) {
+                    const float d0 = (xm >> j) & 1u ? __uint_as_float(ax[j]) : 0.f;
+                    const float d1 = (xm >> (j + 1)) & 1u ? __uint_as_float(ax[j + 1]) : 0.f;
+                    dpk[j >> 1] = pack_bf16x2(d0, d1);
+                    dh[j] = fmaf(dh[j], zk[j], __uint_as_float(ah[j]));
+                    dh[j + 1] = fmaf(dh[j + 1], zk[j + 1], __uint_as_float(ah[j + 1]));
                 }
-                st_row16(buf + 4 * TILE_BYTES2, r, 2 * ch + sc, dp);     // the h_prev slot is free: dpre1 staging
             }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dp_ready);
+            if (i == P.T - 1) stage_dp(i);
             dq = dq_n; xm = xm_n;
         }
     }
