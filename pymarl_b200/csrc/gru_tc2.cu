@@ -658,6 +658,7 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
             const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH);
             const uint32_t xs = smem_u32(smem + XS), ones = smem_u32(smem + ONES);
             const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);          // A K-major, B MN-major
+            const uint32_t idesc2 = umma_idesc_bf16(128, 128, 0, 1);
             const uint32_t idesc_dw = umma_idesc_bf16(128, 128, 1, 1);      // both MN-major: reduction over the 128 rows
             const uint32_t idesc_b = umma_idesc_bf16(128, 16, 1, 1);
             const uint64_t b_one = umma_desc_sw128(ones, TILE_BYTES2, 1024);
@@ -667,20 +668,22 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                 const uint32_t xh_lbo = dg + 4 * TILE_BYTES2 - xs;          // [x | h_prev]: two 64-column blocks this far apart
                 mbar_wait(dg_ready, (uint32_t)(i & 1));
                 tc_fence_after();
-                // dx = da_r W_ir + da_z W_iz + da_n W_in
+                // [dx | dh_rec] = da_r [W_ir | W_hr] + da_z [W_iz | W_hz]: the r and z gate gradients feed both products, so the
+                // two weight images are read as ONE N = 128 operand (W_ih block, W_hh block 24 KB further)
 #pragma unroll
-                for (int g = 0; g < 3; ++g)
+                for (int g = 0; g < 2; ++g)
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16(tmem_base, umma_desc_sw128(dg + g * TILE_BYTES2 + kk * 32, 16, 1024),
-                                  umma_desc_sw128(wih + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
-                // dh_prev (recurrent part) = da_r W_hr + da_z W_hz + (da_n r) W_hn
+                                  umma_desc_sw128(wih + g * 8192 + kk * 2048, WHH - WIH, 1024), idesc2, (g | kk) != 0);
+                // dx += da_n W_in ;  dh_rec += (da_n r) W_hn
 #pragma unroll
-                for (int g = 0; g < 3; ++g)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem_base + 64, umma_desc_sw128(dg + (g == 2 ? 3 : g) * TILE_BYTES2 + kk * 32, 16, 1024),
-                                  umma_desc_sw128(whh + g * 8192 + kk * 2048, 8192, 1024), idesc, (g | kk) != 0);
+                for (int kk = 0; kk < 4; ++kk) {
+                    umma_bf16(tmem_base, umma_desc_sw128(dg + 2 * TILE_BYTES2 + kk * 32, 16, 1024),
+                              umma_desc_sw128(wih + 2 * 8192 + kk * 2048, 8192, 1024), idesc, 1);
+                    umma_bf16(tmem_base + 64, umma_desc_sw128(dg + 3 * TILE_BYTES2 + kk * 32, 16, 1024),
+                              umma_desc_sw128(whh + 2 * 8192 + kk * 2048, 8192, 1024), idesc, 1);
+                }
                 umma_commit(mma_done);
                 // weight gradients, accumulated over all steps: [da_r|da_z]^T [x|h_prev], [da_n|da_n r]^T [x|h_prev], and
                 // the column sums of the four gate-gradient tiles (biases).  Off the dh chain: issued once the epilogue has
