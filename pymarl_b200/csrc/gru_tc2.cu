@@ -764,27 +764,25 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
                 const uint32_t wn_[4] = {vn.x, vn.y, vn.z, vn.w}, wh_[4] = {vh.x, vh.y, vh.z, vh.w};
                 const uint32_t wp_[4] = {vp.x, vp.y, vp.z, vp.w};
                 uint32_t o_r[4], o_z[4], o_n[4], o_nr[4];
+                const f32x2 ONE = f2_make(1.f, 1.f), M1 = f2_make(-1.f, -1.f);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float dr2[2], dz2[2], dn2[2], dnr2[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int jj = 8 * c + 2 * k + e;
-                        const float fr = e ? __uint_as_float(wr_[k] & 0xffff0000u) : __uint_as_float(wr_[k] << 16);
-                        const float fz = e ? __uint_as_float(wz_[k] & 0xffff0000u) : __uint_as_float(wz_[k] << 16);
-                        const float fn = e ? __uint_as_float(wn_[k] & 0xffff0000u) : __uint_as_float(wn_[k] << 16);
-                        const float fhn = e ? __uint_as_float(wh_[k] & 0xffff0000u) : __uint_as_float(wh_[k] << 16);
-                        const float fhp = e ? __uint_as_float(wp_[k] & 0xffff0000u) : __uint_as_float(wp_[k] << 16);
-                        const float d = dh[jj];
-                        const float da_n = d * (1.f - fz) * (1.f - fn * fn);
-                        dr2[e] = (da_n * fhn) * fr * (1.f - fr);
-                        dz2[e] = d * (fhp - fn) * fz * (1.f - fz);
-                        dn2[e] = da_n;
-                        dnr2[e] = da_n * fr;
-                        zk[jj] = fz;
-                    }
-                    o_r[k] = pack_bf16x2(dr2[0], dr2[1]); o_z[k] = pack_bf16x2(dz2[0], dz2[1]);
-                    o_n[k] = pack_bf16x2(dn2[0], dn2[1]); o_nr[k] = pack_bf16x2(dnr2[0], dnr2[1]);
+                for (int k = 0; k < 4; ++k) {                   // two columns per iteration, packed fp32 pairs (FFMA2)
+                    const int jj = 8 * c + 2 * k;
+                    const f32x2 fr = f2_from_bf16x2(wr_[k]), fz = f2_from_bf16x2(wz_[k]), fn = f2_from_bf16x2(wn_[k]);
+                    const f32x2 fhn = f2_from_bf16x2(wh_[k]), fhp = f2_from_bf16x2(wp_[k]);
+                    const f32x2 d = f2_make(dh[jj], dh[jj + 1]);
+                    const f32x2 omz = f2_fma(fz, M1, ONE);                              // 1 - z
+                    const f32x2 omn2 = f2_fma(f2_mul(fn, fn), M1, ONE);                 // 1 - n^2
+                    const f32x2 da_n = f2_mul(f2_mul(d, omz), omn2);
+                    const f32x2 dr = f2_mul(f2_mul(f2_mul(da_n, fhn), fr), f2_fma(fr, M1, ONE));
+                    const f32x2 dz = f2_mul(f2_mul(f2_mul(d, f2_fma(fn, M1, fhp)), fz), omz);
+                    const f32x2 dnr = f2_mul(da_n, fr);
+                    float a0, a1;
+                    f2_split(dr, a0, a1); o_r[k] = pack_bf16x2(a0, a1);
+                    f2_split(dz, a0, a1); o_z[k] = pack_bf16x2(a0, a1);
+                    f2_split(da_n, a0, a1); o_n[k] = pack_bf16x2(a0, a1);
+                    f2_split(dnr, a0, a1); o_nr[k] = pack_bf16x2(a0, a1);
+                    f2_split(fz, zk[jj], zk[jj + 1]);
                 }
                 *reinterpret_cast<uint4*>(buf + off) = make_uint4(o_r[0], o_r[1], o_r[2], o_r[3]);
                 *reinterpret_cast<uint4*>(buf + TILE_BYTES2 + off) = make_uint4(o_z[0], o_z[1], o_z[2], o_z[3]);
