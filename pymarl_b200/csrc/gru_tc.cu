@@ -13,6 +13,7 @@
 //                2 CTAs per SM.  (The learner step uses gru_fwd2 / gru_bwd2 / q_select in gru_tc2.cu.)
 //   agent_dw_tc: fc1 / fc2 weight gradients as one image-fed GEMM kernel.  (The rnn.* gradients are accumulated
 //                inside gru_bwd2, gru_tc2.cu.)
+#include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "gru_tc.cuh"
@@ -78,47 +79,59 @@ __device__ __forceinline__ void load_row16(const uint8_t* tile, uint32_t r, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// rollout step: one GRU step + fc2 + epsilon-greedy selection for all rows
 // ------------------------------------------------------------------------------------------
-namespace gf {
-constexpr int WIH = 0, WHH = 24576, W2 = 49152, XB = 57344, HT = 90112, BIAS = 106496;   // byte offsets
-constexpr int BIAS_FLOATS = 128 + 64 + 64 + 64;                                         // brz | bin | bhn | b2
+// One persistent CTA per SM with TWO tiles in flight (slots).  Everything a tile needs from HBM arrives by bulk copy
+// while the other tile computes: the x tile image (one 16 KB bulk copy), the fp32 hidden state (two tensor-map copies,
+// 128 rows x 32 columns each, landing 128-byte-swizzled so that the row-per-thread 16-byte accesses of the epilogue are
+// conflict-free; rows beyond R arrive as zeros) and the avail rows (one bulk copy per env the tile touches).  The new
+// hidden state goes back through the same staging tiles: each warp stages its 32 rows and writes them out with
+// coalesced 16-byte stores.  Measured on the way: per-thread row-strided global accesses with 2 CTAs per SM and nothing
+// prefetched (first version) 176 us for 16384 x 27 rows; one 256-byte bulk copy per row 320 us (the copy engine's
+// per-operation cost); 16-byte cp.async by one loader warp 244 us (too few bytes in flight per warp).
+// Warps 0-3 / 4-7: epilogue of slot 0 / 1 (one row per thread, hidden state in 64 fp32 registers), warp 8: MMA issuer
+// (gates of tile k, then fc2 of tile k-1), warp 9: loader (all lanes issue row copies).
+namespace ro {
+constexpr int WIH = 0, WHH = 24576, W2 = 49152;
+constexpr int SLOT0 = 57344;
+constexpr int S_X = 0, S_HT = 16384, S_HS = 32768, S_AV = S_HS + 32768;      // S_HS: two fp32 tiles (columns 0-31, 32-63)
+constexpr int AV_BYTES = 18432;                               // staged avail rows: 128 * A * 4 <= this (A <= 36)
+constexpr int SLOT_BYTES = S_AV + AV_BYTES + 2048;            // 86016 = 84 KB (multiple of 1024)
+constexpr int BIAS = SLOT0 + 2 * SLOT_BYTES;
+constexpr int BIAS_FLOATS = 128 + 64 + 64 + 64;               // brz | bin | bhn | b2
 constexpr int BARS = BIAS + BIAS_FLOATS * 4;
-constexpr int SMEM_BYTES = 1024 + BARS + 128;
-constexpr int THREADS = 192;
-}  // namespace gf
+constexpr int SMEM_BYTES = BARS + 128;
+constexpr int THREADS = 320;
+static_assert(SLOT_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "rollout kernel shared memory");
+}  // namespace ro
 
-
-__global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams P) {
-    // Persistent over row tiles (grid = min(#tiles, 2 x #SMs)): the weights are loaded once per CTA.  `it` counts
-    // (tile, step) iterations and drives every barrier parity.
-    using namespace gf;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+__global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParams P, int av_smem,
+                                                                     const __grid_constant__ CUtensorMap tmap_h0) {
+    using namespace ro;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     float* bias = reinterpret_cast<float*>(smem + BIAS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
-    uint64_t* w_full = bars;             // weights landed
-    uint64_t* x_full = bars + 1;         // [2]
-    uint64_t* x_empty = bars + 3;        // [2]
-    uint64_t* gates_full = bars + 5;
-    uint64_t* q_full = bars + 6;
-    uint64_t* h_ready = bars + 7;        // epilogue wrote the h operand tile (also: h_0 of a new tile)
-    uint64_t* tmem_free = bars + 8;      // epilogue finished reading q
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* w_full = bars;
+    uint64_t* in_full = bars + 1;        // [2] x, h0 rows, avail rows landed
+    uint64_t* slot_free = bars + 3;      // [2] every reader of the slot's buffers is done (4 epilogue warps)
+    uint64_t* hb_ready = bars + 5;       // [2] bf16 h operand written: arrival pair per tile (h_0, then h_1)
+    uint64_t* gates_full = bars + 7;     // [2]
+    uint64_t* q_full = bars + 9;         // [2]
+    uint64_t* tmem_free = bars + 11;     // [2] q drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A_pad = (P.A + 15) & ~15;
-
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
-        mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1);
-        mbar_init(&x_empty[0], 1); mbar_init(&x_empty[1], 1);
-        mbar_init(gates_full, 1); mbar_init(q_full, 1);
-        mbar_init(h_ready, 4); mbar_init(tmem_free, 4);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&in_full[i], 1); mbar_init(&slot_free[i], 4); mbar_init(&hb_ready[i], 4);
+            mbar_init(&gates_full[i], 1); mbar_init(&q_full[i], 1); mbar_init(&tmem_free[i], 4);
+        }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 256);
-    // biases: brz = b_ih + b_hh for r, z ; bin = b_ih[n] ; bhn = b_hh[n] ; b2
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
     for (int i = threadIdx.x; i < 128; i += THREADS) bias[i] = P.b_ih[i] + P.b_hh[i];
     for (int i = threadIdx.x; i < 64; i += THREADS) {
         bias[128 + i] = P.b_ih[128 + i];
@@ -129,260 +142,295 @@ __global__ void __launch_bounds__(gf::THREADS, 2) gru_fwd_tc_kernel(GruFwdParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-    if (warp == 5) {
-        // ===== loader: weights once, then one x tile per (tile, step) =====
+    if (warp == 9) {
+        // ===== loader =====
         if (lane == 0) {
             mbar_arrive_expect_tx(w_full, 24576 + 24576 + 8192);
             bulk_copy_g2s(smem + WIH, P.w_ih_img, 24576, w_full);
             bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
             bulk_copy_g2s(smem + W2, P.w2_img, 8192, w_full);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
-                for (int t = 0; t < P.nt; ++t, ++it) {
-                    const int b = it & 1;
-                    mbar_wait(&x_empty[b], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&x_full[b], TILE_BYTES);
-                    bulk_copy_g2s(smem + XB + b * TILE_BYTES, P.x_ti + ((int64_t)t * P.n_tiles + tile) * TILE_BYTES, TILE_BYTES,
-                                  &x_full[b]);
-                }
         }
-    } else if (warp == 4) {
-        // ===== MMA issuer =====
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k & 1, u = k >> 1;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+            uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
+            mbar_wait(&slot_free[s], (uint32_t)((u & 1) ^ 1));
+            const int64_t row0 = tile * TILE_ROWS;
+            const int rows_here = (int)(P.R - row0 < TILE_ROWS ? P.R - row0 : TILE_ROWS);
+            if (lane == 0) {
+                const uint32_t bytes = TILE_BYTES + (P.h0 ? 2 * TILE_BYTES : 0) + (av_smem ? rows_here * P.A * 4 : 0);
+                mbar_arrive_expect_tx(&in_full[s], bytes);
+                bulk_copy_g2s(sl + S_X, P.x_ti + tile * TILE_BYTES, TILE_BYTES, &in_full[s]);
+                if (P.h0) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                                smem_u32(sl + S_HS + hf * TILE_BYTES)),
+                            "l"(reinterpret_cast<uint64_t>(&tmap_h0)), "r"(32 * hf), "r"((int)row0), "r"(smem_u32(&in_full[s]))
+                            : "memory");
+                }
+            }
+            __syncwarp();
+            if (av_smem) {
+                // one copy per env the tile touches (an env's N x A block is contiguous; the batch stride is free)
+                const int64_t e0 = (int64_t)((uint32_t)row0 / (uint32_t)P.N);
+                const int64_t e = e0 + lane;
+                const int64_t ra = e * P.N > row0 ? e * P.N : row0;                          // first row of env e in the tile
+                const int64_t rb = (e + 1) * P.N < row0 + rows_here ? (e + 1) * P.N : row0 + rows_here;
+                if (ra < rb)
+                    bulk_copy_g2s(sl + S_AV + (ra - row0) * P.A * 4, P.avail + e * P.avail_sb + (ra - e * P.N) * P.A,
+                                  (uint32_t)((rb - ra) * P.A * 4), &in_full[s]);
+                // (128 rows span at most 32 envs as long as N >= 4; smaller N: loop)
+                for (int64_t e2 = e + 32; e2 * P.N < row0 + rows_here; e2 += 32) {
+                    const int64_t ra2 = e2 * P.N, rb2 = (e2 + 1) * P.N < row0 + rows_here ? (e2 + 1) * P.N : row0 + rows_here;
+                    bulk_copy_g2s(sl + S_AV + (ra2 - row0) * P.A * 4, P.avail + e2 * P.avail_sb, (uint32_t)((rb2 - ra2) * P.A * 4),
+                                  &in_full[s]);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer: gates of tile k, then fc2 of tile k-1 (its new hidden state is ready by then) =====
         if (lane == 0) {
             const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH), w2 = smem_u32(smem + W2);
-            const uint32_t ht = smem_u32(smem + HT);
             const uint32_t id128 = umma_idesc_bf16(128, 128, 0, 0), id64 = umma_idesc_bf16(128, 64, 0, 0);
             const uint32_t idq = umma_idesc_bf16(128, A_pad, 0, 0);
+            auto fc2 = [&](int j) {
+                const int s = j & 1;
+                const uint32_t ht = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_HT);
+                mbar_wait(&hb_ready[s], 1);                        // second arrival of the tile: h_1 operand written
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem_base + 256 * s, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(w2 + kk * 32, 16, 1024),
+                              idq, kk != 0);
+                umma_commit(&q_full[s]);
+            };
             mbar_wait(w_full, 0);
-            uint32_t it = 0, hr = 0;                           // hr: h_ready completions consumed
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
-                for (int t = 0; t < P.nt; ++t, ++it) {
-                    const int b = it & 1;
-                    const uint32_t xt = smem_u32(smem + XB + b * TILE_BYTES);
-                    mbar_wait(&x_full[b], (it >> 1) & 1);
-                    mbar_wait(tmem_free, (it & 1) ^ 1);            // q of the previous iteration drained (passes at it = 0)
-                    if (t == 0) { mbar_wait(h_ready, hr & 1); ++hr; }   // h_0 of this tile is in the operand tile
-                    tc_fence_after();
+            for (int k = 0; k < n_my; ++k) {
+                const int s = k & 1, u = k >> 1;
+                const uint32_t xt = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_X);
+                const uint32_t ht = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_HT);
+                const uint32_t tm = tmem_base + 256 * s;
+                mbar_wait(&in_full[s], (uint32_t)(u & 1));
+                mbar_wait(&hb_ready[s], 0);                        // first arrival: h_0 operand written
+                mbar_wait(&tmem_free[s], (uint32_t)((u & 1) ^ 1));
+                tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {               // r|z : x . W_i{r,z}^T
-                        umma_bf16(tmem_base, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024),
-                                  id128, kk != 0);
-                    }
+                for (int kk = 0; kk < 4; ++kk)                     // r|z : x . W_i{r,z}^T
+                    umma_bf16(tm, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024), id128,
+                              kk != 0);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {               //       + h . W_h{r,z}^T
-                        umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024),
-                                  id128, 1);
-                    }
+                for (int kk = 0; kk < 4; ++kk)                     //       + h . W_h{r,z}^T
+                    umma_bf16(tm, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024), id128, 1);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {               // n, input part
-                        umma_bf16(tmem_base + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
-                                  umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
-                    }
+                for (int kk = 0; kk < 4; ++kk)                     // n, input part
+                    umma_bf16(tm + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
+                              umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {               // n, hidden part
-                        umma_bf16(tmem_base + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
-                                  umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
-                    }
-                    umma_commit(&x_empty[b]);
-                    umma_commit(gates_full);
-                    // fc2 on the new hidden state
-                    mbar_wait(h_ready, hr & 1); ++hr;
-                    tc_fence_after();
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        umma_bf16(tmem_base, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(w2 + kk * 32, 16, 1024),
-                                  idq, kk != 0);
-                    }
-                    umma_commit(q_full);
-                }
+                for (int kk = 0; kk < 4; ++kk)                     // n, hidden part
+                    umma_bf16(tm + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
+                              umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+                umma_commit(&gates_full[s]);
+                if (k > 0) fc2(k - 1);
+            }
+            if (n_my > 0) fc2(n_my - 1);
         }
     } else {
-        // ===== epilogue: gate math, hidden state update, q =====
-        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const uint32_t r = warp * 32 + lane;                      // tile row of an epilogue thread
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-            // initial hidden state: registers (fp32) + operand tile (bf16).  The MMAs of the previous tile have
-            // completed (its last q_full was waited for), so the operand tile may be overwritten.
-            float h[64];
-            const int64_t row = (int64_t)tile * TILE_ROWS + r;
+        // ===== epilogue of slot s: hidden state in, gate math, hidden state out, q, selection =====
+        const int s = warp >> 2, q4 = warp & 3;
+        uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
+        const uint32_t tlane = tmem_base + 256 * s + ((uint32_t)(q4 * 32) << 16);
+        const uint32_t r = q4 * 32 + lane;                        // tile row of this thread
+        uint8_t* hs = sl + S_HS;
+        for (int k = s; k < n_my; k += 2) {
+            const int u = k >> 1;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+            const int64_t row = tile * TILE_ROWS + r;
             const bool valid = row < P.R;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) h[j] = 0.f;
+            float h[64];
+            mbar_wait(&in_full[s], (uint32_t)(u & 1));
             if (valid && P.h0) {
 #pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4) {
-                    const float4 v = *reinterpret_cast<const float4*>(P.h0 + row * 64 + 4 * j4);
+                for (int j4 = 0; j4 < 16; ++j4) {                 // column 4 j4: tile j4 >> 3, 16-byte chunk j4 & 7
+                    const float4 v = *reinterpret_cast<const float4*>(hs + (j4 >> 3) * TILE_BYTES + sw128_offset(r, (uint32_t)(j4 & 7)));
                     h[4 * j4] = v.x; h[4 * j4 + 1] = v.y; h[4 * j4 + 2] = v.z; h[4 * j4 + 3] = v.w;
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) h[j] = 0.f;
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = h[16 * c + j];
-                store_row16(smem + HT, r, c, f);
-                if (P.h_ti) store_row16(P.h_ti + (int64_t)tile * TILE_BYTES, r, c, f);
+                store_row16(sl + S_HT, r, c, f);
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(h_ready);
-            for (int t = 0; t < P.nt; ++t, ++it) {
-                mbar_wait(gates_full, it & 1);
-                tc_fence_after();
-                uint8_t* hti = P.h_ti ? P.h_ti + ((int64_t)(t + 1) * P.n_tiles + tile) * TILE_BYTES : nullptr;
-                uint8_t* gti = P.g_ti ? P.g_ti + ((int64_t)t * P.n_tiles + tile) * 4 * TILE_BYTES : nullptr;
+            if (lane == 0) mbar_arrive(&hb_ready[s]);
+
+            mbar_wait(&gates_full[s], (uint32_t)(u & 1));
+            tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t ar[16], az[16], ain[16], ahn[16];
-                    tmem_ld_32x16(tlane + 16 * c, ar);
-                    tmem_ld_32x16(tlane + 64 + 16 * c, az);
-                    tmem_ld_32x16(tlane + 128 + 16 * c, ain);
-                    tmem_ld_32x16(tlane + 192 + 16 * c, ahn);
-                    tmem_wait_ld();
-                    float fr[16], fz[16], fn[16], fhn[16], fh[16];
+            for (int c = 0; c < 4; ++c) {
+                uint32_t ar[16], az[16], ain[16], ahn[16];
+                tmem_ld_32x16(tlane + 16 * c, ar);
+                tmem_ld_32x16(tlane + 64 + 16 * c, az);
+                tmem_ld_32x16(tlane + 128 + 16 * c, ain);
+                tmem_ld_32x16(tlane + 192 + 16 * c, ahn);
+                tmem_wait_ld();
+                float fh[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int jj = 16 * c + j;
-                        float rg = fast_sigmoid(__uint_as_float(ar[j]) + bias[jj]);
-                        float zg = fast_sigmoid(__uint_as_float(az[j]) + bias[64 + jj]);
-                        float hn = __uint_as_float(ahn[j]) + bias[192 + jj];
-                        float ng = fast_tanh(__uint_as_float(ain[j]) + bias[128 + jj] + rg * hn);
-                        float hv = ng + zg * (h[jj] - ng);
-                        h[jj] = hv;
-                        fr[j] = rg; fz[j] = zg; fn[j] = ng; fhn[j] = hn; fh[j] = hv;
-                    }
-                    store_row16(smem + HT, r, c, fh);
-                    if (valid) {
-                        if (hti) store_row16(hti, r, c, fh);
-                        if (gti) {
-                            store_row16(gti, r, c, fr);
-                            store_row16(gti + TILE_BYTES, r, c, fz);
-                            store_row16(gti + 2 * TILE_BYTES, r, c, fn);
-                            store_row16(gti + 3 * TILE_BYTES, r, c, fhn);
-                        }
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    const int jj = 16 * c + j;
+                    const float rg = fast_sigmoid(__uint_as_float(ar[j]) + bias[jj]);
+                    const float zg = fast_sigmoid(__uint_as_float(az[j]) + bias[64 + jj]);
+                    const float hn = __uint_as_float(ahn[j]) + bias[192 + jj];
+                    const float ng = fast_tanh(__uint_as_float(ain[j]) + bias[128 + jj] + rg * hn);
+                    const float hv = ng + zg * (h[jj] - ng);
+                    h[jj] = hv;
+                    fh[j] = hv;
                 }
-                tc_fence_before();
-                fence_proxy_async_smem();
+                store_row16(sl + S_HT, r, c, fh);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hb_ready[s]);
+            // new hidden state: own row into the (dead) h_0 staging row, then the warp writes its 32 rows out with
+            // coalesced 16-byte stores (512 contiguous bytes per instruction)
+            if (P.h_last) {
+#pragma unroll
+                for (int j4 = 0; j4 < 16; ++j4)
+                    *reinterpret_cast<float4*>(hs + (j4 >> 3) * TILE_BYTES + sw128_offset(r, (uint32_t)(j4 & 7))) =
+                        make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(h_ready);
-                if (valid && P.h_last && t == P.nt - 1) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 16; ++j4)
-                        *reinterpret_cast<float4*>(P.h_last + row * 64 + 4 * j4) =
-                            make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+                const int64_t trow0 = tile * TILE_ROWS;
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t rr = (uint32_t)(q4 * 32 + 2 * i + (lane >> 4));
+                    const int ch = lane & 15;
+                    if (trow0 + rr < P.R)
+                        *reinterpret_cast<float4*>(P.h_last + (trow0 + rr) * 64 + ch * 4) =
+                            *reinterpret_cast<const float4*>(hs + (ch >> 3) * TILE_BYTES + sw128_offset(rr, (uint32_t)(ch & 7)));
                 }
-                // q = fc2(h)
-                mbar_wait(q_full, it & 1);
-                tc_fence_after();
-                float* qo = P.q ? P.q + ((int64_t)t * P.R + row) * P.A : nullptr;
-                const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
-                const bool select = P.actions_out != nullptr && t == P.nt - 1 && valid;
-                const int32_t* av = nullptr;
-                if (select) {
+                __syncwarp();
+            }
+            // q = fc2(h)
+            mbar_wait(&q_full[s], (uint32_t)(u & 1));
+            tc_fence_after();
+            float* qo = P.q ? P.q + row * P.A : nullptr;
+            const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
+            const bool select = P.actions_out != nullptr && valid;
+            const int32_t* av = nullptr;
+            bool av_vec = true;
+            if (select) {
+                if (av_smem) av = reinterpret_cast<const int32_t*>(sl + S_AV) + r * P.A;
+                else {
                     const int64_t bb = (int64_t)((uint32_t)row / (uint32_t)P.N);
                     av = P.avail + bb * P.avail_sb + (row - bb * P.N) * P.A;
+                    av_vec = (P.A & 3) == 0 && (P.avail_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
                 }
-                const bool av_vec = (P.A & 3) == 0 && (P.avail_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
-                float best = -INFINITY;
-                int bidx = 0x7fffffff, cnt = 0;
-                unsigned long long okmask = 0ull;
-                for (int c0 = 0; c0 < A_pad; c0 += 16) {
-                    uint32_t aq[16];
-                    tmem_ld_32x16(tlane + c0, aq);
-                    tmem_wait_ld();
-                    if (valid) {
-                        float qv[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
-                        if (qo) {
-                            if (q_vec) {
-#pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4)
-                                    if (c0 + 4 * j4 < P.A)
-                                        *reinterpret_cast<float4*>(qo + c0 + 4 * j4) =
-                                            make_float4(qv[4 * j4], qv[4 * j4 + 1], qv[4 * j4 + 2], qv[4 * j4 + 3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (c0 + j < P.A) qo[c0 + j] = qv[j];
-                            }
-                        }
-                        if (select) {
-                            // this chunk's 16 avail flags: four 16-byte loads when the layout allows
-                            int avj[16];
-                            if (av_vec && c0 + 16 <= P.A) {
-#pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) {
-                                    const int4 w4 = __ldg(reinterpret_cast<const int4*>(av + c0) + j4);
-                                    avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? __ldg(av + c0 + j) : 0;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int a = c0 + j;
-                                if (a < P.A) {
-                                    const bool ok = avj[j] != 0;
-                                    cnt += ok ? 1 : 0;
-                                    okmask |= (unsigned long long)(ok ? 1 : 0) << a;
-                                    const float v = ok ? qv[j] : -INFINITY;
-                                    if (v > best) { best = v; bidx = a; }          // ascending a, strict >: lowest index wins
-                                }
-                            }
-                        }
-                    }
-                }
-                if (select) {
-                    if (bidx == 0x7fffffff) bidx = 0;                              // all -inf / NaN: first index
-                    int ridx;
-                    float uu;
-                    if (P.expo) {
-                        // reference arithmetic with injected draws: argmax_a (avail[a] / cnt) / Exp(1)[a]
-                        const float prob = __fdiv_rn(1.0f, (float)cnt);
-                        float rbest = -INFINITY;
-                        ridx = 0x7fffffff;
-                        for (int a = 0; a < P.A; ++a) {
-                            const float ratio = __fdiv_rn(((okmask >> a) & 1ull) ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
-                            if (ratio > rbest) { rbest = ratio; ridx = a; }
-                        }
-                        if (ridx == 0x7fffffff) ridx = 0;
-                        uu = __ldg(P.u + row);
-                    } else {
-                        // Philox mode (same arithmetic as epsilon_greedy_kernel): word x -> epsilon test, word y -> rank
-                        const uint4 r0 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
-                                                                     ((uint32_t)(row >> 32) << 16)),
-                                                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-                        uu = 1.0f - gf_u01(r0.x);                  // [0, 1)
-                        int k = (int)((1.0f - gf_u01(r0.y)) * (float)cnt);
-                        if (k >= cnt) k = cnt - 1;
-                        ridx = 0;
-                        int seen = 0;
-                        for (int a = 0; a < P.A; ++a) {
-                            const bool ok = (okmask >> a) & 1ull;
-                            if (ok && seen == k) ridx = a;
-                            seen += ok ? 1 : 0;
-                        }
-                    }
-                    int pick = (cnt > 0 && uu < P.epsilon) ? ridx : bidx;
-                    if (pick >= P.A) pick = 0;
-                    P.actions_out[row] = pick;
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_free);
             }
+            float best = -INFINITY;
+            int bidx = 0x7fffffff, cnt = 0;
+            unsigned long long okmask = 0ull;
+            for (int c0 = 0; c0 < A_pad; c0 += 16) {
+                uint32_t aq[16];
+                tmem_ld_32x16(tlane + c0, aq);
+                tmem_wait_ld();
+                if (valid) {
+                    float qv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
+                    if (qo) {
+                        if (q_vec) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                if (c0 + 4 * j4 < P.A)
+                                    *reinterpret_cast<float4*>(qo + c0 + 4 * j4) =
+                                        make_float4(qv[4 * j4], qv[4 * j4 + 1], qv[4 * j4 + 2], qv[4 * j4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < P.A) qo[c0 + j] = qv[j];
+                        }
+                    }
+                    if (select) {
+                        int avj[16];
+                        if (av_vec && c0 + 16 <= P.A) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const int4 w4 = *(reinterpret_cast<const int4*>(av + c0) + j4);
+                                avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? av[c0 + j] : 0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int a = c0 + j;
+                            if (a < P.A) {
+                                const bool ok = avj[j] != 0;
+                                cnt += ok ? 1 : 0;
+                                okmask |= (unsigned long long)(ok ? 1 : 0) << a;
+                                const float v = ok ? qv[j] : -INFINITY;
+                                if (v > best) { best = v; bidx = a; }          // ascending a, strict >: lowest index wins
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_free[s]);
+            if (select) {
+                if (bidx == 0x7fffffff) bidx = 0;                              // all -inf / NaN: first index
+                int ridx;
+                float uu;
+                if (P.expo) {
+                    // reference arithmetic with injected draws: argmax_a (avail[a] / cnt) / Exp(1)[a]
+                    const float prob = __fdiv_rn(1.0f, (float)cnt);
+                    float rbest = -INFINITY;
+                    ridx = 0x7fffffff;
+                    for (int a = 0; a < P.A; ++a) {
+                        const float ratio = __fdiv_rn(((okmask >> a) & 1ull) ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
+                        if (ratio > rbest) { rbest = ratio; ridx = a; }
+                    }
+                    if (ridx == 0x7fffffff) ridx = 0;
+                    uu = __ldg(P.u + row);
+                } else {
+                    // Philox mode (same arithmetic as epsilon_greedy_kernel): word x -> epsilon test, word y -> rank
+                    const uint4 r0 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
+                                                                 ((uint32_t)(row >> 32) << 16)),
+                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                    uu = 1.0f - gf_u01(r0.x);                  // [0, 1)
+                    int kq = (int)((1.0f - gf_u01(r0.y)) * (float)cnt);
+                    if (kq >= cnt) kq = cnt - 1;
+                    // the kq-th set bit of okmask
+                    unsigned long long m = okmask;
+                    for (int i = 0; i < kq; ++i) m &= m - 1;
+                    ridx = m ? __ffsll((long long)m) - 1 : 0;
+                }
+                int pick = (cnt > 0 && uu < P.epsilon) ? ridx : bidx;
+                if (pick >= P.A) pick = 0;
+                P.actions_out[row] = pick;
+            }
+            // the slot's buffers may be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_free[s]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -632,10 +680,42 @@ __global__ void ti_zero_pad_kernel(uint8_t* buf, int n_t, int n_tiles, int64_t R
 }  // namespace tc
 
 int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
-    PMB_CUDA(cudaFuncSetAttribute(tc::gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::gf::SMEM_BYTES));
-    const int grid = P.n_tiles < 2 * sm_count() ? P.n_tiles : 2 * sm_count();
-    tc::gru_fwd_tc_kernel<<<grid, tc::gf::THREADS, tc::gf::SMEM_BYTES, s>>>(P);
-    PMB_LAUNCH_CHECK("gru_fwd_tc_kernel");
+    if (P.nt != 1 || P.h_ti || P.g_ti) { set_error("tc_gru_fwd: the rollout kernel does one step and keeps no stash"); return PMB_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(P.h0) & 15) || (reinterpret_cast<uintptr_t>(P.h_last) & 15)) {
+        set_error("tc_gru_fwd: hidden state must be 16-byte aligned");
+        return PMB_ERR_INVALID;
+    }
+    // avail rows are staged through shared memory by bulk copies when they fit and are 16-byte granular
+    const int av_smem = P.actions_out && P.avail && (P.A & 3) == 0 && 128 * P.A * 4 <= tc::ro::AV_BYTES && (P.avail_sb & 3) == 0 &&
+                        ((int64_t)P.N * P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
+    // tensor map of the fp32 hidden state [R][64]: boxes of 128 rows x 32 columns, 128-byte swizzle, zero fill beyond R
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (P.h0) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            PMB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("tc_gru_fwd: cuTensorMapEncodeTiled not available"); return PMB_ERR_CUDA; }
+            encode = reinterpret_cast<EncodeFn>(fn);
+        }
+        const cuuint64_t gdim[2] = {64, (cuuint64_t)P.R};
+        const cuuint64_t gstride[1] = {256};
+        const cuuint32_t box[2] = {32, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P.h0), gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { set_error("tc_gru_fwd: cuTensorMapEncodeTiled failed"); return PMB_ERR_CUDA; }
+    }
+    PMB_CUDA(cudaFuncSetAttribute(tc::gru_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ro::SMEM_BYTES));
+    const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
+    tc::gru_rollout_kernel<<<grid, tc::ro::THREADS, tc::ro::SMEM_BYTES, s>>>(P, av_smem, tmap);
+    PMB_LAUNCH_CHECK("gru_rollout_kernel");
     return PMB_OK;
 }
 
