@@ -89,8 +89,9 @@ __device__ __forceinline__ void load_row16(const uint8_t* tile, uint32_t r, int 
 // coalesced 16-byte stores.  Measured on the way: per-thread row-strided global accesses with 2 CTAs per SM and nothing
 // prefetched (first version) 176 us for 16384 x 27 rows; one 256-byte bulk copy per row 320 us (the copy engine's
 // per-operation cost); 16-byte cp.async by one loader warp 244 us (too few bytes in flight per warp).
-// Warps 0-3 / 4-7: epilogue of slot 0 / 1 (one row per thread, hidden state in 64 fp32 registers), warp 8: MMA issuer
-// (gates of tile k, then fc2 of tile k-1), warp 9: loader (all lanes issue row copies).
+// Warps 0-7 / 8-15: epilogue of slot 0 / 1 (TWO threads per row, 32 hidden columns each in fp32 registers: with one
+// thread per row the 2 epilogue warps per scheduler could not hide the gate-math latencies; the q / selection part of a
+// row is done by its column-half-0 thread), warp 16: MMA issuer (gates of tile k, then fc2 of tile k-1), warp 17: loader.
 namespace ro {
 constexpr int WIH = 0, WHH = 24576, W2 = 49152;
 constexpr int SLOT0 = 57344;
@@ -101,7 +102,8 @@ constexpr int BIAS = SLOT0 + 2 * SLOT_BYTES;
 constexpr int BIAS_FLOATS = 128 + 64 + 64 + 64;               // brz | bin | bhn | b2
 constexpr int BARS = BIAS + BIAS_FLOATS * 4;
 constexpr int SMEM_BYTES = BARS + 128;
-constexpr int THREADS = 320;
+constexpr int THREADS = 576;
+constexpr int MMA_W = 16, LOAD_W = 17;
 static_assert(SLOT_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "rollout kernel shared memory");
 }  // namespace ro
 
@@ -126,12 +128,12 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1); mbar_init(&slot_free[i], 4); mbar_init(&hb_ready[i], 4);
+            mbar_init(&in_full[i], 1); mbar_init(&slot_free[i], 8); mbar_init(&hb_ready[i], 8);
             mbar_init(&gates_full[i], 1); mbar_init(&q_full[i], 1); mbar_init(&tmem_free[i], 4);
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (warp == MMA_W) tmem_alloc(tmem_slot, 512);
     for (int i = threadIdx.x; i < 128; i += THREADS) bias[i] = P.b_ih[i] + P.b_hh[i];
     for (int i = threadIdx.x; i < 64; i += THREADS) {
         bias[128 + i] = P.b_ih[128 + i];
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-    if (warp == 9) {
+    if (warp == LOAD_W) {
         // ===== loader =====
         if (lane == 0) {
             mbar_arrive_expect_tx(w_full, 24576 + 24576 + 8192);
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == MMA_W) {
         // ===== MMA issuer: gates of tile k, then fc2 of tile k-1 (its new hidden state is ready by then) =====
         if (lane == 0) {
             const uint32_t wih = smem_u32(smem + WIH), whh = smem_u32(smem + WHH), w2 = smem_u32(smem + W2);
@@ -200,7 +202,6 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
             auto fc2 = [&](int j) {
                 const int s = j & 1;
                 const uint32_t ht = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_HT);
-                mbar_wait(&hb_ready[s], 1);                        // second arrival of the tile: h_1 operand written
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
@@ -208,15 +209,11 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                               idq, kk != 0);
                 umma_commit(&q_full[s]);
             };
-            mbar_wait(w_full, 0);
-            for (int k = 0; k < n_my; ++k) {
-                const int s = k & 1, u = k >> 1;
+            auto gates = [&](int k) {
+                const int s = k & 1;
                 const uint32_t xt = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_X);
                 const uint32_t ht = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_HT);
                 const uint32_t tm = tmem_base + 256 * s;
-                mbar_wait(&in_full[s], (uint32_t)(u & 1));
-                mbar_wait(&hb_ready[s], 0);                        // first arrival: h_0 operand written
-                mbar_wait(&tmem_free[s], (uint32_t)((u & 1) ^ 1));
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)                     // r|z : x . W_i{r,z}^T
@@ -234,40 +231,59 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                     umma_bf16(tm + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
                               umma_desc_sw128(whh + 16384 + kk * 32, 16, 1024), id64, kk != 0);
                 umma_commit(&gates_full[s]);
-                if (k > 0) fc2(k - 1);
+            };
+            mbar_wait(w_full, 0);
+            // Whatever is ready is issued: the gates of the next tile (inputs landed, h_0 operand written, accumulators
+            // drained) or fc2 of the oldest tile whose new hidden state is written.  A fixed order (gates k, fc2 k-1) made
+            // fc2 of one tile wait for the LOADS of the next one.  The tests are ordered so that no parity test can see a
+            // stale phase: in_full(u) implies the slot's previous use is over; fc2 is only tried after its tile's gates.
+            int kg = 0, kf = 0;
+            while (kf < n_my) {
+                if (kg < n_my) {
+                    const int s = kg & 1, u = kg >> 1;
+                    if (mbar_try_wait(&in_full[s], (uint32_t)(u & 1)) && mbar_try_wait(&hb_ready[s], 0) &&
+                        mbar_try_wait(&tmem_free[s], (uint32_t)((u & 1) ^ 1))) {
+                        gates(kg);
+                        ++kg;
+                    }
+                }
+                if (kf < kg && mbar_try_wait(&hb_ready[kf & 1], 1)) {
+                    fc2(kf);
+                    ++kf;
+                }
             }
-            if (n_my > 0) fc2(n_my - 1);
         }
     } else {
         // ===== epilogue of slot s: hidden state in, gate math, hidden state out, q, selection =====
-        const int s = warp >> 2, q4 = warp & 3;
+        const int s = warp >> 3, q4 = warp & 3, ch = (warp >> 2) & 1;
         uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
         const uint32_t tlane = tmem_base + 256 * s + ((uint32_t)(q4 * 32) << 16);
-        const uint32_t r = q4 * 32 + lane;                        // tile row of this thread
-        uint8_t* hs = sl + S_HS;
+        const uint32_t r = q4 * 32 + lane;                        // tile row of this thread; it owns columns 32 ch .. +31
+        uint8_t* hs = sl + S_HS + ch * TILE_BYTES;                // the fp32 staging tile of this column half
+        const float* bias_c = bias + 32 * ch;
         for (int k = s; k < n_my; k += 2) {
             const int u = k >> 1;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
             const int64_t row = tile * TILE_ROWS + r;
             const bool valid = row < P.R;
-            float h[64];
+            float h[32];
             mbar_wait(&in_full[s], (uint32_t)(u & 1));
             if (valid && P.h0) {
 #pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4) {                 // column 4 j4: tile j4 >> 3, 16-byte chunk j4 & 7
-                    const float4 v = *reinterpret_cast<const float4*>(hs + (j4 >> 3) * TILE_BYTES + sw128_offset(r, (uint32_t)(j4 & 7)));
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 v = *reinterpret_cast<const float4*>(hs + sw128_offset(r, (uint32_t)j4));
                     h[4 * j4] = v.x; h[4 * j4 + 1] = v.y; h[4 * j4 + 2] = v.z; h[4 * j4 + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) h[j] = 0.f;
+                for (int j = 0; j < 32; ++j) h[j] = 0.f;
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = h[16 * c + j];
-                store_row16(sl + S_HT, r, c, f);
+                store_row16(sl + S_HT, r, 2 * ch + c, f);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -276,49 +292,61 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
             mbar_wait(&gates_full[s], (uint32_t)(u & 1));
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t ar[16], az[16], ain[16], ahn[16];
-                tmem_ld_32x16(tlane + 16 * c, ar);
-                tmem_ld_32x16(tlane + 64 + 16 * c, az);
-                tmem_ld_32x16(tlane + 128 + 16 * c, ain);
-                tmem_ld_32x16(tlane + 192 + 16 * c, ahn);
+                tmem_ld_32x16(tlane + 32 * ch + 16 * c, ar);
+                tmem_ld_32x16(tlane + 64 + 32 * ch + 16 * c, az);
+                tmem_ld_32x16(tlane + 128 + 32 * ch + 16 * c, ain);
+                tmem_ld_32x16(tlane + 192 + 32 * ch + 16 * c, ahn);
+                float br[16], bz[16], bn[16], bh[16];                 // 16-byte loads of the bias table (same address in all lanes)
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    *reinterpret_cast<float4*>(&br[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 16 * c + 4 * j4);
+                    *reinterpret_cast<float4*>(&bz[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 64 + 16 * c + 4 * j4);
+                    *reinterpret_cast<float4*>(&bn[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 128 + 16 * c + 4 * j4);
+                    *reinterpret_cast<float4*>(&bh[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 192 + 16 * c + 4 * j4);
+                }
                 tmem_wait_ld();
                 float fh[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int jj = 16 * c + j;
-                    const float rg = fast_sigmoid(__uint_as_float(ar[j]) + bias[jj]);
-                    const float zg = fast_sigmoid(__uint_as_float(az[j]) + bias[64 + jj]);
-                    const float hn = __uint_as_float(ahn[j]) + bias[192 + jj];
-                    const float ng = fast_tanh(__uint_as_float(ain[j]) + bias[128 + jj] + rg * hn);
+                    const float rg = fast_sigmoid(__uint_as_float(ar[j]) + br[j]);
+                    const float zg = fast_sigmoid(__uint_as_float(az[j]) + bz[j]);
+                    const float hn = __uint_as_float(ahn[j]) + bh[j];
+                    const float ng = fast_tanh(__uint_as_float(ain[j]) + bn[j] + rg * hn);
                     const float hv = ng + zg * (h[jj] - ng);
                     h[jj] = hv;
                     fh[j] = hv;
                 }
-                store_row16(sl + S_HT, r, c, fh);
+                store_row16(sl + S_HT, r, 2 * ch + c, fh);
             }
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hb_ready[s]);
-            // new hidden state: own row into the (dead) h_0 staging row, then the warp writes its 32 rows out with
-            // coalesced 16-byte stores (512 contiguous bytes per instruction)
+            // new hidden state: own half row into the (dead) h_0 staging tile, then the warp writes its 32 half rows out
+            // with coalesced 16-byte stores (four 128-byte segments per instruction)
             if (P.h_last) {
 #pragma unroll
-                for (int j4 = 0; j4 < 16; ++j4)
-                    *reinterpret_cast<float4*>(hs + (j4 >> 3) * TILE_BYTES + sw128_offset(r, (uint32_t)(j4 & 7))) =
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(hs + sw128_offset(r, (uint32_t)j4)) =
                         make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
                 __syncwarp();
                 const int64_t trow0 = tile * TILE_ROWS;
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t rr = (uint32_t)(q4 * 32 + 2 * i + (lane >> 4));
-                    const int ch = lane & 15;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t rr = (uint32_t)(q4 * 32 + 4 * i + (lane >> 3));
+                    const int cj = lane & 7;
                     if (trow0 + rr < P.R)
-                        *reinterpret_cast<float4*>(P.h_last + (trow0 + rr) * 64 + ch * 4) =
-                            *reinterpret_cast<const float4*>(hs + (ch >> 3) * TILE_BYTES + sw128_offset(rr, (uint32_t)(ch & 7)));
+                        *reinterpret_cast<float4*>(P.h_last + (trow0 + rr) * 64 + 32 * ch + cj * 4) =
+                            *reinterpret_cast<const float4*>(hs + sw128_offset(rr, (uint32_t)cj));
                 }
                 __syncwarp();
+            }
+            if (ch != 0) {                                        // q and the selection belong to the column-half-0 thread
+                if (lane == 0) mbar_arrive(&slot_free[s]);
+                continue;
             }
             // q = fc2(h)
             mbar_wait(&q_full[s], (uint32_t)(u & 1));
@@ -428,7 +456,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == MMA_W) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
