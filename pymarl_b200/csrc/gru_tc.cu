@@ -101,9 +101,9 @@ constexpr int SLOT_BYTES = S_AV + AV_BYTES + 2048;            // 86016 = 84 KB (
 constexpr int BIAS = SLOT0 + 2 * SLOT_BYTES;
 constexpr int BIAS_FLOATS = 128 + 64 + 64 + 64;               // brz | bin | bhn | b2
 constexpr int BARS = BIAS + BIAS_FLOATS * 4;
-constexpr int SMEM_BYTES = BARS + 128;
-constexpr int THREADS = 576;
-constexpr int MMA_W = 16, LOAD_W = 17;
+constexpr int SMEM_BYTES = BARS + 256;                      // 17 barriers + the TMEM slot
+constexpr int THREADS = 608;
+constexpr int MMA_W = 16, LOAD_W = 17, AV_W = 18;
 static_assert(SLOT_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "rollout kernel shared memory");
 }  // namespace ro
 
@@ -115,20 +115,23 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     float* bias = reinterpret_cast<float*>(smem + BIAS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
     uint64_t* w_full = bars;
-    uint64_t* in_full = bars + 1;        // [2] x, h0 rows, avail rows landed
-    uint64_t* slot_free = bars + 3;      // [2] every reader of the slot's buffers is done (4 epilogue warps)
+    uint64_t* in_full = bars + 1;        // [2] x tile and h_0 tiles landed
+    uint64_t* xh_free = bars + 3;        // [2] x / hidden-state staging of the slot may be refilled (8 epilogue warps)
     uint64_t* hb_ready = bars + 5;       // [2] bf16 h operand written: arrival pair per tile (h_0, then h_1)
     uint64_t* gates_full = bars + 7;     // [2]
     uint64_t* q_full = bars + 9;         // [2]
     uint64_t* tmem_free = bars + 11;     // [2] q drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* av_full = bars + 13;       // [2] avail rows landed
+    uint64_t* av_free = bars + 15;       // [2] selection done with the avail rows (4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A_pad = (P.A + 15) & ~15;
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 1); mbar_init(&slot_free[i], 8); mbar_init(&hb_ready[i], 8);
+            mbar_init(&in_full[i], 1); mbar_init(&xh_free[i], 8); mbar_init(&hb_ready[i], 8);
+            mbar_init(&av_full[i], 1); mbar_init(&av_free[i], 4);
             mbar_init(&gates_full[i], 1); mbar_init(&q_full[i], 1); mbar_init(&tmem_free[i], 4);
         }
         fence_barrier_init();
@@ -154,16 +157,15 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
             bulk_copy_g2s(smem + WHH, P.w_hh_img, 24576, w_full);
             bulk_copy_g2s(smem + W2, P.w2_img, 8192, w_full);
         }
-        for (int k = 0; k < n_my; ++k) {
-            const int s = k & 1, u = k >> 1;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-            uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
-            mbar_wait(&slot_free[s], (uint32_t)((u & 1) ^ 1));
-            const int64_t row0 = tile * TILE_ROWS;
-            const int rows_here = (int)(P.R - row0 < TILE_ROWS ? P.R - row0 : TILE_ROWS);
-            if (lane == 0) {
-                const uint32_t bytes = TILE_BYTES + (P.h0 ? 2 * TILE_BYTES : 0) + (av_smem ? rows_here * P.A * 4 : 0);
-                mbar_arrive_expect_tx(&in_full[s], bytes);
+        // the staging of a slot is released in two steps (x / hidden state after the gate math, avail after the selection),
+        // so the next tile's big copies are in flight while the current one still selects; avail has its own warp
+        if (lane == 0) {
+            for (int k = 0; k < n_my; ++k) {
+                const int s = k & 1, u = k >> 1;
+                const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+                uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
+                mbar_wait(&xh_free[s], (uint32_t)((u & 1) ^ 1));
+                mbar_arrive_expect_tx(&in_full[s], TILE_BYTES + (P.h0 ? 2 * TILE_BYTES : 0));
                 bulk_copy_g2s(sl + S_X, P.x_ti + tile * TILE_BYTES, TILE_BYTES, &in_full[s]);
                 if (P.h0) {
 #pragma unroll
@@ -171,25 +173,30 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                         asm volatile(
                             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                                 smem_u32(sl + S_HS + hf * TILE_BYTES)),
-                            "l"(reinterpret_cast<uint64_t>(&tmap_h0)), "r"(32 * hf), "r"((int)row0), "r"(smem_u32(&in_full[s]))
+                            "l"(reinterpret_cast<uint64_t>(&tmap_h0)), "r"(32 * hf), "r"((int)(tile * TILE_ROWS)),
+                            "r"(smem_u32(&in_full[s]))
                             : "memory");
                 }
             }
-            __syncwarp();
-            if (av_smem) {
-                // one copy per env the tile touches (an env's N x A block is contiguous; the batch stride is free)
+        }
+    } else if (warp == AV_W) {
+        // ===== avail loader: one copy per env the tile touches (an env's N x A block is contiguous; the batch stride is free) =====
+        if (av_smem) {
+            for (int k = 0; k < n_my; ++k) {
+                const int s = k & 1, u = k >> 1;
+                const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+                uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
+                const int64_t row0 = tile * TILE_ROWS;
+                const int rows_here = (int)(P.R - row0 < TILE_ROWS ? P.R - row0 : TILE_ROWS);
+                mbar_wait(&av_free[s], (uint32_t)((u & 1) ^ 1));
+                if (lane == 0) mbar_arrive_expect_tx(&av_full[s], (uint32_t)(rows_here * P.A * 4));
+                __syncwarp();
                 const int64_t e0 = (int64_t)((uint32_t)row0 / (uint32_t)P.N);
-                const int64_t e = e0 + lane;
-                const int64_t ra = e * P.N > row0 ? e * P.N : row0;                          // first row of env e in the tile
-                const int64_t rb = (e + 1) * P.N < row0 + rows_here ? (e + 1) * P.N : row0 + rows_here;
-                if (ra < rb)
+                for (int64_t e = e0 + lane; e * P.N < row0 + rows_here; e += 32) {
+                    const int64_t ra = e * P.N > row0 ? e * P.N : row0;                  // rows of env e inside the tile
+                    const int64_t rb = (e + 1) * P.N < row0 + rows_here ? (e + 1) * P.N : row0 + rows_here;
                     bulk_copy_g2s(sl + S_AV + (ra - row0) * P.A * 4, P.avail + e * P.avail_sb + (ra - e * P.N) * P.A,
-                                  (uint32_t)((rb - ra) * P.A * 4), &in_full[s]);
-                // (128 rows span at most 32 envs as long as N >= 4; smaller N: loop)
-                for (int64_t e2 = e + 32; e2 * P.N < row0 + rows_here; e2 += 32) {
-                    const int64_t ra2 = e2 * P.N, rb2 = (e2 + 1) * P.N < row0 + rows_here ? (e2 + 1) * P.N : row0 + rows_here;
-                    bulk_copy_g2s(sl + S_AV + (ra2 - row0) * P.A * 4, P.avail + e2 * P.avail_sb, (uint32_t)((rb2 - ra2) * P.A * 4),
-                                  &in_full[s]);
+                                  (uint32_t)((rb - ra) * P.A * 4), &av_full[s]);
                 }
             }
         }
@@ -344,18 +351,18 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                 }
                 __syncwarp();
             }
-            if (ch != 0) {                                        // q and the selection belong to the column-half-0 thread
-                if (lane == 0) mbar_arrive(&slot_free[s]);
-                continue;
-            }
-            // q = fc2(h)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xh_free[s]);              // gate MMAs complete, staging read: x / h tiles may be refilled
+            // q = fc2(h).  (Both halves wait: the next tile's h_0 operand must not overwrite HT under the fc2 MMAs.)
             mbar_wait(&q_full[s], (uint32_t)(u & 1));
+            if (ch != 0) continue;                                // q and the selection belong to the column-half-0 thread
             tc_fence_after();
             float* qo = P.q ? P.q + row * P.A : nullptr;
             const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
             const bool select = P.actions_out != nullptr && valid;
             const int32_t* av = nullptr;
             bool av_vec = true;
+            if (av_smem) mbar_wait(&av_full[s], (uint32_t)(u & 1));
             if (select) {
                 if (av_smem) av = reinterpret_cast<const int32_t*>(sl + S_AV) + r * P.A;
                 else {
@@ -449,9 +456,8 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                 if (pick >= P.A) pick = 0;
                 P.actions_out[row] = pick;
             }
-            // the slot's buffers may be refilled
             __syncwarp();
-            if (lane == 0) mbar_arrive(&slot_free[s]);
+            if (lane == 0) mbar_arrive(&av_free[s]);
         }
     }
     tc_fence_before();
