@@ -278,12 +278,11 @@ int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, co
 
 // GRU / fc2 weight images of one agent: [w_ih 24 KB | w_hh 24 KB | fc2 8 KB] (bf16, K-major, 128B swizzle)
 int pack_gru_images(const pmb_dims* d, const AgentParams& ap, char* base, cudaStream_t s) {
-    const float* p1[1] = {ap.w_ih}; const float* p2[1] = {ap.w_hh}; const float* p3[2] = {ap.fc2_w, nullptr};
-    int r1[1] = {192}, l1[1] = {64}, r3[2] = {d->A, 64 - d->A}, l3[2] = {64, 64};
-    int e;
-    if ((e = tc_pack_w(p1, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base), s))) return e;
-    if ((e = tc_pack_w(p2, r1, l1, 1, 64, reinterpret_cast<__nv_bfloat16*>(base + 24576), s))) return e;
-    return tc_pack_w(p3, r3, l3, 2, 64, reinterpret_cast<__nv_bfloat16*>(base + 49152), s);
+    // ONE launch: rnn.weight_ih (192 rows) | rnn.weight_hh (192) | fc2.weight (A rows, zero rows up to 64) stacked into one
+    // [448 x 64] image = the three images at byte offsets 0 / 24576 / 49152
+    const float* p[4] = {ap.w_ih, ap.w_hh, ap.fc2_w, nullptr};
+    int r[4] = {192, 192, d->A, 64 - d->A}, l[4] = {64, 64, 64, 64};
+    return tc_pack_w(p, r, l, 4, 64, reinterpret_cast<__nv_bfloat16*>(base), s);
 }
 
 bool rollout_tc_ok(const pmb_dims* d) {
@@ -520,7 +519,8 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
         uint8_t* x_ti = reinterpret_cast<uint8_t*>(base);
         char* gru_img = base + align_up((int64_t)n_tiles * 16384, 256);
         void* fc1_scr = gru_img + 65536;
-        if ((rc = tc_ti_zero_pad(x_ti, 1, n_tiles, R, s))) return rc;
+        // (no zeroing of the padding rows of the last x tile: tile rows are independent in every MMA of this path and the
+        // rollout kernel neither stores nor selects for rows >= R)
         if ((rc = tc_fc1_fwd_both(d, b, t, 1, ap, ap, reinterpret_cast<float*>(x_ti), nullptr, 1, nullptr, nullptr, fc1_scr,
                                   align_up(tc_fc1_scratch_bytes(d), 256), s))) return rc;
         if ((rc = pack_gru_images(d, ap, gru_img, s))) return rc;
