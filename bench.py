@@ -526,7 +526,9 @@ def rollout_bench(a):
             out.copy_(acts, non_blocking=True)
             th.cuda.synchronize()
         dt = (time.perf_counter() - t0) / a.e2e_steps
-        h2d = sum(host[k][:, :2].numel() * host[k].element_size() for k in ("obs", "actions", "avail_actions", "filled"))
+        # obs / avail_actions: the step itself; actions / filled: the step and the one before (last-action input)
+        h2d = sum(host[k][:, :1].numel() * host[k].element_size() for k in ("obs", "avail_actions")) + \
+            sum(host[k][:, :2].numel() * host[k].element_size() for k in ("actions", "filled"))
         e2e = {"value": world * envs * N / dt, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": envs * N * 8,
                "ms_per_step": dt * 1e3, "steps": a.e2e_steps}
     cpu = None

@@ -193,21 +193,34 @@ _FIELD_DTYPES = {"obs": th.float32, "state": th.float32, "actions": th.int64, "a
                  "reward": th.float32, "terminated": th.uint8, "filled": th.int64}
 
 
-def h2d_time_slice(t, lo, hi, dev):
+def h2d_time_slice(t, lo, hi, dev, lead=0):
     """``t[:, lo:hi]`` of a host tensor [B, T, ...] as a dense device tensor, copied with ONE strided
-    cudaMemcpy2DAsync (no contiguous host temporary).  Falls back to torch for exotic layouts."""
+    cudaMemcpy2DAsync (no contiguous host temporary).  Falls back to torch for exotic layouts.
+
+    ``lead`` > 0 (single timestep only): the result is presented as a ``[B, lead + 1, ...]`` view whose LAST time
+    index holds the copied step (batch stride = time stride = one step; the earlier time indices alias other rows
+    and must not be read).  This lets a kernel that addresses every field with one common time index read a field
+    of which only the current step was transferred next to fields that also carry the previous step."""
     import torch as th
     B, T = t.shape[0], t.shape[1]
     inner = 1
     for s in t.shape[2:]:
         inner *= s
+    assert lead == 0 or hi - lo == 1
     if t.is_cuda or t.dim() < 2 or not t[0].is_contiguous() or t.stride(0) != T * inner or B == 0:
-        return t[:, lo:hi].to(dev, non_blocking=True)
-    out = th.empty((B, hi - lo) + tuple(t.shape[2:]), dtype=t.dtype, device=dev)
-    es = t.element_size()
-    check(lib().pmb_h2d_rows(ptr(out), C.c_void_p(t.data_ptr() + lo * inner * es), B, (hi - lo) * inner * es,
-                             T * inner * es, stream_ptr(dev)), "pmb_h2d_rows")
-    return out
+        if lead:
+            buf = th.empty((B + lead, 1) + tuple(t.shape[2:]), dtype=t.dtype, device=dev)
+            buf[lead:].copy_(t[:, lo:hi], non_blocking=True)
+        else:
+            return t[:, lo:hi].to(dev, non_blocking=True)
+    else:
+        buf = th.empty((B + lead, hi - lo) + tuple(t.shape[2:]), dtype=t.dtype, device=dev)
+        es = t.element_size()
+        check(lib().pmb_h2d_rows(C.c_void_p(buf.data_ptr() + lead * inner * es), C.c_void_p(t.data_ptr() + lo * inner * es), B,
+                                 (hi - lo) * inner * es, T * inner * es, stream_ptr(dev)), "pmb_h2d_rows")
+        if not lead:
+            return buf
+    return th.as_strided(buf, (B, lead + 1) + tuple(t.shape[2:]), (inner, inner) + tuple(buf.stride()[2:]))
 
 
 def gather_episodes(src_tensors, ep_ids, n_src):

@@ -59,9 +59,13 @@ class BasicMAC:
                 fields[k] = ep_batch[k]
             t_local, T_local = t, ep_batch["obs"].shape[1]
         else:
+            # actions / filled: steps t-1 and t (the last-action input); obs / avail_actions: step t only, presented
+            # at the same local time index (they are 99 % of the bytes)
             lo = max(t - 1, 0)
-            for k in ("obs", "actions", "avail_actions", "filled"):
+            for k in ("actions", "filled"):
                 fields[k] = _lib.h2d_time_slice(ep_batch[k], lo, t + 1, dev)
+            for k in ("obs", "avail_actions"):
+                fields[k] = _lib.h2d_time_slice(ep_batch[k], t, t + 1, dev, lead=t - lo)
             t_local, T_local = t - lo, t + 1 - lo
         zero = th.zeros(1, dtype=th.float32, device=dev)
         fields.update(state=zero, reward=zero, terminated=zero.to(th.uint8))
