@@ -881,22 +881,34 @@ __global__ void __launch_bounds__(b2::THREADS, 1) gru_bwd2_kernel(GruBwd2Params 
     }
 }
 
-// rnn gradients from the per-tile partials of gru_bwd2, summed in tile order
-__global__ void gru_bwd2_reduce_kernel(const float* __restrict__ partial, int n_part, float* __restrict__ w_ih,
-                                       float* __restrict__ w_hh, float* __restrict__ b_ih, float* __restrict__ b_hh) {
+// rnn gradients from the per-tile partials of gru_bwd2.  Block = 32 outputs x 8 slices of the tile range; fixed summation
+// order (slice-local ascending, then slices ascending): deterministic
+__global__ void __launch_bounds__(256) gru_bwd2_reduce_kernel(const float* __restrict__ partial, int n_part, float* __restrict__ w_ih,
+                                                              float* __restrict__ w_hh, float* __restrict__ b_ih,
+                                                              float* __restrict__ b_hh) {
     constexpr int PF = b2::PARTIAL_FLOATS;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= PF) return;
+    __shared__ float red[8][33];
+    const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + o;
+    const int per = (n_part + 7) / 8;
+    const int c0 = sl * per, c1 = c0 + per < n_part ? c0 + per : n_part;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= n_part; c += 4) {
-        s0 += partial[(int64_t)c * PF + i];
-        s1 += partial[(int64_t)(c + 1) * PF + i];
-        s2 += partial[(int64_t)(c + 2) * PF + i];
-        s3 += partial[(int64_t)(c + 3) * PF + i];
+    if (i < PF) {
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
+            s0 += partial[(int64_t)c * PF + i];
+            s1 += partial[(int64_t)(c + 1) * PF + i];
+            s2 += partial[(int64_t)(c + 2) * PF + i];
+            s3 += partial[(int64_t)(c + 3) * PF + i];
+        }
+        for (; c < c1; ++c) s0 += partial[(int64_t)c * PF + i];
     }
-    for (; c < n_part; ++c) s0 += partial[(int64_t)c * PF + i];
-    const float s = (s0 + s1) + (s2 + s3);
+    red[sl][o] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (sl != 0 || i >= PF) return;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][o];
     if (i < 192 * 64) w_ih[i] = s;
     else if (i < 2 * 192 * 64) w_hh[i - 192 * 64] = s;
     else {
@@ -961,8 +973,8 @@ int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, co
 
 // rnn.weight_ih / weight_hh / bias_ih / bias_hh gradients out of the partials
 int tc_gru_bwd2_reduce(const float* partial, int n_tiles, float* w_ih, float* w_hh, float* b_ih, float* b_hh, cudaStream_t s) {
-    tc::gru_bwd2_reduce_kernel<<<(unsigned)ceil_div(tc::b2::PARTIAL_FLOATS, 128), 128, 0, s>>>(partial, n_tiles, w_ih, w_hh,
-                                                                                               b_ih, b_hh);
+    tc::gru_bwd2_reduce_kernel<<<(unsigned)ceil_div(tc::b2::PARTIAL_FLOATS, 32), 256, 0, s>>>(partial, n_tiles, w_ih, w_hh,
+                                                                                              b_ih, b_hh);
     PMB_LAUNCH_CHECK("gru_bwd2_reduce_kernel");
     return PMB_OK;
 }

@@ -259,13 +259,23 @@ __global__ void __launch_bounds__(32 * MB_WARPS, 3) mix_bwd_img16_kernel(MixBwdP
     }
 }
 
-__global__ void mix_v2_reduce_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ dv2_w,
-                                     float* __restrict__ dv2_b) {
-    const int i = threadIdx.x;
-    if (i > 32) return;
+// one block per output (32 V.2 weights + the V.2 bias); fixed summation order: deterministic
+__global__ void __launch_bounds__(256) mix_v2_reduce_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ dv2_w,
+                                                            float* __restrict__ dv2_b) {
+    __shared__ float red[8];
+    const int i = blockIdx.x;
     float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * 33 + i];
-    if (i < 32) dv2_w[i] = s; else dv2_b[0] = s;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) s += partial[(int64_t)b * 33 + i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k];
+        if (i < 32) dv2_w[i] = t; else dv2_b[0] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -457,7 +467,7 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
     if (B.n_cblk <= 16 && B.rows_total < (1ll << 31)) tc::mix_bwd_img16_kernel<<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
     else tc::mix_bwd_img_kernel<34><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
     PMB_LAUNCH_CHECK("mix_bwd_img_kernel");
-    tc::mix_v2_reduce_kernel<<<1, 64, 0, s>>>(v2_partial, grid, gv2_w, gv2_b);
+    tc::mix_v2_reduce_kernel<<<33, 256, 0, s>>>(v2_partial, grid, gv2_w, gv2_b);
     PMB_LAUNCH_CHECK("mix_v2_reduce_kernel");
 
     MixDwPlan p = mix_dw_plan(d);
