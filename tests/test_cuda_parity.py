@@ -585,20 +585,31 @@ def test_zero_copy_replay_sample_trains_identically(mixer):
     assert th.equal(idx["obs"], ref["obs"])
 
 
+# 2s3z: avail rows read from global memory (A = 11).  27m_vs_30m / few_agents / wide: avail rows staged through shared
+# memory by per-env bulk copies (A % 4 == 0), with a batch stride (time-major view), partial last tiles, tiles that span
+# more than 32 envs (N = 3) and the widest staged row (A = 36)
+_ROLLOUT_SHAPES = {
+    "2s3z": (SMAC_SHAPES["2s3z"], 53),
+    "27m_vs_30m": (SMAC_SHAPES["27m_vs_30m"], 41),
+    "few_agents": (SmacShape("few_agents", 3, 44, 20, 8, 9), 300),
+    "wide": (SmacShape("wide", 9, 130, 50, 36, 9), 97),
+}
+
+
+@pytest.mark.parametrize("shape_name", list(_ROLLOUT_SHAPES))
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_fused_rollout_selection_equals_separate_kernel(precision):
+def test_fused_rollout_selection_equals_separate_kernel(precision, shape_name):
     """pmb_select_actions_step with the epsilon-greedy selection fused into the step (Philox draws inside the kernel)
     picks exactly the actions that pmb_epsilon_greedy picks from the step's Q tensor with the same (seed, offset)."""
     import ctypes as C
     from cuda_utils import to_batch
     from pymarl_b200 import mac_REGISTRY, _lib
     from pymarl_b200.synthetic import make_scheme
-    shape = SMAC_SHAPES["2s3z"]
+    shape, B = _ROLLOUT_SHAPES[shape_name]
     args = default_args(shape, device="cuda", precision=precision, action_rng="philox")
     scheme, groups = make_scheme(shape)
     mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
     mac.cuda()
-    B = 53
     fields = numpy_episode_fields(shape, B, 4, seed=11, ragged=False)
     batch = to_batch(shape, fields)
     mac.init_hidden(B)
