@@ -6,11 +6,11 @@
 // a tile in, and the same bytes serve as K-major A operand (forward) and as MN-major operand (weight
 // gradients) - only the descriptor changes.
 //
-//   gru_fwd_tc : the ROLLOUT step kernel (fp32 hidden state in and out, fc2 inside): persistent over 128-row tiles,
-//                W_ih / W_hh / fc2 images resident in shared memory, hidden state in registers (fp32, one row per
-//                epilogue thread) and in a bf16 operand tile.  Per step: 16 tcgen05.mma for the gates (r|z fused over
-//                [x|h], n input part, n hidden part), gate math out of TMEM, 4 mma for fc2, q out of TMEM.
-//                2 CTAs per SM.  (The learner step uses gru_fwd2 / gru_bwd2 / q_select in gru_tc2.cu.)
+//   gru_rollout: the ROLLOUT step kernel (fp32 hidden state in and out, fc2 and the epsilon-greedy selection inside):
+//                one persistent CTA per SM with two 128-row tiles in flight, W_ih / W_hh / fc2 images resident in shared
+//                memory, hidden state in fp32 registers and in a bf16 operand tile.  Per tile: 16 tcgen05.mma for the
+//                gates (r|z fused over [x|h], n input part, n hidden part), gate math out of TMEM, 4 mma for fc2, q out
+//                of TMEM.  (The learner step uses gru_fwd2 / gru_bwd2 / q_select in gru_tc2.cu.)
 //   agent_dw_tc: fc1 / fc2 weight gradients as one image-fed GEMM kernel.  (The rnn.* gradients are accumulated
 //                inside gru_bwd2, gru_tc2.cu.)
 #include <cuda.h>
