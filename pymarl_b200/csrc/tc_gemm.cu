@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
         for (int i = 0; i < N_SLOTS; ++i) { mbar_init(&st_full[i], 1 + 32); mbar_init(&st_empty[i], N_CONV); }
-        mbar_init(a_full, N_CONV); mbar_init(a_free, 2);
+        mbar_init(a_full, N_CONV); mbar_init(a_free, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], N_EPI); }
         fence_barrier_init();
     }
@@ -696,7 +696,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         }
         const int c_last = P.n_chunks - 1;
         const int j_pad = c_last * BK + 2 * lane - P.O;       // index of this lane's first column in the K padding
-        const uint32_t a_base = smem_u32(a_s) + ((uint32_t)(lane >> 2) << 4) + (lane & 3) * 4;   // + row*128, ^ swizzle
+        const uint32_t a_s_u32 = smem_u32(a_s);
+        const uint32_t a_base = a_s_u32 + ((uint32_t)(lane >> 2) << 4) + (lane & 3) * 4;   // + row*128, ^ swizzle
         uint32_t git = 0, ti = 0;
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
             for (int g = 0; g < GROUPS; ++g, ++git) {
@@ -752,6 +753,15 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
 #pragma unroll
                         for (int c = 0; c < MAX_CHUNKS; ++c)
                             if (c < P.n_chunks) sts_b32(dst + c * A_STAGE_BYTES, pk[rr][c]);
+                        // the obs image leaves from here too: the warp's 32 words are one full 128-byte line of the image
+                        // (a bulk store of the finished A tile kept the tile busy for ~2500 cycles after the MMAs were
+                        // done with it: the converters of the next tile waited 22 % of the kernel time for it)
+                        if (P.obs_img) {
+                            uint8_t* img = P.obs_img + item * tile_bytes + (dst - a_s_u32);
+#pragma unroll
+                            for (int c = 0; c < MAX_CHUNKS; ++c)
+                                if (c < P.n_chunks) __stcs(reinterpret_cast<uint32_t*>(img + c * A_STAGE_BYTES), pk[rr][c]);
+                        }
                     }
                 }
             }
@@ -782,19 +792,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             }
         }
     } else if (warp == STORE_W) {
-        if (lane == 0) {
-            uint32_t ti = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
-                mbar_wait(a_full, ti & 1);
-                if (P.obs_img) {
-                    bulk_copy_s2g(P.obs_img + item * tile_bytes, a_s, (uint32_t)tile_bytes);
-                    bulk_commit_group();
-                    bulk_wait_group_read<0>();
-                }
-                mbar_arrive(a_free);
-            }
-            bulk_wait_group<0>();
-        }
+        // (idle: the obs image is written by the converters)
     } else {
         // ===== epilogue: one row per thread; x = relu(acc [+ id/bias table] + act table) -> bf16 tile images + mask =====
         const uint32_t r = (uint32_t)(warp * 32 + lane);
