@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libpymarl_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-          "-Xptxas", "-v"]
+          "-Xptxas", "-v"] + os.environ.get("PMB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

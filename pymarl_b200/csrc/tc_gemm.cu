@@ -555,11 +555,15 @@ __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// NC = number of 64-column k-chunks of the obs (compile time: the converters are instruction-latency bound - 8 warps,
+// ~300 dependent instructions per 16-row group each - and with NC known the per-chunk predicates of all but the last
+// chunk and the run-time "is this the last chunk" selects disappear)
+template <int NC>
 __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamParams P) {
     using namespace fs;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int tile_bytes = P.n_chunks * A_STAGE_BYTES;
+    constexpr int tile_bytes = NC * A_STAGE_BYTES;
     uint8_t* w_s = smem;                                    // [n_chunks][16 KB]
     uint8_t* a_s = smem + tile_bytes;                       // [n_chunks][16 KB]
     uint8_t* stage = a_s + tile_bytes;                      // [N_SLOTS][slot_bytes]
@@ -688,13 +692,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         // (which of a lane's two columns per chunk exist, where the one-hot padding columns are) is hoisted: the
         // first version spent ~2400 cycles per group in a serial chain of predicate / address arithmetic. =====
         const int cw = warp - FIRST_CONV_W;
-        uint32_t ok0 = 0, ok1 = 0;                            // bit c: column 64c + 2 lane (+1) < O
-#pragma unroll
-        for (int c = 0; c < MAX_CHUNKS; ++c) {
-            if (c < P.n_chunks && c * BK + 2 * lane < P.O) ok0 |= 1u << c;
-            if (c < P.n_chunks && c * BK + 2 * lane + 1 < P.O) ok1 |= 1u << c;
-        }
-        const int c_last = P.n_chunks - 1;
+        constexpr int c_last = NC - 1;
+        // every column of the chunks before the last exists (O > 64 (NC-1)); the last chunk: per lane
+        const bool okl0 = c_last * BK + 2 * lane < P.O, okl1 = c_last * BK + 2 * lane + 1 < P.O;
         const int j_pad = c_last * BK + 2 * lane - P.O;       // index of this lane's first column in the K padding
         const uint32_t a_s_u32 = smem_u32(a_s);
         const uint32_t a_base = a_s_u32 + ((uint32_t)(lane >> 2) << 4) + (lane & 3) * 4;   // + row*128, ^ swizzle
@@ -710,22 +710,22 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     offs[rr] = rowoff[slot * GROUP_ROWS + RPW * cw + rr];
                     nns[rr] = rown[slot * GROUP_ROWS + RPW * cw + rr];
                 }
-                float v0[RPW][MAX_CHUNKS], v1[RPW][MAX_CHUNKS];
+                float v0[RPW][NC], v1[RPW][NC];
                 {
 #pragma unroll
                     for (int rr = 0; rr < RPW; ++rr) {           // all loads first
                         const int off = offs[rr];
-                        const uint32_t src = sl + (uint32_t)(off < 0 ? 0 : off);
-                        const uint32_t m0 = off < 0 ? 0u : ok0, m1 = off < 0 ? 0u : ok1;
+                        const bool real = off >= 0;
+                        const uint32_t src = sl + (uint32_t)(real ? off : 0);
 #pragma unroll
-                        for (int c = 0; c < MAX_CHUNKS; ++c) {
+                        for (int c = 0; c < NC; ++c) {
                             v0[rr][c] = 0.f; v1[rr][c] = 0.f;
-                            if ((m0 >> c) & 1u) v0[rr][c] = lds_f32(src + c * 256);
-                            if ((m1 >> c) & 1u) v1[rr][c] = lds_f32(src + c * 256 + 4);
+                            if (real && (c < c_last || okl0)) v0[rr][c] = lds_f32(src + c * 256);
+                            if (real && (c < c_last || okl1)) v1[rr][c] = lds_f32(src + c * 256 + 4);
                         }
                     }
                     // pack first (consumes every loaded value), release the staging slot, then write the A tile
-                    uint32_t pk[RPW][MAX_CHUNKS];
+                    uint32_t pk[RPW][NC];
 #pragma unroll
                     for (int rr = 0; rr < RPW; ++rr) {
                         const int off = offs[rr];
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                         const bool hit0 = fold && j_pad >= 0 && (j_pad == nn || j_pad == P.N);
                         const bool hit1 = fold && j_pad + 1 >= 0 && (j_pad + 1 == nn || j_pad + 1 == P.N);
 #pragma unroll
-                        for (int c = 0; c < MAX_CHUNKS; ++c) {
+                        for (int c = 0; c < NC; ++c) {
                             float a = v0[rr][c], b = v1[rr][c];
                             if (c == c_last) { a = hit0 ? 1.0f : a; b = hit1 ? 1.0f : b; }
                             pk[rr][c] = pack_bf16x2(a, b);
@@ -751,16 +751,14 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                         const uint32_t rt = (uint32_t)(g * GROUP_ROWS + RPW * cw + rr);
                         const uint32_t dst = (a_base + rt * 128u) ^ ((rt & 7u) << 4);
 #pragma unroll
-                        for (int c = 0; c < MAX_CHUNKS; ++c)
-                            if (c < P.n_chunks) sts_b32(dst + c * A_STAGE_BYTES, pk[rr][c]);
+                        for (int c = 0; c < NC; ++c) sts_b32(dst + c * A_STAGE_BYTES, pk[rr][c]);
                         // the obs image leaves from here too: the warp's 32 words are one full 128-byte line of the image
                         // (a bulk store of the finished A tile kept the tile busy for ~2500 cycles after the MMAs were
                         // done with it: the converters of the next tile waited 22 % of the kernel time for it)
                         if (P.obs_img) {
                             uint8_t* img = P.obs_img + item * tile_bytes + (dst - a_s_u32);
 #pragma unroll
-                            for (int c = 0; c < MAX_CHUNKS; ++c)
-                                if (c < P.n_chunks) __stcs(reinterpret_cast<uint32_t*>(img + c * A_STAGE_BYTES), pk[rr][c]);
+                            for (int c = 0; c < NC; ++c) __stcs(reinterpret_cast<uint32_t*>(img + c * A_STAGE_BYTES), pk[rr][c]);
                         }
                     }
                 }
@@ -780,7 +778,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 mbar_wait(&tempty[b], ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tm = tmem_base + 128u * b;
-                for (int c = 0; c < P.n_chunks; ++c) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
                     const uint32_t a_addr = smem_u32(a_s + c * A_STAGE_BYTES), w_addr = smem_u32(w_s + c * A_STAGE_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk)
@@ -1047,10 +1046,21 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             Q.relu_mask = relu_mask; Q.use_act = d->obs_last_action;
             Q.n_nets = x_tg ? 2 : 1; Q.t0 = t0;
             Q.l2_prefetch = 1;
-            PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
             const int64_t n_items = (int64_t)nt * n_tiles;
             const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
-            tc::fc1_stream_kernel<<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q);
+#define PMB_FC1_STREAM_LAUNCH(NC)                                                                                            \
+    case NC:                                                                                                                 \
+        PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need)); \
+        tc::fc1_stream_kernel<NC><<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q);                                       \
+        break;
+            switch (n_chunks) {
+                PMB_FC1_STREAM_LAUNCH(1)
+                PMB_FC1_STREAM_LAUNCH(2)
+                PMB_FC1_STREAM_LAUNCH(3)
+                PMB_FC1_STREAM_LAUNCH(4)
+                PMB_FC1_STREAM_LAUNCH(5)
+            }
+#undef PMB_FC1_STREAM_LAUNCH
             PMB_LAUNCH_CHECK("fc1_stream_kernel");
             return PMB_OK;
         }

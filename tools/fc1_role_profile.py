@@ -1,5 +1,8 @@
+"""Per-role wait profile of fc1_stream_kernel.  Needs a library built with
+PMB_EXTRA_NVCC_FLAGS=-DPMB_FC1_PROFILE python -c 'from pymarl_b200.build import build; build(force=True)'."""
 import sys, os, ctypes as C
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch as th
 import bench
 from cuda_utils import Logger
@@ -28,8 +31,8 @@ v = list(out)
 n_cta = v[9]
 tot = v[8] / n_cta
 names = ["producer: st_empty (x3 warps)", "converter: st_full (x8 warps)", "converter: a_free (x8)", "MMA: a_full", "MMA: tempty",
-         "epilogue: tfull (x4)", "store: a_full"]
-mult = [3, 8, 8, 1, 1, 4, 1]
+         "epilogue: tfull (x4)", "converter: load + pack phase (x8)", "converter: store phase incl. a_free (x8)"]
+mult = [3, 8, 8, 1, 1, 4, 8, 8]
 print("CTAs", n_cta, "cycles per CTA", round(tot))
 for i, (nm, m) in enumerate(zip(names, mult)):
     print(f"{nm:34s} {v[i] / n_cta / m / tot * 100:6.1f} % of the kernel time per warp")
