@@ -558,8 +558,25 @@ __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
 // NC = number of 64-column k-chunks of the obs (compile time: the converters are instruction-latency bound - 8 warps,
 // ~300 dependent instructions per 16-row group each - and with NC known the per-chunk predicates of all but the last
 // chunk and the run-time "is this the last chunk" selects disappear)
+// Per-role wait accounting (build with PMB_EXTRA_NVCC_FLAGS=-DPMB_FC1_PROFILE, read with tools/fc1_role_profile.py): cycles
+// each role spends blocked on each barrier / in each converter phase, summed over CTAs.  This is what located the
+// obs-image bulk store as the reason the converters idled between tiles.
+#ifdef PMB_FC1_PROFILE
+__device__ unsigned long long g_fc1_prof[16];
+#define TWAIT(idx, bar, par) do { long long _t0 = clock64(); mbar_wait(bar, par); if (lane == 0) prof_acc[idx] += clock64() - _t0; } while (0)
+#define TMARK(var) const long long var = clock64()
+#define TADD(idx, expr) do { if (lane == 0) prof_acc[idx] += (expr); } while (0)
+#else
+#define TWAIT(idx, bar, par) mbar_wait(bar, par)
+#define TMARK(var)
+#define TADD(idx, expr)
+#endif
 template <int NC>
 __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamParams P) {
+#ifdef PMB_FC1_PROFILE
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = clock64();
+#endif
     using namespace fs;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -669,7 +686,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
                     }
                 }
-                mbar_wait(&st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
+                TWAIT(0, &st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
                 if (cnt > 0) {
                     for (int k = 0; k < cnt; ++k) { ro[lr + k] = (int)(cur + (uint32_t)k * P.O * 4u); rn[lr + k] = n0 + k; }
                     if (t_beg > h_end) bulk_copy_g2s(sl + cur + h_end, ga + h_end, t_beg - h_end, &st_full[slot]);
@@ -702,7 +719,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
             for (int g = 0; g < GROUPS; ++g, ++git) {
                 const int slot = git % N_SLOTS;
-                mbar_wait(&st_full[slot], (git / N_SLOTS) & 1);
+                TWAIT(1, &st_full[slot], (git / N_SLOTS) & 1);
+                TMARK(pt1);
                 const uint32_t sl = smem_u32(stage + slot * P.slot_bytes) + 8u * lane;
                 int offs[RPW], nns[RPW];
 #pragma unroll
@@ -743,9 +761,11 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&st_empty[slot]);
+                    TMARK(pt2);
+                    TADD(6, pt2 - pt1);                            // load + pack phase
                     // the first group of a tile waits here (values already in registers, slot already released) until
                     // the MMAs and the image store of the previous tile are done with the A tile
-                    if (g == 0) mbar_wait(a_free, (ti & 1) ^ 1);
+                    if (g == 0) TWAIT(2, a_free, (ti & 1) ^ 1);
 #pragma unroll
                     for (int rr = 0; rr < RPW; ++rr) {
                         const uint32_t rt = (uint32_t)(g * GROUP_ROWS + RPW * cw + rr);
@@ -761,6 +781,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                             for (int c = 0; c < NC; ++c) __stcs(reinterpret_cast<uint32_t*>(img + c * A_STAGE_BYTES), pk[rr][c]);
                         }
                     }
+                    TADD(7, clock64() - pt2);                      // store phase (includes the a_free wait of group 0)
                 }
             }
             fence_proxy_async_smem();
@@ -774,8 +795,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             uint32_t ti = 0;
             for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
                 const int b = ti & 1;
-                mbar_wait(a_full, ti & 1);
-                mbar_wait(&tempty[b], ((ti >> 1) & 1) ^ 1);
+                TWAIT(3, a_full, ti & 1);
+                TWAIT(4, &tempty[b], ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tm = tmem_base + 128u * b;
 #pragma unroll
@@ -791,9 +812,11 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             }
         }
     } else if (warp == STORE_W) {
-        // (idle: the obs image is written by the converters)
+        // (idle: the obs image is written by the converters.  One warp copying the finished A tile out with 16-byte loads /
+        // stores took longer than the MMAs - 8.65 against 7.23 ms)
     } else {
-        // ===== epilogue: one row per thread; x = relu(acc [+ id/bias table] + act table) -> bf16 tile images + mask =====
+        // ===== epilogue: one row per thread; x = relu(acc [+ id/bias table] + act table) -> bf16 tile images + mask.
+        // (Eight epilogue warps, one per row and net, measured slower: 7.21 -> 7.53 ms.) =====
         const uint32_t r = (uint32_t)(warp * 32 + lane);
         // the previous action of a row, fetched one item ahead (-1: none / step not filled, -2: padding row)
         auto fetch_prev = [&](int64_t item, int& n_out) {
@@ -817,7 +840,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
             const int b = ti & 1;
             const int a_next = fetch_prev(item + gridDim.x, n_nxt);
-            mbar_wait(&tfull[b], (ti >> 1) & 1);
+            TWAIT(5, &tfull[b], (ti >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + 128u * b + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
@@ -867,6 +890,12 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             a_prev = a_next; n_cur = n_nxt;
         }
     }
+#ifdef PMB_FC1_PROFILE
+    if (lane == 0) {
+        for (int i = 0; i < 8; ++i) if (prof_acc[i]) atomicAdd(&g_fc1_prof[i], (unsigned long long)prof_acc[i]);
+        if (threadIdx.x == 0) { atomicAdd(&g_fc1_prof[8], (unsigned long long)(clock64() - prof_t0)); atomicAdd(&g_fc1_prof[9], 1ull); }
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_W) {
@@ -977,6 +1006,14 @@ __global__ void fc1_stream_pack_kernel(const float* __restrict__ w_on, const flo
     }
 }
 
+#ifdef PMB_FC1_PROFILE
+extern "C" int pmb_debug_fc1_prof(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tc::g_fc1_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_fc1_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
                     float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, uint32_t* relu_mask, void* scratch,
                     int64_t scratch_bytes, cudaStream_t s) {
