@@ -580,9 +580,10 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
         // pipeline: the generators, not the copies or the MMAs, were the critical path).  All four warps: final epilogue.
         {
             const int rr = (warp & 1) * 32 + lane;             // row within the half tile
-            struct Idx { int a, ap; float dq; };
+            // RAW loaded values: nothing in fetch() depends on a load (in-order issue: the warp would stall right there)
+            struct Idx { long long a, ap, f; float dq; };
             auto fetch = [&](int64_t i) {
-                Idx x{-1, -1, 0.f};
+                Idx x{-1, -1, 0, 0.f};
                 if (i >= n_my) return x;
                 const int64_t item = beg + i;
                 const int64_t tt = item >> 1;
@@ -595,22 +596,20 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
                     const int64_t be = ep_row(P.ep_index, b);
                     if (t < P.T - 1) {
                         x.dq = __ldg(P.d_chosen + (b * (P.T - 1) + t) * P.N + n);
-                        x.a = (int)__ldg(P.actions + be * P.actions_sb + t * P.N + n);
+                        x.a = __ldg(P.actions + be * P.actions_sb + t * P.N + n);
                     }
-                    if (P.use_act && t > 0) {                  // both loads issued unconditionally, then selected
-                        const int64_t f = __ldg(P.filled + be * P.filled_sb + (t - 1));
-                        const int apv = (int)__ldg(P.actions + be * P.actions_sb + (t - 1) * P.N + n);
-                        x.ap = f != 0 ? apv : -1;
+                    if (P.use_act && t > 0) {
+                        x.f = __ldg(P.filled + be * P.filled_sb + (t - 1));
+                        x.ap = __ldg(P.actions + be * P.actions_sb + (t - 1) * P.N + n);
                     }
                 }
                 return x;
             };
-            Idx cur = fetch(warp >> 1);
-            for (int64_t i = warp >> 1; i < n_my; i += 2) {
+            // write the one-hot tiles of item i from the resolved indices, publish the stage
+            auto emit = [&](int64_t i, const Idx& x) {
                 const int s = (int)(i % STAGES);
-                const Idx nxt = fetch(i + 2);
-                const int a = cur.a, ap = cur.ap;
-                const uint32_t dqb = pack_bf16x2(cur.dq, 0.f) & 0xffffu;      // bf16 bits of dq
+                const int a = (int)x.a, ap = x.f != 0 ? (int)x.ap : -1;
+                const uint32_t dqb = pack_bf16x2(x.dq, 0.f) & 0xffffu;        // bf16 bits of dq
                 mbar_wait(&empty[s], (uint32_t)(((i / STAGES) & 1) ^ 1));
                 uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
@@ -625,7 +624,21 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
-                cur = nxt;
+            };
+            // Two items in flight per warp, their loads issued AFTER the proxy fence of emit() (it compiles to MEMBAR.ALL.CTA
+            // + FENCE.VIEW.ASYNC and waits for every load the thread has in flight) and by two distinct sets of load
+            // instructions (a scoreboard is a counter: a wait on one item's values also waits for newer loads on it).
+            // Role profile (clock64 around every wait): the generators, not the copies or the MMAs, bound this kernel -
+            // the MMA warp waits for their tiles ~38 % of the time; most of a generator's time is load latency that the
+            // fence or the next use exposes.  Separate index-loader warps feeding the writers through a two-slot ring were
+            // measured at 6.0-6.5 ms against 3.27 (the ring is too shallow; there is no shared memory for a deeper one).
+            const int64_t i0 = warp >> 1;
+            Idx x0 = fetch(i0), x1 = fetch(i0 + 2);
+            for (int64_t i = i0; i < n_my; i += 4) {
+                emit(i, x0);
+                x0 = fetch(i + 4);
+                if (i + 2 < n_my) emit(i + 2, x1);
+                x1 = fetch(i + 6);
             }
         }
         float* out = P.partial + (int64_t)blockIdx.x * PARTIAL_FLOATS;
