@@ -486,7 +486,9 @@ constexpr int STAGE_BYTES = (4 + MAX_CHUNKS) * HALF;         // dpre1 | Q1 | P1 
 constexpr int ONES = STAGES * STAGE_BYTES;
 constexpr int BARS = ONES + HALF;
 constexpr int SMEM_BYTES = 1024 + BARS + 128;
-constexpr int THREADS = 192;
+constexpr int N_PAIR = STAGES;                                // generator warp pairs (warps 0-3 and 6-7): pair p owns stage p
+static_assert(N_PAIR == STAGES, "a pair per stage: its parity waits on the stage barrier are then never two phases apart");
+constexpr int THREADS = 32 * (6 + 2 * (N_PAIR - 2));
 constexpr int OBS_LD = MAX_CHUNKS * 64;                      // 320
 constexpr int PARTIAL_FLOATS = 64 * OBS_LD + 64 * 64 + 128 + 128 * 64;   // dW1obs | dW2 | (db1|db2) | (dW1act|dW1id)
 }  // namespace ad
@@ -632,15 +634,19 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
             // the MMA warp waits for their tiles ~38 % of the time; most of a generator's time is load latency that the
             // fence or the next use exposes.  Separate index-loader warps feeding the writers through a two-slot ring were
             // measured at 6.0-6.5 ms against 3.27 (the ring is too shallow; there is no shared memory for a deeper one).
-            const int64_t i0 = warp >> 1;
-            Idx x0 = fetch(i0), x1 = fetch(i0 + 2);
-            for (int64_t i = i0; i < n_my; i += 4) {
+            // (one pair per stage: with two pairs, a pair's budget per item - two item times - was spent almost entirely on
+            // exposed load latency and the MMA warp waited for the tiles 38 % of the time; four pairs over three stages
+            // let a pair run two barrier phases ahead - a parity wait cannot tell - and corrupted a stage)
+            const int64_t i0 = warp < 4 ? (warp >> 1) : 2 + ((warp - 6) >> 1);
+            Idx x0 = fetch(i0), x1 = fetch(i0 + N_PAIR);
+            for (int64_t i = i0; i < n_my; i += 2 * N_PAIR) {
                 emit(i, x0);
-                x0 = fetch(i + 4);
-                if (i + 2 < n_my) emit(i + 2, x1);
-                x1 = fetch(i + 6);
+                x0 = fetch(i + 2 * N_PAIR);
+                if (i + N_PAIR < n_my) emit(i + N_PAIR, x1);
+                x1 = fetch(i + 3 * N_PAIR);
             }
         }
+        if (warp >= 4) goto tail;                               // the final epilogue: warps 0-3 (one TMEM lane quarter each)
         float* out = P.partial + (int64_t)blockIdx.x * PARTIAL_FLOATS;
         float* p_obs = out, *p_w2 = out + 64 * OBS_LD, *p_b = p_w2 + 64 * 64, *p_a2 = p_b + 128;
         const int c = warp * 32 + lane;                        // accumulator row 0..127
@@ -676,6 +682,7 @@ __global__ void __launch_bounds__(ad::THREADS, 1) agent_dw_tc_kernel(AgentDwPara
             for (int i = threadIdx.x; i < PARTIAL_FLOATS; i += 128) out[i] = 0.f;
         }
     }
+tail:
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
