@@ -373,49 +373,60 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
             }
             float best = -INFINITY;
             int bidx = 0x7fffffff, cnt = 0;
-            unsigned long long okmask = 0ull;
-            for (int c0 = 0; c0 < A_pad; c0 += 16) {
-                uint32_t aq[16];
-                tmem_ld_32x16(tlane + c0, aq);
-                tmem_wait_ld();
-                if (valid) {
-                    float qv[16];
+            uint32_t ok_lo = 0u, ok_hi = 0u;                      // available actions 0..31 / 32..63
+            // four chunks of 16 actions, the action index a compile-time constant in each (the first version looped over
+            // c0 with 64-bit variable shifts and spent ~6000 cycles per tile here)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(aq[j]) + bias[256 + c0 + j];
-                    if (qo) {
-                        if (q_vec) {
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c0 = 16 * cc;
+                if (c0 < A_pad) {
+                    uint32_t aq[16];
+                    tmem_ld_32x16(tlane + c0, aq);
+                    float bq[16];
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4)
-                                if (c0 + 4 * j4 < P.A)
-                                    *reinterpret_cast<float4*>(qo + c0 + 4 * j4) =
-                                        make_float4(qv[4 * j4], qv[4 * j4 + 1], qv[4 * j4 + 2], qv[4 * j4 + 3]);
-                        } else {
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        *reinterpret_cast<float4*>(&bq[4 * j4]) = *reinterpret_cast<const float4*>(bias + 256 + c0 + 4 * j4);
+                    tmem_wait_ld();
+                    if (valid) {
+                        float qv[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < P.A) qo[c0 + j] = qv[j];
-                        }
-                    }
-                    if (select) {
-                        int avj[16];
-                        if (av_vec && c0 + 16 <= P.A) {
+                        for (int j = 0; j < 16; ++j) qv[j] = __uint_as_float(aq[j]) + bq[j];
+                        if (qo) {
+                            if (q_vec) {
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const int4 w4 = *(reinterpret_cast<const int4*>(av + c0) + j4);
-                                avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
+                                for (int j4 = 0; j4 < 4; ++j4)
+                                    if (c0 + 4 * j4 < P.A)
+                                        *reinterpret_cast<float4*>(qo + c0 + 4 * j4) =
+                                            make_float4(qv[4 * j4], qv[4 * j4 + 1], qv[4 * j4 + 2], qv[4 * j4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < P.A) qo[c0 + j] = qv[j];
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? av[c0 + j] : 0;
                         }
+                        if (select) {
+                            int avj[16];
+                            if (av_vec && c0 + 16 <= P.A) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int a = c0 + j;
-                            if (a < P.A) {
-                                const bool ok = avj[j] != 0;
-                                cnt += ok ? 1 : 0;
-                                okmask |= (unsigned long long)(ok ? 1 : 0) << a;
-                                const float v = ok ? qv[j] : -INFINITY;
-                                if (v > best) { best = v; bidx = a; }          // ascending a, strict >: lowest index wins
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const int4 w4 = *(reinterpret_cast<const int4*>(av + c0) + j4);
+                                    avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? av[c0 + j] : 0;
+                            }
+                            uint32_t oks = 0u;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) oks |= (avj[j] != 0 ? 1u : 0u) << j;
+                            const int left = P.A - c0;                               // actions of this chunk that exist
+                            oks &= left >= 16 ? 0xffffu : ((1u << (left > 0 ? left : 0)) - 1u);
+                            cnt += __popc(oks);
+                            if (cc < 2) ok_lo |= oks << (16 * (cc & 1)); else ok_hi |= oks << (16 * (cc & 1));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float v = (oks >> j) & 1u ? qv[j] : -INFINITY;
+                                if (v > best) { best = v; bidx = c0 + j; }          // ascending a, strict >: lowest index wins
                             }
                         }
                     }
@@ -434,7 +445,8 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                     float rbest = -INFINITY;
                     ridx = 0x7fffffff;
                     for (int a = 0; a < P.A; ++a) {
-                        const float ratio = __fdiv_rn(((okmask >> a) & 1ull) ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
+                        const bool oka = ((a < 32 ? ok_lo >> a : ok_hi >> (a - 32)) & 1u) != 0u;
+                        const float ratio = __fdiv_rn(oka ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
                         if (ratio > rbest) { rbest = ratio; ridx = a; }
                     }
                     if (ridx == 0x7fffffff) ridx = 0;
@@ -447,10 +459,9 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                     uu = 1.0f - gf_u01(r0.x);                  // [0, 1)
                     int kq = (int)((1.0f - gf_u01(r0.y)) * (float)cnt);
                     if (kq >= cnt) kq = cnt - 1;
-                    // the kq-th set bit of okmask
-                    unsigned long long m = okmask;
-                    for (int i = 0; i < kq; ++i) m &= m - 1;
-                    ridx = m ? __ffsll((long long)m) - 1 : 0;
+                    // the kq-th set bit of the availability mask
+                    const int c_lo = __popc(ok_lo);
+                    ridx = cnt <= 0 ? 0 : (kq < c_lo ? (int)__fns(ok_lo, 0u, kq + 1) : 32 + (int)__fns(ok_hi, 0u, kq - c_lo + 1));
                 }
                 int pick = (cnt > 0 && uu < P.epsilon) ? ridx : bidx;
                 if (pick >= P.A) pick = 0;
