@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
-        for (int i = 0; i < N_SLOTS; ++i) { mbar_init(&st_full[i], 1 + 32); mbar_init(&st_empty[i], N_CONV); }
+        for (int i = 0; i < N_SLOTS; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], N_CONV); }
         mbar_init(a_full, N_CONV); mbar_init(a_free, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], N_EPI); }
         fence_barrier_init();
@@ -647,22 +647,21 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 if (cnt < 0) cnt = 0;
                 const int n0 = lane == 0 ? n00 : 0;
                 const char* ga = nullptr;
-                uint32_t bytes = 0, cur = 0, h_end = 0, t_beg = 0;
+                uint32_t cur = 0, phase = 0, cp_bytes = 0;
                 if (cnt > 0) {
                     ga = reinterpret_cast<const char*>(P.obs + ep_row(P.ep_index, (int64_t)b0 + lane) * P.obs_sb +
                                                        ((t + P.t0) * P.N + n0) * (int64_t)P.O);
-                    bytes = (uint32_t)cnt * P.O * 4u;
-                    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
-                    // staging offset: same 16-byte phase as the source; 32 bytes of slack per run keep runs disjoint
-                    cur = (((uint32_t)lr * P.O * 4u + 15u) & ~15u) + 32u * lane + phase;
-                    // [ga, ga+bytes) = head (< 16 B) | 16-byte aligned interior | tail (< 16 B)
-                    h_end = (16u - phase) & 15u;
-                    if (h_end > bytes) h_end = bytes;
-                    t_beg = (phase + bytes) & ~15u;
-                    t_beg = t_beg > phase ? t_beg - phase : 0u;
-                    if (t_beg < h_end) t_beg = h_end;
+                    phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
+                    // staging offset: same 16-byte phase as the source; 48 bytes of slack per run keep the runs - and the
+                    // up to 15 bytes copied before / after each of them - disjoint
+                    cur = (((uint32_t)lr * P.O * 4u + 15u) & ~15u) + 48u * lane + phase;
+                    // ONE bulk copy per run, widened to 16-byte boundaries on both sides (the extra bytes stay inside the
+                    // 16-byte granules the run touches anyway - never another page - and land in the slack).  The first
+                    // version copied the aligned interior and fetched head / tail with 4-byte cp.async: with the 32
+                    // no-increment barrier arrivals that needs, publishing a slot took ~1600 cycles.
+                    cp_bytes = (phase + (uint32_t)cnt * P.O * 4u + 15u) & ~15u;
                 }
-                const uint32_t tx = __reduce_add_sync(0xffffffffu, t_beg - h_end);
+                const uint32_t tx = __reduce_add_sync(0xffffffffu, cp_bytes);
                 // L2 prefetch of the same group of this CTA's NEXT tile: the staging ring is all the shared memory that is
                 // left (3 x 18 KB in flight per SM), so the copies should see L2 latency, not loaded-HBM latency
                 if (P.l2_prefetch && cnt > 0 && item + gridDim.x < n_items) {
@@ -686,18 +685,16 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
                     }
                 }
+                // row tables, one row per lane: row j belongs to run rj (run 0 holds first_cnt rows, the others N each)
+                const int rj = lane < first_cnt ? 0 : 1 + (lane - first_cnt) / P.N;
+                const int lrj = rj == 0 ? 0 : first_cnt + (rj - 1) * P.N;
+                const uint32_t cur_j = __shfl_sync(0xffffffffu, cur, rj & 31);
                 TWAIT(0, &st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
-                if (cnt > 0) {
-                    for (int k = 0; k < cnt; ++k) { ro[lr + k] = (int)(cur + (uint32_t)k * P.O * 4u); rn[lr + k] = n0 + k; }
-                    if (t_beg > h_end) bulk_copy_g2s(sl + cur + h_end, ga + h_end, t_beg - h_end, &st_full[slot]);
-                    for (uint32_t o = 0; o < h_end; o += 4)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
-                    for (uint32_t o = t_beg; o < bytes; o += 4)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sl + cur + o)), "l"(ga + o) : "memory");
+                if (lane < GROUP_ROWS) {
+                    ro[lane] = lane < rows_here ? (int)(cur_j + (uint32_t)(lane - lrj) * P.O * 4u) : -1;   // rows beyond R: zeros
+                    rn[lane] = (rj == 0 ? n00 : 0) + (lane - lrj);
                 }
-                if (lane >= rows_here && lane < GROUP_ROWS) ro[lane] = -1;       // rows beyond R: zeros
-                // arrives when all earlier cp.async of this lane have landed (does not change the expected count)
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&st_full[slot])) : "memory");
+                if (cnt > 0) bulk_copy_g2s(sl + cur - phase, ga - phase, cp_bytes, &st_full[slot]);
                 __syncwarp();
                 if (lane == 0) {
                     if (tx) mbar_arrive_expect_tx(&st_full[slot], tx); else mbar_arrive(&st_full[slot]);
@@ -1029,7 +1026,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     // the streaming kernel packs its own W (fc1_stream_pack_kernel) and needs the agent-id table only when the one-hot
     // columns do not fit the K padding
     const int n_chunks_s = (d->O + tc::BK - 1) / tc::BK;
-    const int slot_bytes_s = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 32 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
+    const int slot_bytes_s = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 48 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
     const int64_t smem_need_s = 1024 + 2 * (int64_t)n_chunks_s * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes_s +
                                 2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
     const bool use_stream = tile_images && n_chunks_s <= tc::fs::MAX_CHUNKS && smem_need_s <= 232448;
@@ -1063,7 +1060,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
                          reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
                          d->obs_last_action, n_tiles, R, relu_mask};
         const int n_chunks = (d->O + tc::BK - 1) / tc::BK;
-        const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 32 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
+        const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 48 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
         const int64_t smem_need = 1024 + 2 * (int64_t)n_chunks * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes +
                                   2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
         if (n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
