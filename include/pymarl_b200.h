@@ -101,7 +101,9 @@ typedef struct pmb_hparams {
     float gamma, lr, alpha, eps, grad_norm_clip;
     int32_t do_target_sync;          /* host decides: (episode_num - last)/interval >= 1  */
     int32_t skip_update;             /* 1: stop after the gradients (multi-GPU: all-reduce, then pmb_clip_rmsprop_update) */
-    int32_t keep_q;                  /* bf16 tier: 1 = also write the Q tensors (mac_out) into the workspace (tests) */
+    int32_t keep_q;                  /* debug bits (tests): 1 = bf16 tier also writes the Q tensors (mac_out) into the
+                                      * workspace; 2 = stop after the forward pass and the loss sums (q_learner.py:39-97),
+                                      * leaving every forward intermediate in the workspace */
 } pmb_hparams;
 
 /* stats buffer: 16 doubles on the device, written by the step */
@@ -190,6 +192,17 @@ int pmb_clip_rmsprop_update(int64_t n, float* flat_p, float* flat_g, float* flat
                             int32_t do_target_sync, double* stats, float lr, float alpha, float eps,
                             float grad_norm_clip, float* scratch, pmb_stream stream);
 
+/* ---- K8: data-parallel exchange (no counterpart in the reference, which is single-process) ----
+ * Episodes shard over ranks; every rank runs pmb_qlearner_train_step with skip_update = 1, then
+ *   pmb_dp_pack(n, flat_g, stats)    : appends the five loss sums as (hi, lo) float pairs behind the n gradients
+ *   ONE all-reduce(sum, fp32) over flat_g[0 .. n + PMB_DP_TAIL_FLOATS)   (NCCL, issued by the host plumbing)
+ *   pmb_dp_unpack(n, flat_g, stats)  : restores the (now global) sums
+ *   pmb_clip_rmsprop_update(...)     : identical update on every rank (replicated parameters / optimizer state)
+ * flat_g must therefore hold n + PMB_DP_TAIL_FLOATS floats. */
+#define PMB_DP_TAIL_FLOATS 16
+int pmb_dp_pack(int64_t n, float* flat_g, const double* stats, pmb_stream stream);
+int pmb_dp_unpack(int64_t n, const float* flat_g, double* stats, pmb_stream stream);
+
 /* ---- K7: epsilon-greedy action selection (components/action_selectors.py:44-62) --------- */
 /* q [rows_b][N][A] f32, avail [rows_b][N][A] i32.  Draw modes:
  *   u != NULL, expo != NULL : injected draws (u [b][N] uniform, expo [b][N][A] Exp(1)), the
@@ -250,6 +263,25 @@ typedef struct pmb_gather_field {
 int pmb_gather_episodes(const pmb_gather_field* fields_host, int32_t n_fields, const int64_t* ep_ids, int64_t n_ids,
                         int64_t n_src_episodes, pmb_stream stream);
 int pmb_max_t_filled(const int64_t* filled, int64_t B, int32_t T, int64_t filled_sb, int64_t* out, pmb_stream stream);
+
+/* pmb_batch_update: EpisodeBatch.update(data, bs, ts, mark_filled) (components/episode_buffer.py:98-154) for a batch that
+ * lives in HBM, every field of the call in ONE launch.  Source field f is a dense device array [nb][nt][cell_bytes]; cell
+ * (i, j) is written to episode b(i) = b_index[i] (device array, may be NULL: b0 + i * b_step), timestep t0 + j of the
+ * destination field (byte strides given).  onehot_dim > 0 fuses the OneHot preprocess (components/transforms.py:12-21,
+ * `preprocess = {"actions": ("actions_onehot", [OneHot(n_actions)])}`, run.py:133-135): the source cell holds int64
+ * indices [G] and the destination cell is float32 [G][onehot_dim].  filled (may be NULL): filled[b][t] = 1 for every
+ * written cell (mark_filled).  `fields` is a HOST array of at most 12 entries; n_rows = episodes in the destination. */
+typedef struct pmb_update_field {
+    const void* src;
+    void* dst;
+    int64_t cell_bytes;
+    int64_t dst_batch_stride_bytes;
+    int64_t dst_time_stride_bytes;         /* 0 for episode-constant fields */
+    int32_t onehot_dim;
+    int32_t reserved;
+} pmb_update_field;
+int pmb_batch_update(const pmb_update_field* fields_host, int32_t n_fields, const int64_t* b_index, int64_t b0, int64_t b_step,
+                     int64_t nb, int64_t n_rows, int64_t t0, int64_t nt, int64_t* filled, int64_t filled_sb, pmb_stream stream);
 
 /* Strided host -> device copy of `rows` pieces of `row_bytes` (source pitch `src_pitch_bytes`, destination dense):
  * one cudaMemcpy2DAsync.  Replaces the per-timestep `.to(self.args.device)` of a host-resident runner batch

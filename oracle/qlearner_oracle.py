@@ -113,7 +113,7 @@ def mac_unroll(p, batch, obs_last_action=True, obs_agent_id=True, keep_cache=Fal
 # ----------------------------------------------------------------------------------------
 # chosen-action gather, target masking, double-Q  (learners/q_learner.py:55-78)
 # ----------------------------------------------------------------------------------------
-def target_select(mac_out, target_mac_out_full, avail, actions, double_q=True):
+def target_select(mac_out, target_mac_out_full, avail, actions, double_q=True, cur_max_override=None):
     """mac_out, target_mac_out_full: [B, T, N, A]; avail [B, T, N, A]; actions [B, T, N, 1].
     Returns chosen [B, T-1, N], target_max [B, T-1, N], cur_max_actions [B, T-1, N] (int64;
     argmax ties -> lowest index like torch CPU).  The target net's t == 0 output is dropped
@@ -125,6 +125,8 @@ def target_select(mac_out, target_mac_out_full, avail, actions, double_q=True):
         qd = mac_out.copy()
         qd[avail == 0] = MASK_VALUE
         cur_max = qd[:, 1:].argmax(axis=3)
+        if cur_max_override is not None:          # referee runs: the arg-max decisions of another (lower precision) run
+            cur_max = np.asarray(cur_max_override).astype(cur_max.dtype)
         tmax = np.take_along_axis(tq, cur_max[..., None], axis=3)[..., 0]
     else:
         cur_max = tq.argmax(axis=3)
@@ -159,18 +161,21 @@ def qmixer_forward(mp, agent_qs, states, cache=None):
     return y.reshape(B, -1, 1)
 
 
-def qmixer_backward(mp, cache, g):
+def qmixer_backward(mp, cache, g, decisions=None):
     """Gradient of qmixer_forward w.r.t. mixer parameters and agent_qs, given g = dL/dq_tot
     [M, 1] (what autograd does at learners/q_learner.py:101: d|x| = sign(x), dELU = 1 if
-    pre > 0 else exp(pre), dReLU = (x > 0); no gradient flows to the state)."""
+    pre > 0 else exp(pre), dReLU = (x > 0); no gradient flows to the state).
+    `decisions` (referee runs only): the discontinuous derivative choices of another run - sign_w1 [M, N*E],
+    sign_wf [M, E], v0_mask [M, E] - used instead of this run's own."""
     c = cache
+    dec = decisions or {}
     N, E = c["w1"].shape[1:]
     g = g.reshape(-1, 1)
     d_hidden = g * c["wf"]
-    d_raw_wf = np.sign(c["raw_wf"]) * (g * c["hidden"])
-    d_v0pre = (c["v0pre"] > 0) * (g * mp["V.2.weight"])
+    d_raw_wf = dec.get("sign_wf", np.sign(c["raw_wf"])) * (g * c["hidden"])
+    d_v0pre = dec.get("v0_mask", c["v0pre"] > 0) * (g * mp["V.2.weight"])
     d_pre = d_hidden * np.where(c["pre"] > 0, 1.0, np.exp(np.minimum(c["pre"], 0))).astype(g.dtype)
-    d_raw_w1 = (np.sign(c["raw_w1"]).reshape(-1, N, E) * c["q"][:, :, None] * d_pre[:, None, :]).reshape(-1, N * E)
+    d_raw_w1 = (dec.get("sign_w1", np.sign(c["raw_w1"])).reshape(-1, N, E) * c["q"][:, :, None] * d_pre[:, None, :]).reshape(-1, N * E)
     d_q = np.einsum("mne,me->mn", c["w1"], d_pre)
     s = c["s"]
     grads = {
@@ -191,10 +196,11 @@ def vdn_forward(agent_qs):
 # ----------------------------------------------------------------------------------------
 # agent backward (BPTT) - what loss.backward() does through learners/q_learner.py:47-55
 # ----------------------------------------------------------------------------------------
-def agent_bptt(p, cache, actions, d_chosen, B, N):
+def agent_bptt(p, cache, actions, d_chosen, B, N, relu_mask=None):
     """d_chosen [B, T-1, N] = dL/d chosen_action_qvals.  Gradient reaches mac_out only at
     the taken action for t < T-1 (gather, :55); the double-Q argmax path is detached (:73).
-    Returns grads for the 8 agent tensors."""
+    Returns grads for the 8 agent tensors.  `relu_mask` [T, B*N, H] (referee runs only): the ReLU
+    decisions (x > 0) of another run, used instead of this run's own."""
     T = len(cache)
     H = p["fc1.weight"].shape[0]
     A = p["fc2.weight"].shape[0]
@@ -224,7 +230,7 @@ def agent_bptt(p, cache, actions, d_chosen, B, N):
         g["rnn.bias_hh"] += dgh.sum(0)
         dx = dgi @ p["rnn.weight_ih"]
         dh_next = dh * z + dgh @ p["rnn.weight_hh"]
-        dpre1 = dx * (c["x"] > 0)
+        dpre1 = dx * ((c["x"] > 0) if relu_mask is None else relu_mask[t])
         g["fc1.weight"] += dpre1.T @ c["inputs"]
         g["fc1.bias"] += dpre1.sum(0)
     return g
@@ -279,7 +285,7 @@ class OracleQLearner:
         self.stats = {}
         self.n_target_updates = 0
 
-    def forward_loss(self, batch, keep_cache=True):
+    def forward_loss(self, batch, keep_cache=True, cur_max_override=None):
         """q_learner.py:39-97.  Returns a dict with every intermediate the tests compare."""
         a = self.args
         dt = self.agent["fc1.weight"].dtype
@@ -293,7 +299,7 @@ class OracleQLearner:
 
         mac_out, cache = mac_unroll(self.agent, batch, ola, oid, keep_cache)
         target_out, _ = mac_unroll(self.target_agent, batch, ola, oid, False)
-        chosen, tmax, cur_max = target_select(mac_out, target_out, avail, batch["actions"], a.double_q)
+        chosen, tmax, cur_max = target_select(mac_out, target_out, avail, batch["actions"], a.double_q, cur_max_override)
 
         mcache = {}
         if self.mixer == "qmix":
@@ -316,29 +322,32 @@ class OracleQLearner:
                     td=td, mask=mask_e, masked_td=masked_td, mask_sum=mask_sum, loss=loss,
                     cache=cache, mcache=mcache, actions=actions)
 
-    def backward(self, fw, batch):
-        """loss.backward() (q_learner.py:100-101) by hand."""
+    def backward(self, fw, batch, decisions=None):
+        """loss.backward() (q_learner.py:100-101) by hand.  `decisions`: see qmixer_backward / agent_bptt."""
+        dec = decisions or {}
         B, T, N = batch["obs"].shape[:3]
         g_tot = 2.0 * fw["masked_td"] * fw["mask"] / fw["mask_sum"]        # dL/dq_tot
         grads = {}
         if self.mixer == "qmix":
-            mg, d_q = qmixer_backward(self.mixer_p, fw["mcache"], g_tot.reshape(-1, 1))
+            mg, d_q = qmixer_backward(self.mixer_p, fw["mcache"], g_tot.reshape(-1, 1), dec)
             grads.update({"mixer." + k: v for k, v in mg.items()})
             d_chosen = d_q.reshape(B, T - 1, N)
         elif self.mixer == "vdn":
             d_chosen = np.broadcast_to(g_tot, (B, T - 1, N)).copy()
         else:
             d_chosen = g_tot
-        ag = agent_bptt(self.agent, fw["cache"], batch["actions"], d_chosen.astype(g_tot.dtype), B, N)
+        ag = agent_bptt(self.agent, fw["cache"], batch["actions"], d_chosen.astype(g_tot.dtype), B, N, dec.get("relu_mask"))
         grads.update({"agent." + k: v for k, v in ag.items()})
         return grads
 
-    def train(self, batch, t_env, episode_num):
+    def train(self, batch, t_env, episode_num, decisions=None):
         """q_learner.py:37-116.  Returns the 5 logged scalars (always, not only when the
-        log interval fires) plus the gradients for inspection."""
+        log interval fires) plus the gradients for inspection.  `decisions` (referee runs only): the
+        discontinuous choices of another run (cur_max, relu_mask, sign_w1, sign_wf, v0_mask)."""
         a = self.args
-        fw = self.forward_loss(batch)
-        grads = self.backward(fw, batch)
+        dec = decisions or {}
+        fw = self.forward_loss(batch, cur_max_override=dec.get("cur_max"))
+        grads = self.backward(fw, batch, dec)
         names = ["agent." + k for k in AGENT_PARAM_NAMES]
         if self.mixer == "qmix":
             names += ["mixer." + k for k in QMIX_PARAM_NAMES]

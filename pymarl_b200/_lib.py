@@ -23,6 +23,7 @@ PARAM_ORDER = [  # enum pmb_param_id
 ]
 STAT_IDS = dict(mask_sum=0, td2_sum=1, tdabs_sum=2, qtaken_sum=3, target_sum=4, grad_norm=5, loss=6, clip_coef=7)
 STATS_LEN = 16
+DP_TAIL_FLOATS = 16          # PMB_DP_TAIL_FLOATS
 
 
 class Dims(C.Structure):
@@ -57,6 +58,11 @@ class GatherField(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes_per_episode", C.c_int64)]
 
 
+class UpdateField(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("cell_bytes", C.c_int64), ("dst_batch_stride_bytes", C.c_int64),
+                ("dst_time_stride_bytes", C.c_int64), ("onehot_dim", C.c_int32), ("reserved", C.c_int32)]
+
+
 class WsViews(C.Structure):
     _names = ("x_on", "x_tg", "h_stash", "gates", "q_on", "q_tg", "chosen", "tmax", "raw_on", "raw_tg",
               "q_tot", "t_tot", "g", "d_chosen", "scratch")
@@ -79,6 +85,8 @@ _SIGS = {
     "pmb_profile_begin": (C.c_int, []),
     "pmb_profile_end": (C.c_int, [C.POINTER(C.c_float), C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "pmb_gather_episodes": (C.c_int, [C.POINTER(GatherField), C.c_int32, _P, C.c_int64, C.c_int64, _P]),
+    "pmb_batch_update": (C.c_int, [C.POINTER(UpdateField), C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                   C.c_int64, _P, C.c_int64, _P]),
     "pmb_max_t_filled": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P]),
     "pmb_h2d_rows": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "pmb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)]),
@@ -98,6 +106,8 @@ _SIGS = {
     "pmb_agent_unroll_bwd": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "pmb_clip_rmsprop_update": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int32, _P, C.c_float, C.c_float, C.c_float,
                                           C.c_float, _P, _P]),
+    "pmb_dp_pack": (C.c_int, [C.c_int64, _P, _P, _P]),
+    "pmb_dp_unpack": (C.c_int, [C.c_int64, _P, _P, _P]),
     "pmb_epsilon_greedy": (C.c_int, [C.c_int64, C.c_int32, _P, _P, C.c_float, _P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "pmb_select_actions_workspace_bytes": (C.c_int64, [C.POINTER(Dims)]),
     "pmb_select_actions_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.c_int32, _P, _P, C.c_float, _P, _P,

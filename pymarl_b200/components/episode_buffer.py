@@ -72,6 +72,8 @@ class EpisodeBatch:
     # ---- writes ---------------------------------------------------------------------------
     def update(self, data, bs=slice(None), ts=slice(None), mark_filled=True):
         slices = self._parse_slices((bs, ts))
+        if self._update_on_device(data, slices, mark_filled):
+            return
         for k, v in data.items():
             if k in self.data.transition_data:
                 store, sl = self.data.transition_data, tuple(slices)
@@ -94,6 +96,84 @@ class EpisodeBatch:
                 for tr in transforms:
                     out = tr.transform(out)
                 store[new_k][sl] = out.view_as(store[new_k][sl])
+
+    def _update_on_device(self, data, slices, mark_filled):
+        """A batch that lives in HBM: ALL fields of the call, `filled` and the fused OneHot preprocess in ONE launch
+        (pmb_batch_update) instead of one indexed assignment + one scatter per field.  Returns False (caller takes the
+        generic path) for what the kernel does not cover: episode-constant fields, boolean / strided-time indices,
+        preprocess chains other than a single OneHot."""
+        import ctypes as C
+        from .transforms import OneHot
+        store = self.data.transition_data
+        if th.device(self.device).type != "cuda" or not data or len(data) > 8:
+            return False
+        bs, ts = slices
+        some = next(iter(store.values()))
+        n_rows, n_t = some.shape[0], some.shape[1]
+        if not isinstance(ts, slice):
+            return False
+        t0, t1, tstep = ts.indices(n_t)
+        if tstep != 1 or t1 <= t0:
+            return False
+        nt = t1 - t0
+        b_index, b0, b_step = None, 0, 1
+        if isinstance(bs, slice):
+            b0, b1, b_step = bs.indices(n_rows)
+            if b_step < 1:
+                return False
+            nb = max(0, -(-(b1 - b0) // b_step))
+        else:
+            if isinstance(bs, th.Tensor):
+                if bs.dtype == th.bool:
+                    return False
+                b_index = bs.to(device=self.device, dtype=th.int64).reshape(-1).contiguous()
+                lo_hi = (int(b_index.min()), int(b_index.max())) if b_index.numel() else (0, 0)
+            else:
+                arr = np.asarray(bs)
+                if arr.dtype == np.bool_ or arr.ndim != 1:
+                    return False
+                lo_hi = (int(arr.min()), int(arr.max())) if arr.size else (0, 0)
+                b_index = th.as_tensor(arr.astype(np.int64)).to(self.device)
+            nb = int(b_index.numel())
+            if nb and (lo_hi[0] < -n_rows or lo_hi[1] >= n_rows):
+                raise IndexError("episode index out of range")
+            if nb and lo_hi[0] < 0:
+                b_index = th.where(b_index < 0, b_index + n_rows, b_index)
+        if nb == 0:
+            return True
+        from .. import _lib
+        descs, keep = [], []
+        for k, v in data.items():
+            if k not in store:
+                return False
+            dest = store[k]
+            if not dest[0, 0].is_contiguous():
+                return False
+            dtype = self.scheme[k].get("dtype", th.float32)
+            v = th.as_tensor(v, dtype=dtype, device=self.device) if not isinstance(v, th.Tensor) \
+                else v.to(device=self.device, dtype=dtype)
+            cell = dest[0, 0].numel()
+            self._check_safe_view(v, SimpleNamespace(shape=(nb, nt) + tuple(dest.shape[2:])))
+            if v.numel() != nb * nt * cell:
+                raise ValueError("Unsafe reshape of {} to {}".format(tuple(v.shape), (nb, nt) + tuple(dest.shape[2:])))
+            v = v.reshape(nb, nt, cell).contiguous()
+            keep.append(v)
+            es = dest.element_size()
+            descs.append(_lib.UpdateField(v.data_ptr(), dest.data_ptr(), cell * es, dest.stride(0) * es, dest.stride(1) * es, 0, 0))
+            if k in self.preprocess:
+                new_k, transforms = self.preprocess[k]
+                if len(transforms) != 1 or not isinstance(transforms[0], OneHot) or dtype != th.int64 \
+                        or store[new_k].dtype != th.float32 or store[new_k][0, 0].numel() != cell * transforms[0].out_dim:
+                    return False
+                oh = store[new_k]
+                descs.append(_lib.UpdateField(v.data_ptr(), oh.data_ptr(), cell * 8, oh.stride(0) * 4, oh.stride(1) * 4,
+                                              transforms[0].out_dim, 0))
+        arr = (_lib.UpdateField * len(descs))(*descs)
+        filled = store["filled"] if mark_filled else None
+        _lib.check(_lib.lib().pmb_batch_update(arr, len(descs), _lib.ptr(b_index), b0, b_step, nb, n_rows, t0, nt,
+                                               _lib.ptr(filled), filled.stride(0) if filled is not None else 0,
+                                               _lib.stream_ptr(some.device)), "pmb_batch_update")
+        return True
 
     @staticmethod
     def _check_safe_view(v, dest):

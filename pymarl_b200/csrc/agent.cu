@@ -475,7 +475,7 @@ int launch_fwd(const AgentParams& p, int A, int64_t R, int nt, const float* x, c
                float* gates, float* q, float* h_last, cudaStream_t s) {
     size_t bytes = FwdSmem<H, RW>::floats(A) * sizeof(float);
     auto kern = gru_unroll_fwd_kernel<H, RW>;
-    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    PMB_SMEM_ATTR(kern, (int)bytes);
     unsigned grid = (unsigned)ceil_div(R, 16 * RW);
     kern<<<grid, NT, bytes, s>>>(p, A, R, nt, x, h0, h_stash, gates, q, h_last);
     PMB_LAUNCH_CHECK("gru_unroll_fwd_kernel");
@@ -488,7 +488,7 @@ int launch_bwd(const AgentParams& p, int A, int N, int T, int64_t R, const float
                cudaStream_t s) {
     size_t bytes = BwdSmem<H, RW>::floats(A) * sizeof(float);
     auto kern = gru_unroll_bwd_kernel<H, RW>;
-    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    PMB_SMEM_ATTR(kern, (int)bytes);
     unsigned grid = (unsigned)ceil_div(R, 16 * RW);
     kern<<<grid, NT, bytes, s>>>(p, A, N, T, R, x, h_stash, gates, d_chosen, actions, actions_sb, dpre1);
     PMB_LAUNCH_CHECK("gru_unroll_bwd_kernel");
@@ -564,7 +564,7 @@ int scatter_grads_dispatch(const pmb_dims* d, const pmb_batch* b, const float* h
 #define PMB_SC(HH)                                                                                                \
     {                                                                                                             \
         auto kern = agent_scatter_grads_kernel<HH>;                                                               \
-        PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        PMB_SMEM_ATTR(kern, (int)smem);             \
         kern<<<n_cta, NT, smem, s>>>(d->A, d->N, d->T, R, h_stash, dpre1, d_chosen, b->actions, b->actions_sb,    \
                                      b->filled, b->filled_sb, d->obs_last_action, d->obs_agent_id, items_per_cta, \
                                      partial, ti_tiles);                                                          \

@@ -2,6 +2,9 @@
 // the whole learner step (learners/q_learner.py:37-107).
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "gru_tc.cuh"
@@ -32,6 +35,8 @@ int launch_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mi
 int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
                    float* g_out, double* stats, cudaStream_t s);
 int launch_stats_reset(double* stats, cudaStream_t s);
+int launch_dp_pack(const double* stats, float* tail, cudaStream_t s);
+int launch_dp_unpack(const float* tail, double* stats, cudaStream_t s);
 int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target, int do_sync, double* stats, float lr,
                         float alpha, float eps, float clip, float* scratch, cudaStream_t s);
 
@@ -48,29 +53,28 @@ int64_t tc_atb_ti_scratch_bytes(int T, int n_tiles, int K);
 int64_t tc_fc1_scratch_bytes(const pmb_dims* d);
 
 static thread_local char g_err[512] = "";
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 // ---- optional per-phase timing (pmb_profile_begin / pmb_profile_end) --------------------------
 // When armed, the step records a CUDA event on the launch stream between its kernels; the
 // host reads the elapsed times after the step.  Disarmed (the default) it costs one branch.
-constexpr int kMaxPhases = 48;
+// Per host thread (the thread that arms the timer is the thread that launches); up to kMaxPhases phases per
+// begin/end pair, i.e. several steps of the learner can be profiled back to back inside one timed region.
+constexpr int kMaxPhases = 1024;
 struct PhaseTimer {
     bool armed = false;
     int n = 0;
+    int created = 0;                       // events created so far (lazily, only as many as are used)
     cudaEvent_t ev[kMaxPhases + 1];
     const char* name[kMaxPhases];
-    bool created = false;
 };
-static PhaseTimer g_timer;
+static thread_local PhaseTimer g_timer;
 
 static void phase_mark(cudaStream_t s, const char* name) {
     PhaseTimer& t = g_timer;
     if (!t.armed) return;
-    if (!t.created) {
-        for (int i = 0; i <= kMaxPhases; ++i) cudaEventCreate(&t.ev[i]);
-        t.created = true;
-    }
     if (t.n > kMaxPhases) return;
+    while (t.created <= t.n) cudaEventCreate(&t.ev[t.created++]);
     cudaEventRecord(t.ev[t.n], s);           // event i closes phase i-1 and opens phase i
     if (t.n < kMaxPhases) t.name[t.n] = name;
     t.n++;
@@ -89,17 +93,34 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return PMB_ERR_CUDA;
 }
 
+// SM count of the CURRENT device (cached per device ordinal)
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;          // B200
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> cached[kMaxDev];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;   // B200
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size) instead of on every launch
+cudaError_t set_smem_attr(const void* func, int bytes) {
+    struct Key { const void* f; int dev, bytes; };
+    static std::mutex mu;
+    static std::vector<Key> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Key& k : done)
+        if (k.f == func && k.dev == dev && k.bytes >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.push_back(Key{func, dev, bytes});
+    return e;
 }
 
 int validate_dims(const pmb_dims* d) {
@@ -326,7 +347,7 @@ int pmb_profile_end(float* ms_host, char* names_host, int32_t names_stride, int3
     t.n = 0;
     return PMB_OK;
 }
-int pmb_version(void) { return 101; }
+int pmb_version(void) { return 200; }
 
 int pmb_h2d_rows(void* dst_dev, const void* src_host, int64_t rows, int64_t row_bytes, int64_t src_pitch_bytes,
                  pmb_stream stream) {
@@ -479,6 +500,16 @@ int pmb_clip_rmsprop_update(int64_t n, float* flat_p, float* flat_g, float* flat
                                grad_norm_clip, scratch, (cudaStream_t)stream);
 }
 
+int pmb_dp_pack(int64_t n, float* flat_g, const double* stats, pmb_stream stream) {
+    PMB_REQUIRE(n > 0 && flat_g && stats, "dp_pack: bad arguments");
+    return launch_dp_pack(stats, flat_g + n, (cudaStream_t)stream);
+}
+
+int pmb_dp_unpack(int64_t n, const float* flat_g, double* stats, pmb_stream stream) {
+    PMB_REQUIRE(n > 0 && flat_g && stats, "dp_unpack: bad arguments");
+    return launch_dp_unpack(flat_g + n, stats, (cudaStream_t)stream);
+}
+
 int pmb_epsilon_greedy(int64_t rows, int32_t A, const float* q, const int32_t* avail, float epsilon, const float* u,
                        const float* expo, uint64_t seed, uint64_t offset, int64_t* actions_out, pmb_stream stream) {
     PMB_REQUIRE(rows >= 0 && A > 0 && q && avail && actions_out, "epsilon_greedy: bad arguments");
@@ -628,7 +659,7 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         // :55-78 fused with fc2 of both nets
         PHASE(s, "q_select_tc");
         if ((rc = tc_q_select(d, b, img(49152), img(57344 + 49152), on.fc2_b, tg.fc2_b, h_ti, hg_ti, n_tiles, v.chosen,
-                              v.tmax, hp->keep_q ? v.q_on : nullptr, hp->keep_q ? v.q_tg : nullptr, s))) return rc;
+                              v.tmax, (hp->keep_q & 1) ? v.q_on : nullptr, (hp->keep_q & 1) ? v.q_tg : nullptr, s))) return rc;
     } else {
         PHASE(s, "fc1_fwd_online");
         if ((rc = fc1_fwd(d, b, 0, d->T, on, v.x_on, s))) return rc;
@@ -667,6 +698,10 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     // :86-97
     PHASE(s, "td_loss");
     if ((rc = launch_td_loss(d, b, v.q_tot, v.t_tot, hp->gamma, v.g, stats, s))) return rc;
+    if (hp->keep_q & 2) {              // debug: forward pass + loss sums only, intermediates stay in the workspace
+        PHASE(s, "end");
+        return PMB_OK;
+    }
     // :100-101 backward
     PHASE(s, "mixer_bwd");
     if (tc_mixer) {

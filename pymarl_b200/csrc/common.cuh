@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/pymarl_b200.h"
 
 namespace pmb {
@@ -16,7 +17,9 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         cudaError_t _e = (call);                                                    \
         if (_e != cudaSuccess) return ::pmb::cuda_fail(_e, #call, __FILE__, __LINE__); \
     } while (0)
-extern long long g_launch_count;     // kernels launched by this library (pmb_launch_count)
+extern std::atomic<long long> g_launch_count;     // kernels launched by this library (pmb_launch_count)
+cudaError_t set_smem_attr(const void* func, int bytes);     // MaxDynamicSharedMemorySize, once per (kernel, device)
+#define PMB_SMEM_ATTR(kern, bytes) PMB_CUDA(::pmb::set_smem_attr(reinterpret_cast<const void*>(kern), (int)(bytes)))
 #define PMB_LAUNCH_CHECK(name)                                                      \
     do {                                                                            \
         ++::pmb::g_launch_count;                                                    \

@@ -760,13 +760,15 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
+        static std::atomic<EncodeFn> encode_cache{nullptr};   // process-wide driver entry point; racing initialisers store the same value
+        EncodeFn encode = encode_cache.load(std::memory_order_acquire);
         if (!encode) {
             void* fn = nullptr;
             cudaDriverEntryPointQueryResult qres;
             PMB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
             if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("tc_gru_fwd: cuTensorMapEncodeTiled not available"); return PMB_ERR_CUDA; }
             encode = reinterpret_cast<EncodeFn>(fn);
+            encode_cache.store(encode, std::memory_order_release);
         }
         const cuuint64_t gdim[2] = {64, (cuuint64_t)P.R};
         const cuuint64_t gstride[1] = {256};
@@ -777,7 +779,7 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { set_error("tc_gru_fwd: cuTensorMapEncodeTiled failed"); return PMB_ERR_CUDA; }
     }
-    PMB_CUDA(cudaFuncSetAttribute(tc::gru_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ro::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::gru_rollout_kernel, tc::ro::SMEM_BYTES);
     const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
     tc::gru_rollout_kernel<<<grid, tc::ro::THREADS, tc::ro::SMEM_BYTES, s>>>(P, av_smem, tmap);
     PMB_LAUNCH_CHECK("gru_rollout_kernel");
@@ -785,7 +787,8 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
 }
 
 
-int64_t tc_agent_dw_scratch_bytes() { return align_up((int64_t)148 * 2 * tc::ad::PARTIAL_FLOATS * 4, 256); }
+// one partial block per CTA of the persistent grid (grid <= SM count of the current device), with 2x head room
+int64_t tc_agent_dw_scratch_bytes() { return align_up((int64_t)sm_count() * 2 * tc::ad::PARTIAL_FLOATS * 4, 256); }
 
 int tc_agent_dw(const pmb_dims* d, const pmb_batch* b, const uint8_t* dpre1_ti, const uint8_t* h_ti, const uint8_t* obs_ti,
                 const float* d_chosen, int n_tiles, float* fc1_w, float* fc1_b, float* fc2_w, float* fc2_b, void* scratch,
@@ -801,7 +804,7 @@ int tc_agent_dw(const pmb_dims* d, const pmb_batch* b, const uint8_t* dpre1_ti, 
     if ((int64_t)grid * tc::ad::PARTIAL_FLOATS * 4 > scratch_bytes) { set_error("tc_agent_dw: scratch too small"); return PMB_ERR_WORKSPACE; }
     P.items_per_cta = ceil_div(P.n_items, grid);
     P.partial = static_cast<float*>(scratch);
-    PMB_CUDA(cudaFuncSetAttribute(tc::agent_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ad::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::agent_dw_tc_kernel, tc::ad::SMEM_BYTES);
     tc::agent_dw_tc_kernel<<<grid, tc::ad::THREADS, tc::ad::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("agent_dw_tc_kernel");
     tc::agent_dw_reduce_kernel<<<(unsigned)ceil_div(tc::ad::PARTIAL_FLOATS, 256), 256, 0, s>>>(

@@ -926,7 +926,7 @@ int tc_gru_fwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, co
     tc::GruFwd2Params P;
     P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.b_ih = b_ih; P.b_hh = b_hh;
     P.x_ti = x_ti; P.h_ti = h_ti; P.g_ti = g_ti; P.R = R; P.nt = nt; P.n_tiles = n_tiles;
-    PMB_CUDA(cudaFuncSetAttribute(tc::gru_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g2::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::gru_fwd2_kernel, tc::g2::SMEM_BYTES);
     tc::gru_fwd2_kernel<<<(n_tiles + 1) / 2, tc::g2::THREADS, tc::g2::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("gru_fwd2_kernel");
     return PMB_OK;
@@ -945,7 +945,7 @@ int tc_q_select(const pmb_dims* d, const pmb_batch* b, const __nv_bfloat16* w2_o
     const int64_t n_items = (int64_t)d->T * n_tiles;
     int grid = 2 * sm_count();
     if (grid > n_items) grid = (int)n_items;
-    PMB_CUDA(cudaFuncSetAttribute(tc::q_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::qs::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::q_select_kernel, tc::qs::SMEM_BYTES);
     tc::q_select_kernel<<<grid, tc::qs::THREADS, tc::qs::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("q_select_kernel");
     return PMB_OK;
@@ -965,7 +965,7 @@ int tc_gru_bwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, co
     P.relu_mask = relu_mask; P.d_chosen = d_chosen; P.actions = actions; P.actions_sb = actions_sb;
     P.partial = partial; P.ep_index = ep_index;
     P.R = R; P.T = T; P.N = N; P.A = A; P.n_tiles = n_tiles;
-    PMB_CUDA(cudaFuncSetAttribute(tc::gru_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::b2::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::gru_bwd2_kernel, tc::b2::SMEM_BYTES);
     tc::gru_bwd2_kernel<<<n_tiles, tc::b2::THREADS, tc::b2::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("gru_bwd2_kernel");
     return PMB_OK;

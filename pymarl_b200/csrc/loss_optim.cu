@@ -62,6 +62,26 @@ __global__ void stats_reset_kernel(double* stats) {
     if (threadIdx.x < PMB_S_COUNT) stats[threadIdx.x] = 0.0;
 }
 
+// Data-parallel exchange: the five double loss sums ride in the tail of the fp32 gradient buffer as (hi, lo) float pairs,
+// so ONE all-reduce(sum, fp32) over [grads | 10 floats] carries everything a step exchanges.  hi + lo reproduces the
+// double to 2^-48; the fp32 sums over <= 8 ranks keep ~1e-7 relative (mask_sum, an integer < 2^24, stays exact).
+__global__ void dp_pack_stats_kernel(const double* __restrict__ stats, float* __restrict__ tail) {
+    const int i = threadIdx.x;
+    if (i < 5) {
+        const double v = stats[i];
+        const float hi = (float)v;
+        tail[2 * i] = hi;
+        tail[2 * i + 1] = (float)(v - (double)hi);
+    } else if (i < PMB_DP_TAIL_FLOATS / 2) {
+        tail[2 * i] = 0.f;
+        tail[2 * i + 1] = 0.f;
+    }
+}
+__global__ void dp_unpack_stats_kernel(const float* __restrict__ tail, double* __restrict__ stats) {
+    const int i = threadIdx.x;
+    if (i < 5) stats[i] = (double)tail[2 * i] + (double)tail[2 * i + 1];
+}
+
 constexpr int OPT_BLOCKS = 256, OPT_THREADS = 256;
 
 // fixed grid-stride assignment -> the partial sums, and their fixed-order total, are deterministic
@@ -138,6 +158,18 @@ int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, co
 int launch_stats_reset(double* stats, cudaStream_t s) {
     stats_reset_kernel<<<1, 32, 0, s>>>(stats);
     PMB_LAUNCH_CHECK("stats_reset_kernel");
+    return PMB_OK;
+}
+
+int launch_dp_pack(const double* stats, float* tail, cudaStream_t s) {
+    dp_pack_stats_kernel<<<1, 32, 0, s>>>(stats, tail);
+    PMB_LAUNCH_CHECK("dp_pack_stats_kernel");
+    return PMB_OK;
+}
+
+int launch_dp_unpack(const float* tail, double* stats, cudaStream_t s) {
+    dp_unpack_stats_kernel<<<1, 32, 0, s>>>(tail, stats);
+    PMB_LAUNCH_CHECK("dp_unpack_stats_kernel");
     return PMB_OK;
 }
 

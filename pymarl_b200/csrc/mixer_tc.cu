@@ -475,7 +475,7 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
     W.raw_img = raw_img; W.state_img = state_img; W.partial = partial;
     W.n_cblk = tc_mix_cblks(d); W.n_chunks = tc_state_chunks(d); W.n_ct = p.n_ct; W.n_kt = p.n_kt; W.ldk = p.ldk;
     W.n_halves = p.n_halves; W.halves_per_slice = p.halves_per_slice;
-    PMB_CUDA(cudaFuncSetAttribute(tc::mix_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::md::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::mix_dw_tc_kernel, tc::md::SMEM_BYTES);
     tc::mix_dw_tc_kernel<<<p.n_ct * p.n_kt * p.slices, tc::md::THREADS, tc::md::SMEM_BYTES, s>>>(W);
     PMB_LAUNCH_CHECK("mix_dw_tc_kernel");
     const int64_t total = (int64_t)(d->N + 3) * 32 * (d->S + 1);

@@ -71,6 +71,66 @@ __global__ void __launch_bounds__(256) max_t_filled_kernel(const int64_t* __rest
     if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(out, (unsigned long long)s);
 }
 
+// ---- EpisodeBatch.update on the device -------------------------------------------
+// One launch writes every field of an `update(data, bs, ts)` call (components/episode_buffer.py:98-154): cell (i, j) of
+// the dense source [nb][nt][cell] goes to episode row(i) / timestep t0 + j of the destination field; `filled` is marked;
+// the OneHot preprocess (transforms.py:12-21) is fused: an int64 index cell [G][1] becomes a float32 cell [G][dim].
+constexpr int UPDATE_MAX_FIELDS = 12;
+struct UpdateArgs {
+    const char* src[UPDATE_MAX_FIELDS];
+    char* dst[UPDATE_MAX_FIELDS];
+    int64_t cell[UPDATE_MAX_FIELDS];         // bytes of one source cell
+    int64_t sb[UPDATE_MAX_FIELDS];           // destination batch stride (bytes)
+    int64_t st[UPDATE_MAX_FIELDS];           // destination time stride (bytes; 0: episode-constant field)
+    int32_t vec[UPDATE_MAX_FIELDS];
+    int32_t onehot[UPDATE_MAX_FIELDS];       // > 0: fused OneHot of this width
+    int32_t n_fields;
+    const int64_t* b_index;                  // device ids of the nb episodes, or NULL: b0 + i * b_step
+    int64_t b0, b_step, nb, n_rows, t0, nt;
+    int64_t* filled; int64_t filled_sb;      // elements
+};
+
+template <typename V>
+__device__ __forceinline__ void copy_cell(const char* __restrict__ s, char* __restrict__ d, int64_t n_vec) {
+    const V* sv = reinterpret_cast<const V*>(s);
+    V* dv = reinterpret_cast<V*>(d);
+    for (int64_t i = threadIdx.x; i < n_vec; i += blockDim.x) dv[i] = sv[i];
+}
+
+// one block per (episode i, timestep j) cell
+__global__ void __launch_bounds__(128) batch_update_kernel(UpdateArgs A) {
+    const int64_t c = blockIdx.x;
+    const int64_t i = c / A.nt, j = c - i * A.nt;
+    const int64_t b = A.b_index ? A.b_index[i] : A.b0 + i * A.b_step;
+    if (b < 0 || b >= A.n_rows) return;                   // checked on the host as well
+    const int64_t t = A.t0 + j;
+    if (A.filled && threadIdx.x == 0) A.filled[b * A.filled_sb + t] = 1;
+    for (int f = 0; f < A.n_fields; ++f) {
+        const char* s = A.src[f] + c * A.cell[f];
+        char* d = A.dst[f] + b * A.sb[f] + t * A.st[f];
+        if (A.onehot[f] > 0) {
+            const int dim = A.onehot[f];
+            const int64_t G = A.cell[f] / 8;              // int64 indices in the cell
+            const int64_t* idx = reinterpret_cast<const int64_t*>(s);
+            float* o = reinterpret_cast<float*>(d);
+            for (int64_t e = threadIdx.x; e < G * dim; e += blockDim.x) {
+                const int64_t g = e / dim;
+                o[e] = (idx[g] == e - g * dim) ? 1.f : 0.f;
+            }
+        } else {
+            switch (A.vec[f]) {
+                case 16: copy_cell<uint4>(s, d, A.cell[f] / 16); break;
+                case 8: copy_cell<uint2>(s, d, A.cell[f] / 8); break;
+                case 4: copy_cell<uint32_t>(s, d, A.cell[f] / 4); break;
+                default: copy_cell<uint8_t>(s, d, A.cell[f]); break;
+            }
+        }
+        // fields are applied in call order like the reference's loop over data.items(): a later field that targets the same
+        // cells (insert_episode_batch copies actions_onehot AFTER the preprocess of actions produced it) wins
+        __syncthreads();
+    }
+}
+
 }  // namespace
 }  // namespace pmb
 
@@ -105,6 +165,31 @@ int pmb_gather_episodes(const pmb_gather_field* fields, int32_t n_fields, const 
     dim3 grid((unsigned)bx, (unsigned)n_ids);
     gather_episodes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
     PMB_LAUNCH_CHECK("gather_episodes_kernel");
+    return PMB_OK;
+}
+
+int pmb_batch_update(const pmb_update_field* fields, int32_t n_fields, const int64_t* b_index, int64_t b0, int64_t b_step,
+                     int64_t nb, int64_t n_rows, int64_t t0, int64_t nt, int64_t* filled, int64_t filled_sb, pmb_stream stream) {
+    PMB_REQUIRE(fields && n_fields > 0 && n_fields <= UPDATE_MAX_FIELDS, "batch_update: 1..%d fields", UPDATE_MAX_FIELDS);
+    PMB_REQUIRE(nb >= 0 && nt > 0 && t0 >= 0 && n_rows > 0 && nb * nt < ((int64_t)1 << 31), "batch_update: bad index range");
+    PMB_REQUIRE(b_index || (b0 >= 0 && b_step > 0 && b0 + (nb - 1) * b_step < n_rows), "batch_update: episode range outside the batch");
+    if (nb == 0) return PMB_OK;
+    UpdateArgs A;
+    A.n_fields = n_fields; A.b_index = b_index; A.b0 = b0; A.b_step = b_step; A.nb = nb; A.n_rows = n_rows; A.t0 = t0; A.nt = nt;
+    A.filled = filled; A.filled_sb = filled_sb;
+    for (int f = 0; f < n_fields; ++f) {
+        const pmb_update_field& u = fields[f];
+        PMB_REQUIRE(u.src && u.dst && u.cell_bytes > 0, "batch_update: field %d is empty", f);
+        PMB_REQUIRE(u.onehot_dim <= 0 || u.cell_bytes % 8 == 0, "batch_update: a one-hot source cell holds int64 indices");
+        A.src[f] = static_cast<const char*>(u.src); A.dst[f] = static_cast<char*>(u.dst);
+        A.cell[f] = u.cell_bytes; A.sb[f] = u.dst_batch_stride_bytes; A.st[f] = u.dst_time_stride_bytes;
+        A.onehot[f] = u.onehot_dim;
+        const uintptr_t bits = reinterpret_cast<uintptr_t>(u.src) | reinterpret_cast<uintptr_t>(u.dst) | (uintptr_t)u.cell_bytes |
+                               (uintptr_t)u.dst_batch_stride_bytes | (uintptr_t)u.dst_time_stride_bytes;
+        A.vec[f] = (bits & 15) == 0 ? 16 : ((bits & 7) == 0 ? 8 : ((bits & 3) == 0 ? 4 : 1));
+    }
+    batch_update_kernel<<<(unsigned)(nb * nt), 128, 0, (cudaStream_t)stream>>>(A);
+    PMB_LAUNCH_CHECK("batch_update_kernel");
     return PMB_OK;
 }
 

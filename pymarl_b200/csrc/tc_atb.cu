@@ -340,7 +340,7 @@ int tc_gemm_atb(const float* D, RowMap dmap, int C, const float* A, RowMap amap,
     P.partial = static_cast<float*>(scratch);
     P.tile_w = tc_atb_tile_w(K);
     P.d_ti = nullptr; P.ti_T = P.ti_N = P.ti_n_tiles = 0; P.ti_R = 0;
-    PMB_CUDA(cudaFuncSetAttribute(tc::tc_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::atb::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::tc_atb_kernel, tc::atb::SMEM_BYTES);
     dim3 grid((unsigned)ceil_div(K + 1, P.tile_w), (unsigned)ceil_div(C, tc::atb::BC), (unsigned)slices);
     tc::tc_atb_kernel<<<grid, tc::atb::THREADS, tc::atb::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("tc_atb_kernel");
@@ -363,7 +363,7 @@ int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, co
     P.partial = static_cast<float*>(scratch);
     P.tile_w = tc_atb_tile_w(K);
     P.d_ti = d_ti; P.ti_T = T; P.ti_N = N; P.ti_n_tiles = n_tiles; P.ti_R = R;
-    PMB_CUDA(cudaFuncSetAttribute(tc::tc_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::atb::SMEM_BYTES));
+    PMB_SMEM_ATTR(tc::tc_atb_kernel, tc::atb::SMEM_BYTES);
     dim3 grid((unsigned)ceil_div(K + 1, P.tile_w), 1, (unsigned)slices);
     tc::tc_atb_kernel<<<grid, tc::atb::THREADS, tc::atb::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("tc_atb_kernel<ti>");

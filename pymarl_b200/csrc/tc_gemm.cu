@@ -489,7 +489,7 @@ template <class Epi>
 int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
     if (P.M <= 0) return PMB_OK;
     auto kern = tc_gemm_kernel<Epi>;
-    PMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + Epi::EXTRA_SMEM));
+    PMB_SMEM_ATTR(kern, SMEM_BYTES + Epi::EXTRA_SMEM);
     int64_t n_tiles = (P.M + BM - 1) / BM;
     int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     kern<<<grid, THREADS, SMEM_BYTES + Epi::EXTRA_SMEM, s>>>(P, epi);
@@ -1084,7 +1084,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
 #define PMB_FC1_STREAM_LAUNCH(NC)                                                                                            \
     case NC:                                                                                                                 \
-        PMB_CUDA(cudaFuncSetAttribute(tc::fc1_stream_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need)); \
+        PMB_SMEM_ATTR(tc::fc1_stream_kernel<NC>, (int)smem_need); \
         tc::fc1_stream_kernel<NC><<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q);                                       \
         break;
             switch (n_chunks) {

@@ -7,8 +7,9 @@ RMSprop and the hard target sync.  Parameters, gradients, RMSprop state and targ
 parameters live in four flat fp32 buffers; the nn.Parameters (reference names) are views.
 
 Data parallel: with torch.distributed initialised (one process per GPU, NCCL) every rank
-trains on its shard of the episodes; the un-normalised gradients and the five loss sums are
-all-reduced once per step and every rank applies the identical update.
+trains on its shard of the episodes (train() slices the sampled batch itself); the un-normalised
+gradients and the five loss sums travel in ONE all-reduce per step and every rank applies the
+identical update.  args.cuda_graph = True replays the whole step as one CUDA graph.
 """
 import copy
 import ctypes as C
@@ -80,6 +81,8 @@ class QLearner:
         self._flat = None               # dict(p, g, sq, target, layout, key)
         self._workspace = None
         self._stats = None
+        self._dp_scratch = None         # 4096 floats for the replicated clip + RMSprop of the data-parallel path
+        self._graphs = {}               # CUDA graphs of the step (args.cuda_graph)
         self.last_stats = None          # device tensor [16] float64 of the latest step
 
     # ---- flat storage -----------------------------------------------------------------------
@@ -111,7 +114,9 @@ class QLearner:
             if ok:
                 return f
         n = layout.n_total
-        new = dict(p=th.zeros(n, dtype=th.float32, device=dev), g=th.zeros(n, dtype=th.float32, device=dev),
+        # the gradient buffer carries PMB_DP_TAIL_FLOATS extra floats: the loss sums of the data-parallel exchange
+        new = dict(p=th.zeros(n, dtype=th.float32, device=dev),
+                   g=th.zeros(n + _lib.DP_TAIL_FLOATS, dtype=th.float32, device=dev),
                    sq=th.zeros(n, dtype=th.float32, device=dev), target=th.zeros(n, dtype=th.float32, device=dev),
                    layout=layout)
         _flat.bind(new["p"], layout, self.mac.agent, "agent", grad=new["g"])
@@ -128,6 +133,7 @@ class QLearner:
             sq_views.append(view)
         self.optimiser.square_avg = sq_views
         self._flat = new
+        self._graphs = {}
         return new
 
     def _ensure_workspace(self, dims, dev):
@@ -166,52 +172,85 @@ class QLearner:
         return out
 
     # ---- the step ---------------------------------------------------------------------------
+    def _step_fields(self, batch, names, dev, dp):
+        """The tensors one step reads: (fields, ep_index, B, T).  With data parallelism active (and unless
+        args.dp_shard_batch is False: the caller already passes rank-local episodes) every rank keeps the contiguous
+        episode slice data_parallel.shard_slice gives it - views, or a slice of the sampled ids for a zero-copy replay
+        sample; a host-resident batch is sliced BEFORE the H2D copy (run.py:214), so each rank transfers 1/world of it."""
+        lo = hi = None
+        if dp and getattr(self.args, "dp_shard_batch", True):
+            lo, hi = data_parallel.shard_slice(batch.batch_size, data_parallel.rank(), data_parallel.world_size())
+        fields, ep_index = {}, None
+        if hasattr(batch, "ep_ids") and hasattr(batch, "buffer"):
+            # zero-copy replay sample (IndexedEpisodeBatch): the kernels read the buffer's episodes in place
+            ep_index = batch.ep_ids if lo is None else batch.ep_ids[lo:hi]
+            for k in names:
+                fields[k] = batch.buffer.data.transition_data[k]
+            return fields, ep_index, int(ep_index.numel()), batch.max_seq_length
+        for k in names:
+            t = batch[k]
+            if lo is not None:
+                t = t[lo:hi]
+            fields[k] = t if t.is_cuda else t.to(dev, non_blocking=True)       # host batch: H2D here (run.py:214)
+        obs = fields["obs"]
+        return fields, None, obs.shape[0], obs.shape[1]
+
+    def _launch(self, dims, pb, hp, f, need, dev, dp):
+        """The device work of one step on the current stream: ONE C call; with data parallelism the exchange
+        (pack -> one all-reduce -> unpack) and the replicated update follow."""
+        L = _lib.lib()
+        s = _lib.stream_ptr(dev)
+        n = f["layout"].n_total
+        if dims.B > 0:
+            _lib.check(L.pmb_qlearner_train_step(C.byref(dims), C.byref(pb), C.byref(hp), _lib.ptr(f["p"]),
+                                                 _lib.ptr(f["g"]), _lib.ptr(f["sq"]), _lib.ptr(f["target"]),
+                                                 _lib.ptr(self._workspace), need, _lib.ptr(self._stats), s),
+                       "pmb_qlearner_train_step")
+        else:                                   # a rank without episodes still takes part in the exchange
+            f["g"].zero_()
+            self._stats.zero_()
+        if dp:
+            # one exchange per step: [gradients of sum((td*mask)^2) | the five loss sums as (hi, lo) floats]
+            _lib.check(L.pmb_dp_pack(n, _lib.ptr(f["g"]), _lib.ptr(self._stats), s), "pmb_dp_pack")
+            data_parallel.allreduce_step(f["g"])
+            _lib.check(L.pmb_dp_unpack(n, _lib.ptr(f["g"]), _lib.ptr(self._stats), s), "pmb_dp_unpack")
+            _lib.check(L.pmb_clip_rmsprop_update(n, _lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["sq"]),
+                                                 _lib.ptr(f["target"]), hp.do_target_sync, _lib.ptr(self._stats), hp.lr,
+                                                 hp.alpha, hp.eps, hp.grad_norm_clip, _lib.ptr(self._dp_scratch), s),
+                       "pmb_clip_rmsprop_update")
+
     def train(self, batch, t_env: int, episode_num: int):
         a = self.args
         f = self._ensure_flat()
         dev = f["p"].device
         keep = []
-        fields = {}
         names = ["obs", "actions", "avail_actions", "reward", "terminated", "filled"]
         if a.mixer == "qmix":
             names.append("state")
-        ep_index = None
-        if hasattr(batch, "ep_ids") and hasattr(batch, "buffer"):
-            # zero-copy replay sample (IndexedEpisodeBatch): the kernels read the buffer's episodes in place
-            ep_index = batch.ep_ids
-            for k in names:
-                fields[k] = batch.buffer.data.transition_data[k]
-        else:
-            for k in names:
-                t = batch[k]
-                fields[k] = t if t.is_cuda else t.to(dev, non_blocking=True)   # host batch: H2D here (run.py:214)
+        dp = data_parallel.is_active() and getattr(a, "data_parallel", True)
+        fields, ep_index, B, T = self._step_fields(batch, names, dev, dp)
         obs = fields["obs"]
-        B, T, N, O = obs.shape
-        if ep_index is not None:
-            B, T = batch.batch_size, batch.max_seq_length
-        S = fields["state"].shape[-1] if "state" in fields else 1
-        dims = self._layout_dims(B=B, T=T, O=O, S=S)
+        N, O = obs.shape[2], obs.shape[3]
+        S = 1
+        if "state" in fields:
+            for dim in fields["state"].shape[2:]:            # like QMixer: state_dim = prod(state_shape) (qmix.py:13)
+                S *= int(dim)
+        dims = self._layout_dims(B=max(B, 1), T=T, O=O, S=S)
+        dims.B = B
         pb = _lib.make_batch(fields, need_state=(a.mixer == "qmix"), keep=keep, ep_index=ep_index)
-        need = self._ensure_workspace(dims, dev)
+        need = self._ensure_workspace(dims, dev) if B > 0 else 0
+        if dp and (self._dp_scratch is None or self._dp_scratch.device != dev):
+            self._dp_scratch = th.empty(4096, dtype=th.float32, device=dev)
 
         do_sync = (episode_num - self.last_target_update_episode) / a.target_update_interval >= 1.0
-        dp = data_parallel.is_active() and getattr(a, "data_parallel", True)
-        hp = _lib.HParams(a.gamma, a.lr, a.optim_alpha, a.optim_eps, a.grad_norm_clip, int(do_sync), int(dp),
-                          int(bool(getattr(a, "keep_q", False))))
-        L = _lib.lib()
-        s = _lib.stream_ptr(dev)
-        _lib.check(L.pmb_qlearner_train_step(C.byref(dims), C.byref(pb), C.byref(hp), _lib.ptr(f["p"]),
-                                             _lib.ptr(f["g"]), _lib.ptr(f["sq"]), _lib.ptr(f["target"]),
-                                             _lib.ptr(self._workspace), need, _lib.ptr(self._stats), s),
-                   "pmb_qlearner_train_step")
-        if dp:
-            # one exchange per step: gradients of sum((td*mask)^2) and the five loss sums
-            data_parallel.allreduce_step(f["g"], self._stats[:5])
-            scratch = self._workspace[:4096 * 4].view(th.float32)
-            _lib.check(L.pmb_clip_rmsprop_update(f["layout"].n_total, _lib.ptr(f["p"]), _lib.ptr(f["g"]),
-                                                 _lib.ptr(f["sq"]), _lib.ptr(f["target"]), int(do_sync),
-                                                 _lib.ptr(self._stats), a.lr, a.optim_alpha, a.optim_eps,
-                                                 a.grad_norm_clip, _lib.ptr(scratch), s), "pmb_clip_rmsprop_update")
+        # the optimiser's (possibly checkpoint-restored) hyper-parameters, like torch's param_groups (q_learner.py:30,143)
+        od = self.optimiser.defaults
+        hp = _lib.HParams(a.gamma, od["lr"], od["alpha"], od["eps"], a.grad_norm_clip, int(do_sync), int(dp),
+                          int(getattr(a, "keep_q", 0)))
+        if getattr(a, "cuda_graph", False) and not dp and B > 0:
+            self._run_graphed(dims, pb, hp, f, need, dev, keep)
+        else:
+            self._launch(dims, pb, hp, f, need, dev, dp)
         self.optimiser.step_count += 1
         self.last_stats = self._stats
         self._last_dims = dims
@@ -224,11 +263,37 @@ class QLearner:
             st = self._stats.tolist()                                            # one D2H sync
             mask_elems = st[_lib.STAT_IDS["mask_sum"]]
             self.logger.log_stat("loss", st[_lib.STAT_IDS["td2_sum"]] / mask_elems, t_env)
-            self.logger.log_stat("grad_norm", self._stats[_lib.STAT_IDS["grad_norm"]].float(), t_env)
+            self.logger.log_stat("grad_norm", st[_lib.STAT_IDS["grad_norm"]], t_env)
             self.logger.log_stat("td_error_abs", st[_lib.STAT_IDS["tdabs_sum"]] / mask_elems, t_env)
             self.logger.log_stat("q_taken_mean", st[_lib.STAT_IDS["qtaken_sum"]] / (mask_elems * a.n_agents), t_env)
             self.logger.log_stat("target_mean", st[_lib.STAT_IDS["target_sum"]] / (mask_elems * a.n_agents), t_env)
             self.log_stats_t = t_env
+
+    # ---- CUDA graph of the whole step (args.cuda_graph) ---------------------------------------
+    # The C ABI allocates nothing and takes the stream as an argument, so the ~25 launches of a step capture into one
+    # graph.  At the small BASELINE configs (3m / 32, 2s3z / 1024) launch latency, not the kernels, bounds the step.
+    # A graph is keyed on everything its launches bake in: dims, every field pointer / stride, the hyper-parameters
+    # and the target-sync flag - so a batch that lives somewhere else (or needed a dtype / layout conversion, which
+    # yields fresh tensors) simply misses the cache.  First sight of a key runs eagerly, the second captures and
+    # replays, later ones replay.  Copies / conversions of the inputs stay outside the graph, ordered before it on the
+    # same stream.
+    def _run_graphed(self, dims, pb, hp, f, need, dev, keep):
+        key = (tuple(getattr(dims, k) for k, _ in dims._fields_), tuple(getattr(pb, k) for k, _ in pb._fields_),
+               tuple(getattr(hp, k) for k, _ in hp._fields_), f["p"].data_ptr(), self._workspace.data_ptr(),
+               self._stats.data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 16:                     # bounded cache (ring of replay batches etc.)
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = "seen"
+            return self._launch(dims, pb, hp, f, need, dev, False)
+        if entry == "seen":
+            g = th.cuda.CUDAGraph()
+            th.cuda.synchronize(dev)
+            with th.cuda.graph(g):
+                self._launch(dims, pb, hp, f, need, dev, False)
+            entry = self._graphs[key] = (g, list(keep))
+        entry[0].replay()
 
     def stats(self):
         """The 5 logged scalars + grad_norm of the latest step as python floats (syncs)."""

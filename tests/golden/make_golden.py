@@ -298,8 +298,107 @@ def run_replay_sample():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+
+def run_checkpoint():
+    """Checkpoint files written by the REFERENCE (learner.save_models -> agent.th / mixer.th / opt.th,
+    q_learner.py:124-135) after two train steps, plus what a second reference learner holds after
+    load_models (q_learner.py:137-143: the target MAC loads the online weights, the target mixer is left
+    alone) and after one more train step."""
+    tiny = SmacShape("tiny", 3, 10, 14, 5, 8)
+    args = default_args(tiny, mixer="qmix", double_q=True, learner_log_interval=0, rnn_hidden_dim=16, mixing_embed_dim=8)
+    fields = numpy_episode_fields(tiny, 4, 8, seed=21, ragged=True)
+    batch, _, _ = ref_batch(tiny, fields)
+    out = {"in/" + k: v for k, v in fields.items()}
+    writer, _ = build_ref_learner(tiny, args, th.float32, seed=31)
+    writer.train(batch, 0, 0)
+    writer.train(batch, 1, 0)
+    ckpt = os.path.join(HERE, "ckpt_ref")
+    os.makedirs(ckpt, exist_ok=True)
+    writer.save_models(ckpt)
+    reader, logger = build_ref_learner(tiny, copy.copy(args), th.float32, seed=32)
+    for tag, mod in (("agent", reader.mac.agent), ("target_agent", reader.target_mac.agent), ("mixer", reader.mixer),
+                     ("target_mixer", reader.target_mixer)):
+        for k, v in state_np(mod).items():
+            out["init/%s/%s" % (tag, k)] = v
+    reader.load_models(ckpt)
+    for tag, mod in (("agent", reader.mac.agent), ("target_agent", reader.target_mac.agent), ("mixer", reader.mixer),
+                     ("target_mixer", reader.target_mixer)):
+        for k, v in state_np(mod).items():
+            out["loaded/%s/%s" % (tag, k)] = v
+    sq = [reader.optimiser.state[p]["square_avg"].numpy().copy() for p in reader.params]
+    out["loaded/square_avg_flat"] = np.concatenate([s_.ravel() for s_ in sq])
+    reader.train(batch, 2, 0)
+    for tag, mod in (("agent", reader.mac.agent), ("mixer", reader.mixer)):
+        for k, v in state_np(mod).items():
+            out["after/%s/%s" % (tag, k)] = v
+    for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+        out["after/stat/" + key] = np.float64(logger.stats[key][-1][1])
+    sq = [reader.optimiser.state[p]["square_avg"].numpy().copy() for p in reader.params]
+    out["after/square_avg_flat"] = np.concatenate([s_.ravel() for s_ in sq])
+    out["meta"] = np.array(repr(dict(name="checkpoint", shape=tuple(tiny), mixer="qmix", double_q=True,
+                                     over=dict(rnn_hidden_dim=16, mixing_embed_dim=8))))
+    path = os.path.join(HERE, "checkpoint.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "+", sorted(os.listdir(ckpt)))
+
+
+def run_episode_update():
+    """EpisodeBatch.update / ReplayBuffer.insert_episode_batch (episode_buffer.py:98-154, 271-286) with the OneHot
+    preprocess (transforms.py:12-21), driven the way the runners drive them (parallel_runner.py:100-204): per timestep a
+    pre-transition update of state / avail_actions / obs for the live envs, then actions / reward / terminated with
+    mark_filled=False; list-valued `bs`, scalar `ts`; finally two inserts into a ring buffer that wrap around."""
+    from components.episode_buffer import ReplayBuffer as RefReplayBuffer
+    shape = SmacShape("tiny", 3, 6, 7, 5, 6)
+    scheme, groups, preprocess = ref_scheme(shape)
+    B, T = 5, shape.max_seq_length
+    rng = np.random.default_rng(17)
+    eb = RefEpisodeBatch(scheme, groups, B, T, preprocess=preprocess, device="cpu")
+    out, calls = {}, []
+
+    def do(data, bs, ts, mark_filled):
+        i = len(calls)
+        for k, v in data.items():
+            out["call%d/%s" % (i, k)] = np.asarray(v)
+        out["call%d/bs" % i] = np.asarray(bs, dtype=np.int64)
+        calls.append(dict(ts=int(ts), mark_filled=bool(mark_filled), keys=sorted(data)))
+        eb.update({k: np.asarray(v) for k, v in data.items()}, bs=list(bs), ts=ts, mark_filled=mark_filled)
+
+    live = list(range(B))
+    for t in range(T - 1):
+        n = len(live)
+        avail = (rng.random((n, shape.n_agents, shape.n_actions)) < 0.6).astype(np.int32)
+        avail[..., 0] = 1
+        do({"state": rng.standard_normal((n, shape.state_dim)).astype(np.float32), "avail_actions": avail,
+            "obs": rng.standard_normal((n, shape.n_agents, shape.obs_dim)).astype(np.float32)}, live, t, True)
+        acts = (rng.random((n, shape.n_agents, shape.n_actions)) * avail).argmax(-1).astype(np.int64)
+        term = (rng.random(n) < 0.25)
+        do({"actions": acts[:, :, None], "reward": rng.standard_normal((n, 1)).astype(np.float32),
+            "terminated": term[:, None].astype(np.uint8)}, live, t, False)
+        live = [e for e, d in zip(live, term) if not d]
+        if not live:
+            break
+    for k, v in eb.data.transition_data.items():
+        out["final/" + k] = v.numpy()
+    buf = RefReplayBuffer(scheme, groups, 8, T, preprocess=preprocess, device="cpu")
+    buf.insert_episode_batch(eb)
+    buf.insert_episode_batch(eb)                       # 5 + 5 into 8 slots: wraps
+    for k, v in buf.data.transition_data.items():
+        out["buffer/" + k] = v.numpy()
+    out["buffer/index"] = np.int64(buf.buffer_index)
+    out["buffer/episodes"] = np.int64(buf.episodes_in_buffer)
+    out["meta"] = np.array(repr(dict(shape=tuple(shape), B=B, T=T, calls=calls)))
+    path = os.path.join(HERE, "episode_update.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
 if __name__ == "__main__":
     th.set_num_threads(1)
+    only = set(sys.argv[1:])            # e.g. `make_golden.py checkpoint episode_update`: regenerate just those
+    if only:
+        for name in sorted(only):
+            {"checkpoint": run_checkpoint, "episode_update": run_episode_update, "select_actions": run_select_actions,
+             "replay_sample": run_replay_sample}[name]()
+        sys.exit(0)
     tiny = SmacShape("tiny", 3, 10, 14, 5, 8)
     small = dict(rnn_hidden_dim=16, mixing_embed_dim=8)
     run_case("qmix_tiny", tiny, B=4, T=8, mixer="qmix", double_q=True, seed=1, **small)
@@ -313,3 +412,5 @@ if __name__ == "__main__":
     run_case("qmix_3m", m3, B=5, T=12, mixer="qmix", double_q=True, seed=5, n_steps=2)
     run_select_actions()
     run_replay_sample()
+    run_checkpoint()
+    run_episode_update()

@@ -437,12 +437,16 @@ def test_bf16_tier_train_step_matches_oracle(shape_name, B, T, mixer):
             assert rel_err(prm.detach().cpu().numpy(), expect(init[name], gg)) < 1e-5, (kind, name)
 
 
-@pytest.mark.parametrize("shape_name,B,T,mixer", [("3m", 32, 60, "qmix"), ("MMM2", 16, 20, "vdn"),
+@pytest.mark.parametrize("shape_name,B,T,mixer", [("3m", 32, 60, "qmix"), ("MMM2", 16, 20, "vdn"), ("MMM2", 16, 20, None),
                                                    ("27m_vs_30m", 8, 12, "qmix")])
 def test_bf16_tier_post_update_parameters_match_oracle(shape_name, B, T, mixer):
-    """The north_star statement for the tensor-core tier: with the reference hyper-parameters (grad_norm_clip = 10)
-    the post-update parameters agree with the reference algorithm within 1e-2 (norm-wise per tensor), as do loss and
-    grad_norm.  RMSprop state pre-warmed on both sides (see the test above for why)."""
+    """The north_star statement for the tensor-core tier with the reference hyper-parameters (grad_norm_clip = 10, so the
+    clip is active): loss and grad_norm within 1e-2, and the parameter UPDATE p' - p of every tensor against the
+    oracle's update in the relative L2 norm (comparing the parameters themselves would hide the update: one RMSprop step
+    moves a tensor by less than 1e-2 of its norm).  RMSprop state pre-warmed on both sides so the update is ~linear in
+    the gradient.  Bounds: tensors behind a discontinuous derivative carry the decision-flip noise of a single bf16 pass
+    (fc1: ReLU mask, hypernets: sign of |.|); tests/test_bf16_evidence.py pins those decisions and gets every tensor
+    within 1e-2."""
     from cuda_utils import build_learner, to_batch
     shape = SMAC_SHAPES[shape_name]
     args = default_args(shape, mixer=mixer, learner_log_interval=0, precision="bf16")
@@ -452,17 +456,27 @@ def test_bf16_tier_post_update_parameters_match_oracle(shape_name, B, T, mixer):
     for sq in list(olr.sq_agent.values()) + list(olr.sq_mixer.values()):
         sq[...] = 1e-2
     learner._flat["sq"].fill_(1e-2)
+    before = {"agent": {k: v.copy() for k, v in olr.agent.items()}, "mixer": {k: v.copy() for k, v in olr.mixer_p.items()}}
     stats, _, _ = olr.train(fields, 0, 0)
     learner.train(to_batch(shape, fields), 0, 0)
     st = learner.stats()
+    assert st["clip_coef"] < 1.0 or stats["grad_norm"] <= args.grad_norm_clip        # the clip is exercised where it should be
     for key in ("loss", "grad_norm"):
         assert abs(st[key] - stats[key]) <= TOL_BF16 * max(1.0, abs(stats[key])), (key, st[key], stats[key])
-    oracle_after = {"agent": olr.agent, "mixer": olr.mixer_p}
-    for kind, mod in (("agent", learner.mac.agent), ("mixer", learner.mixer)):
+    after = {"agent": olr.agent, "mixer": olr.mixer_p}
+    errs = {}
+    for kind, mod in (("agent", learner.mac.agent), ("mixer", learner.mixer if mixer == "qmix" else None)):
         if mod is None:
             continue
         for name, prm in mod.named_parameters():
-            assert rel_err(prm.detach().cpu().numpy(), oracle_after[kind][name]) < TOL_BF16, (kind, name)
+            u_ref = after[kind][name].astype(np.float64) - before[kind][name].astype(np.float64)
+            u_gpu = prm.detach().cpu().numpy().astype(np.float64) - before[kind][name].astype(np.float64)
+            assert np.abs(u_ref).max() > 0, (kind, name)
+            errs[kind + "." + name] = np.linalg.norm(u_gpu - u_ref) / np.linalg.norm(u_ref)
+    print({k: "%.1e" % v for k, v in errs.items()})
+    for k, e in errs.items():
+        bound = 0.15 if k.startswith("mixer.") else (5e-2 if k.startswith("agent.fc1") else 2e-2)
+        assert e < bound, (k, e)
 
 
 @pytest.mark.parametrize("shape_name,B", [("3m", 37), ("27m_vs_30m", 19)])

@@ -32,7 +32,7 @@ def _run(rank, world, port, out_dir):
     fields = numpy_episode_fields(shape, 7, 10, seed=3)               # 7 episodes: uneven shards (4 + 3)
     names = ["agent." + k for k in orc.AGENT_PARAM_NAMES] + ["mixer." + k for k in orc.QMIX_PARAM_NAMES]
 
-    assert dp.is_active()
+    assert dp.is_active() and dp.rank() == rank and dp.world_size() == world
     lo, hi = dp.shard_slice(7, rank, world)
     mine = dp.shard_fields({k: th.from_numpy(v) for k, v in fields.items()}, rank, world)
     mine = {k: v.numpy() for k, v in mine.items()}
@@ -43,7 +43,9 @@ def _run(rank, world, port, out_dir):
     flat = th.from_numpy(_flat(g, names) * float(fw["mask_sum"]))      # -> un-normalised
     sums = th.tensor([float(fw["mask_sum"]), float((fw["masked_td"] ** 2).sum()), float(np.abs(fw["masked_td"]).sum()),
                       float((fw["q_tot"] * fw["mask"]).sum()), float((fw["targets"] * fw["mask"]).sum())], dtype=th.float64)
-    dp.allreduce_step(flat, sums)
+    buf = th.cat([flat, sums])                                        # ONE buffer, ONE collective per step
+    dp.allreduce_step(buf)
+    flat, sums = buf[:-5], buf[-5:]
     flat = flat.numpy() / float(sums[0])
 
     full = orc.OracleQLearner(agent, mixer, copy.copy(args))

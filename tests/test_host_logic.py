@@ -146,3 +146,53 @@ def test_optimizer_state_dict_is_torch_rmsprop_compatible():
     ref2 = th.optim.RMSprop(ps, lr=5e-4, alpha=0.99, eps=1e-5)
     ref2.load_state_dict(sd)                                   # the reference can load our opt.th
     assert th.equal(ref2.state_dict()["state"][1]["square_avg"], sd["state"][1]["square_avg"])
+
+
+def replay_update_golden(device):
+    """Replays the update / insert calls recorded from the reference (tests/golden/make_golden.py:run_episode_update) on
+    this package's EpisodeBatch / ReplayBuffer living on `device`; returns (batch, buffer, golden)."""
+    import ast
+    g = np.load(os.path.join(REPO, "tests", "golden", "episode_update.npz"))
+    meta = ast.literal_eval(str(g["meta"]))
+    shape = SmacShape(*meta["shape"])
+    scheme, groups = make_scheme(shape)
+    preprocess = {"actions": ("actions_onehot", [OneHot(out_dim=shape.n_actions)])}
+    eb = EpisodeBatch(scheme, groups, meta["B"], meta["T"], preprocess=preprocess, device=device)
+    for i, call in enumerate(meta["calls"]):
+        data = {k: g["call%d/%s" % (i, k)] for k in call["keys"]}
+        eb.update(data, bs=[int(b) for b in g["call%d/bs" % i]], ts=call["ts"], mark_filled=call["mark_filled"])
+    buf = ReplayBuffer(scheme, groups, 8, meta["T"], preprocess=preprocess, device=device)
+    buf.insert_episode_batch(eb)
+    buf.insert_episode_batch(eb)
+    return eb, buf, g
+
+
+def test_episode_batch_update_matches_reference_golden():
+    """EpisodeBatch.update / insert_episode_batch / OneHot (episode_buffer.py:98-154, 271-286; transforms.py:12-21): the
+    host path against what the reference's classes produced for the same calls - every field bit-exact."""
+    eb, buf, g = replay_update_golden("cpu")
+    for k, v in eb.data.transition_data.items():
+        np.testing.assert_array_equal(v.numpy(), g["final/" + k], err_msg=k)
+    for k, v in buf.data.transition_data.items():
+        np.testing.assert_array_equal(v.numpy(), g["buffer/" + k], err_msg=k)
+    assert buf.buffer_index == int(g["buffer/index"]) and buf.episodes_in_buffer == int(g["buffer/episodes"])
+
+
+def test_reference_checkpoint_loads_on_cpu_modules():
+    """agent.th / mixer.th / opt.th written by the REFERENCE's save_models (tests/golden/ckpt_ref) load into this package's
+    modules by name, the reference quirks included (target MAC <- online weights, target mixer untouched)."""
+    g = Golden("checkpoint")
+    shape = g.shape
+    scheme, groups = make_scheme(shape)
+    args = g.args()
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    learner = le_REGISTRY["q_learner"](mac, scheme, None, args)
+    learner.target_mixer.load_state_dict({k: th.from_numpy(v) for k, v in g.group("init/target_mixer").items()})
+    learner.load_models(os.path.join(REPO, "tests", "golden", "ckpt_ref"))
+    for tag, mod in (("agent", learner.mac.agent), ("target_agent", learner.target_mac.agent), ("mixer", learner.mixer),
+                     ("target_mixer", learner.target_mixer)):
+        for k, v in g.group("loaded/" + tag).items():
+            np.testing.assert_array_equal(mod.state_dict()[k].numpy(), v, err_msg=tag + "." + k)
+    flat = np.concatenate([sq.numpy().ravel() for sq in learner.optimiser.square_avg])
+    np.testing.assert_array_equal(flat, g["loaded/square_avg_flat"])
+    assert learner.optimiser.step_count == 2
