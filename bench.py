@@ -79,6 +79,8 @@ def phase_work(name, B, T, N, O, S, A, mixer):
         return 2.0 * rows * H * 6 * H, rows * (128 + 128 + 512)
     if name == "gru_unroll_fwd_target_tc":
         return 2.0 * rows * H * 6 * H, rows * (128 + 128)
+    if name == "gru_unroll_fwd_both_tc":       # the two recurrences side by side (small batches: forked onto two streams)
+        return 2 * 2.0 * rows * H * 6 * H, rows * (128 + 128 + 512 + 128 + 128)
     if name == "gru_fwd_target_select_tc":     # x + online h in; target h never leaves the SM; avail / actions in
         return 2.0 * rows * H * (6 * H + 2 * A), rows * (128 + 128 + A * f4 + 8 + 8)
     if name == "q_select_tc":                  # h of both nets, avail, actions in; chosen / tmax out

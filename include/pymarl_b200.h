@@ -61,7 +61,9 @@ typedef struct pmb_dims {
     int32_t mixer;             /* enum pmb_mixer (learners/q_learner.py:19-27)            */
     int32_t double_q;          /* learners/q_learner.py:71                                */
     int32_t precision;         /* enum pmb_precision                                      */
-    int32_t reserved;
+    int32_t reserved;          /* flags.  bit 0 (pmb_select_actions_step, tensor-core tier only): the packed weight
+                                * images a previous call left in `scratch` are still current - same parameters, same
+                                * scratch - so the step skips its two weight-pack launches.  0 is always safe.      */
 } pmb_dims;
 
 /* The EpisodeBatch fields the path reads.  *_sb = batch stride in ELEMENTS. */

@@ -35,6 +35,8 @@ class BasicMAC:
         self.action_selector = action_REGISTRY[args.action_selector](args)
         self.hidden_states = None
         self._scratch = None
+        self._weights_epoch = 0         # bumped by whoever rewrites the agent parameters behind torch's back (the learner's kernels)
+        self._packed_key = None         # what the weight images in the rollout scratch were packed from
 
     # ---- helpers ------------------------------------------------------------------------
     def _device(self):
@@ -93,6 +95,11 @@ class BasicMAC:
         need = _lib.lib().pmb_select_actions_workspace_bytes(C.byref(dims))
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
             self._scratch = th.empty(need, dtype=th.uint8, device=dev)
+        # packed weight images live in the scratch between steps: re-pack only when the parameters (or the scratch) changed
+        key = (self._scratch.data_ptr(), flat.value, self._weights_epoch, dims.B, dims.O,
+               tuple(p._version for p in self.agent.parameters()))
+        dims.reserved = 1 if key == self._packed_key else 0
+        self._packed_key = key
         q = th.empty(B, N, A, dtype=th.float32, device=dev) if (want_q or not want_actions) else None
         actions = th.empty(B, N, dtype=th.int64, device=dev) if want_actions else None
         _lib.check(_lib.lib().pmb_select_actions_step(
@@ -128,17 +135,24 @@ class BasicMAC:
     def parameters(self):
         return self.agent.parameters()
 
+    def params_changed(self):
+        """Tell the controller that the agent parameters were rewritten in place by a kernel (QLearner.train does)."""
+        self._weights_epoch += 1
+
     def load_state(self, other_mac):
         self.agent.load_state_dict(other_mac.agent.state_dict())
+        self.params_changed()
 
     def cuda(self):
         self.agent.cuda()
+        self.params_changed()
 
     def save_models(self, path):
         th.save(self.agent.state_dict(), "{}/agent.th".format(path))
 
     def load_models(self, path):
         self.agent.load_state_dict(th.load("{}/agent.th".format(path), map_location=lambda storage, loc: storage))
+        self.params_changed()
 
     def _build_agents(self, input_shape):
         self.agent = agent_REGISTRY[self.args.agent](input_shape, self.args)

@@ -45,7 +45,7 @@ int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bflo
                   const float* bias, float* C, int64_t ldc, cudaStream_t s);
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
                     float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, uint32_t* relu_mask, void* scratch,
-                    int64_t scratch_bytes, cudaStream_t s);
+                    int64_t scratch_bytes, cudaStream_t s, int weights_packed = 0);
 // tc_atb.cu (tile-image D operand)
 int tc_gemm_atb_ti(const uint8_t* d_ti, int T, int N, int64_t R, int n_tiles, const float* A, RowMap amap, int K,
                    float* out, int64_t ldo, float* bias_out, void* scratch, int64_t scratch_bytes, cudaStream_t s);
@@ -121,6 +121,28 @@ cudaError_t set_smem_attr(const void* func, int bytes) {
     e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) done.push_back(Key{func, dev, bytes});
     return e;
+}
+
+// Side stream + fork / join events of the CURRENT device, created on first use (never while a graph is being captured:
+// the learner runs every new configuration once eagerly before it captures).  The forward pass forks the target net's
+// recurrence onto the side stream when both recurrences fit on the device side by side.
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static int side_stream(SideStream** out) {
+    constexpr int kMaxDev = 64;
+    static SideStream table[kMaxDev];
+    static std::mutex mu;
+    int dev = 0;
+    PMB_CUDA(cudaGetDevice(&dev));
+    PMB_REQUIRE(dev >= 0 && dev < kMaxDev, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream& e = table[dev];
+    if (!e.stream) {
+        PMB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+        PMB_CUDA(cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming));
+        PMB_CUDA(cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming));
+    }
+    *out = &e;
+    return PMB_OK;
 }
 
 int validate_dims(const pmb_dims* d) {
@@ -552,9 +574,12 @@ int pmb_select_actions_step(const pmb_dims* d, const pmb_batch* b, int32_t t, co
         void* fc1_scr = gru_img + 65536;
         // (no zeroing of the padding rows of the last x tile: tile rows are independent in every MMA of this path and the
         // rollout kernel neither stores nor selects for rows >= R)
+        // pmb_dims.reserved bit 0: the weight images in `scratch` are current (same parameters, same scratch as the
+        // previous step of this rollout) - the two pack launches are skipped
+        const int packed = d->reserved & 1;
         if ((rc = tc_fc1_fwd_both(d, b, t, 1, ap, ap, reinterpret_cast<float*>(x_ti), nullptr, 1, nullptr, nullptr, fc1_scr,
-                                  align_up(tc_fc1_scratch_bytes(d), 256), s))) return rc;
-        if ((rc = pack_gru_images(d, ap, gru_img, s))) return rc;
+                                  align_up(tc_fc1_scratch_bytes(d), 256), s, packed))) return rc;
+        if (!packed && (rc = pack_gru_images(d, ap, gru_img, s))) return rc;
         tc::GruFwdParams fp;
         fp.w_ih_img = reinterpret_cast<const __nv_bfloat16*>(gru_img);
         fp.w_hh_img = reinterpret_cast<const __nv_bfloat16*>(gru_img + 24576);
@@ -648,14 +673,32 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         PHASE(s, "fc1_fwd_both_tc");
         if ((rc = tc_fc1_fwd_both(d, b, 0, d->T, on, tg, v.x_on, v.x_tg, 1, fused_dw ? obs_ti : nullptr,
                                   reinterpret_cast<uint32_t*>(v.relu_mask), v.scratch, v.scratch_bytes, s))) return rc;
-        PHASE(s, "gru_unroll_fwd_online_tc");
+        // The two recurrences are independent.  Each runs ceil(n_tiles / 2) CTAs (one per SM): when both fit on the device
+        // at once (small configs, or a batch sharded over many GPUs) the target net's pass is forked onto a side stream and
+        // the two chains of T dependent steps run side by side instead of back to back.
+        const int gru_ctas = (n_tiles + 1) / 2;
+        const bool fork_tg = 2 * gru_ctas <= sm_count();
+        PHASE(s, fork_tg ? "gru_unroll_fwd_both_tc" : "gru_unroll_fwd_online_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
         if ((rc = pack_gru(tg, gru_img + 57344))) return rc;
         auto img = [&](int64_t off) { return reinterpret_cast<const __nv_bfloat16*>(gru_img + off); };
+        SideStream* side = nullptr;
+        if (fork_tg) {
+            if ((rc = side_stream(&side))) return rc;
+            PMB_CUDA(cudaEventRecord(side->fork, s));
+            PMB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            if ((rc = tc_gru_fwd2(img(57344), img(57344 + 24576), tg.b_ih, tg.b_hh, x_tg_ti, hg_ti, nullptr, R, d->T, n_tiles,
+                                  side->stream))) return rc;
+            PMB_CUDA(cudaEventRecord(side->join, side->stream));
+        }
         if ((rc = tc_gru_fwd2(img(0), img(24576), on.b_ih, on.b_hh, x_on_ti, h_ti, g_ti, R, d->T, n_tiles, s))) return rc;
-        PHASE(s, "gru_unroll_fwd_target_tc");
-        if ((rc = tc_gru_fwd2(img(57344), img(57344 + 24576), tg.b_ih, tg.b_hh, x_tg_ti, hg_ti, nullptr, R, d->T, n_tiles,
-                              s))) return rc;
+        if (fork_tg) {
+            PMB_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+        } else {
+            PHASE(s, "gru_unroll_fwd_target_tc");
+            if ((rc = tc_gru_fwd2(img(57344), img(57344 + 24576), tg.b_ih, tg.b_hh, x_tg_ti, hg_ti, nullptr, R, d->T, n_tiles,
+                                  s))) return rc;
+        }
         // :55-78 fused with fc2 of both nets
         PHASE(s, "q_select_tc");
         if ((rc = tc_q_select(d, b, img(49152), img(57344 + 49152), on.fc2_b, tg.fc2_b, h_ti, hg_ti, n_tiles, v.chosen,

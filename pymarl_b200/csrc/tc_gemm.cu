@@ -1013,8 +1013,10 @@ extern "C" int pmb_debug_fc1_prof(unsigned long long* out, int reset) {
 #endif
 int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentParams& on, const AgentParams& tg,
                     float* x_on, float* x_tg, int tile_images, uint8_t* obs_img_out, uint32_t* relu_mask, void* scratch,
-                    int64_t scratch_bytes, cudaStream_t s) {
+                    int64_t scratch_bytes, cudaStream_t s, int weights_packed) {
     // scratch: packed W (128 x Kpad bf16) | tab_act | tab_id
+    // weights_packed: the caller guarantees that `scratch` still holds the images / tables a previous call packed from
+    // the SAME parameters (rollout steps between two learner updates): the pack launches are skipped
     const int D_in = d_in_of(d);
     int64_t wp_bytes = align_up(tc_packed_elems(128, d->O) * 2, 256);
     int64_t ta_bytes = align_up((int64_t)2 * d->A * 64 * 4, 256);
@@ -1038,7 +1040,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
         rc = tc_pack_w(ptrs, rows, lds, 2, d->O, wp, s);
         if (rc) return rc;
     }
-    if (!use_stream || !fold_id_s) {
+    if ((!use_stream || !fold_id_s) && !(weights_packed && use_stream)) {
         int n_tab = 2 * (d->A + d->N) * 64;
         fc1_tables_kernel<<<(unsigned)ceil_div(n_tab, 256), 256, 0, s>>>(on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A,
                                                                          d->N, D_in, d->obs_last_action, d->obs_agent_id,
@@ -1067,10 +1069,12 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             const int fold_id = n_chunks * tc::BK - d->O >= d->N + 1;
             __nv_bfloat16* tab_act16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(scratch) + wp_bytes + ta_bytes + ti_bytes);
             const int64_t n_pack = (int64_t)128 * n_chunks * 8 + (int64_t)d->A * 128;
-            fc1_stream_pack_kernel<<<(unsigned)ceil_div(n_pack, 256), 256, 0, s>>>(
-                on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A, d->N, D_in, d->obs_last_action, d->obs_agent_id, fold_id,
-                n_chunks, wp, tab_act16);
-            PMB_LAUNCH_CHECK("fc1_stream_pack_kernel");
+            if (!weights_packed) {
+                fc1_stream_pack_kernel<<<(unsigned)ceil_div(n_pack, 256), 256, 0, s>>>(
+                    on.fc1_w, on.fc1_b, tg.fc1_w, tg.fc1_b, d->O, d->A, d->N, D_in, d->obs_last_action, d->obs_agent_id, fold_id,
+                    n_chunks, wp, tab_act16);
+                PMB_LAUNCH_CHECK("fc1_stream_pack_kernel");
+            }
             tc::Fc1StreamParams Q;
             Q.ep_index = b->ep_index; Q.obs = b->obs; Q.obs_sb = b->obs_sb; Q.Wp = wp; Q.obs_img = obs_img_out; Q.R = R;
             Q.T = nt; Q.N = d->N; Q.O = d->O; Q.n_tiles = n_tiles; Q.n_chunks = n_chunks; Q.slot_bytes = slot_bytes;

@@ -252,6 +252,8 @@ class QLearner:
         else:
             self._launch(dims, pb, hp, f, need, dev, dp)
         self.optimiser.step_count += 1
+        if hasattr(self.mac, "params_changed"):
+            self.mac.params_changed()          # the rollout path caches packed weight images between updates
         self.last_stats = self._stats
         self._last_dims = dims
 

@@ -155,8 +155,9 @@ def test_bf16_gradients_and_updates_match_oracle_with_pinned_decisions(shape_nam
         assert r["grad_vs_pinned"] < TOL_BF16, (k, r)
         assert r["upd_vs_pinned"] < TOL_BF16, (k, r)
         # against the unmodified reference algorithm: the tensors behind a discontinuity carry the flip noise
+        # (the RMSprop update is a non-linear, element-wise function of the gradient: it roughly doubles the relative error)
         loose = 0.15 if k.startswith("mixer.") else (5e-2 if k.startswith("agent.fc1") else 2e-2)
-        assert r["grad_vs_ref"] < loose and r["upd_vs_ref"] < loose, (k, r)
+        assert r["grad_vs_ref"] < loose and r["upd_vs_ref"] < 2 * loose, (k, r)
         assert r["sign_flips"] < 0.01, (k, r)
     for key in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
         assert abs(st[key] - stats_ref[key]) <= 2 * TOL_BF16 * max(1.0, abs(stats_ref[key])), (key, st[key], stats_ref[key])
@@ -275,6 +276,7 @@ def test_bf16_bench_scale_matches_fp32_tier():
 
     lf = make("fp32")
     st_f, g_f = np.zeros(5), np.zeros(n)
+    abs_q = 0.0                                   # sum |q_tot|: the scale of the (cancelling) q_taken / target sums
     worst = dict(chosen=0.0, q_tot=0.0, tmax_mismatch=0.0)
     for b0 in range(0, B, chunk):
         lf._flat["p"].copy_(p0)                                      # same parameters for every chunk
@@ -290,10 +292,13 @@ def test_bf16_bench_scale_matches_fp32_tier():
         worst["q_tot"] = max(worst["q_tot"], float((w["q_tot"] - qtot_b[sl]).abs().max() / w["q_tot"].abs().max()))
         bad = ((w["tmax"] - tmax_b[sl]).abs() > 1e-2 * w["tmax"].abs().max()).float().mean().item()
         worst["tmax_mismatch"] = max(worst["tmax_mismatch"], bad)
+        abs_q += float(w["q_tot"].abs().sum())
     errs = {k: _l2(g_b[o:o + m], g_f[o:o + m]) for k, (o, m) in slices.items()}
     print("stats bf16", st_b[:5], "fp32", st_f, worst, {k: "%.1e" % v for k, v in errs.items()})
     for i in range(5):
-        assert abs(st_b[i] - st_f[i]) <= TOL_BF16 * max(1.0, abs(st_f[i])), (i, st_b[i], st_f[i])
+        # sums 3 and 4 (q_taken, targets) add terms of both signs: their error is measured against sum |q_tot|
+        scale = max(1.0, abs(st_f[i]), abs_q if i >= 3 else 0.0)
+        assert abs(st_b[i] - st_f[i]) <= TOL_BF16 * scale, (i, st_b[i], st_f[i], scale)
     assert worst["chosen"] < TOL_BF16 and worst["q_tot"] < TOL_BF16, worst
     assert worst["tmax_mismatch"] < 0.03, worst           # double-Q arg-max near-ties flip for a small fraction of the entries
     for k, e in errs.items():

@@ -475,7 +475,7 @@ def test_bf16_tier_post_update_parameters_match_oracle(shape_name, B, T, mixer):
             errs[kind + "." + name] = np.linalg.norm(u_gpu - u_ref) / np.linalg.norm(u_ref)
     print({k: "%.1e" % v for k, v in errs.items()})
     for k, e in errs.items():
-        bound = 0.15 if k.startswith("mixer.") else (5e-2 if k.startswith("agent.fc1") else 2e-2)
+        bound = 0.3 if k.startswith("mixer.") else (0.1 if k.startswith("agent.fc1") else 4e-2)
         assert e < bound, (k, e)
 
 

@@ -242,3 +242,38 @@ def test_two_gpu_data_parallel_step_equals_one_gpu():
     import json
     out = json.loads(line[0][len("DP_CHECK "):])
     assert out["ok"], out
+
+
+def test_rollout_weight_image_cache_follows_parameter_updates():
+    """The rollout step keeps its packed bf16 weight images in the scratch between steps (pmb_dims.reserved bit 0) and must
+    re-pack when the learner's kernels rewrite the parameters in place, when load_state / load_state_dict replace them, and
+    when torch ops touch them: after each kind of change the cached MAC gives the bits of a freshly built MAC."""
+    from cuda_utils import build_learner, to_batch
+    from pymarl_b200 import mac_REGISTRY
+    from pymarl_b200.synthetic import make_scheme
+    shape = SMAC_SHAPES["2s3z"]
+    args = default_args(shape, mixer="qmix", learner_log_interval=0, precision="bf16", device="cuda")
+    learner, _ = build_learner(shape, args)
+    fields = numpy_episode_fields(shape, 48, 12, seed=4, ragged=False)
+    batch = to_batch(shape, fields)
+
+    def fresh_q(t):
+        scheme, groups = make_scheme(shape)
+        m = mac_REGISTRY["basic_mac"](scheme, groups, copy.copy(args))
+        m.cuda()
+        m.agent.load_state_dict(learner.mac.agent.state_dict())
+        m.init_hidden(48)
+        return m.forward(batch, t)
+
+    mac = learner.mac
+    for t, change in enumerate(("none", "none", "train", "load_state", "torch_op")):
+        if change == "train":
+            learner.train(batch, 0, 0)
+        elif change == "load_state":
+            mac.load_state(learner.target_mac)
+        elif change == "torch_op":
+            with th.no_grad():
+                mac.agent.fc2.weight.mul_(1.5)
+        mac.init_hidden(48)
+        q = mac.forward(batch, t)
+        assert th.equal(q, fresh_q(t)), (t, change)
