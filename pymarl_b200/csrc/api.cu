@@ -676,7 +676,9 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         // The two recurrences are independent.  Each runs ceil(n_tiles / 2) CTAs (one per SM): when both fit on the device
         // at once (small configs, or a batch sharded over many GPUs) the target net's pass is forked onto a side stream and
         // the two chains of T dependent steps run side by side instead of back to back.
-        const int gru_ctas = (n_tiles + 1) / 2;
+        // With very few tiles (2 passes x n_tiles CTAs fit) every CTA takes ONE tile: no ping-pong, shorter per-step chain.
+        const int tpc = 2 * n_tiles <= sm_count() ? 1 : 2;
+        const int gru_ctas = (n_tiles + tpc - 1) / tpc;
         const bool fork_tg = 2 * gru_ctas <= sm_count();
         PHASE(s, fork_tg ? "gru_unroll_fwd_both_tc" : "gru_unroll_fwd_online_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
@@ -688,10 +690,10 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
             PMB_CUDA(cudaEventRecord(side->fork, s));
             PMB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
             if ((rc = tc_gru_fwd2(img(57344), img(57344 + 24576), tg.b_ih, tg.b_hh, x_tg_ti, hg_ti, nullptr, R, d->T, n_tiles,
-                                  side->stream))) return rc;
+                                  side->stream, tpc))) return rc;
             PMB_CUDA(cudaEventRecord(side->join, side->stream));
         }
-        if ((rc = tc_gru_fwd2(img(0), img(24576), on.b_ih, on.b_hh, x_on_ti, h_ti, g_ti, R, d->T, n_tiles, s))) return rc;
+        if ((rc = tc_gru_fwd2(img(0), img(24576), on.b_ih, on.b_hh, x_on_ti, h_ti, g_ti, R, d->T, n_tiles, s, tpc))) return rc;
         if (fork_tg) {
             PMB_CUDA(cudaStreamWaitEvent(s, side->join, 0));
         } else {

@@ -82,7 +82,7 @@ struct GruFwd2Params {
     uint8_t* h_ti;                   // [(nt+1)][n_tiles][16 KB]   slot 0 = h_0 = 0 (written here), slot t+1 = h_t
     uint8_t* g_ti;                   // [nt][n_tiles][4][16 KB] (r, z, n, hn) or null
     int64_t R;
-    int nt, n_tiles;
+    int nt, n_tiles, tiles_per_cta;
 };
 
 __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params P) {
@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(g2::THREADS, 1) gru_fwd2_kernel(GruFwd2Params 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile0 = 2 * blockIdx.x;
-    const int n_my = P.n_tiles - tile0 >= 2 ? 2 : 1;
+    // tiles_per_cta = 2: ping-pong (the tensor core works on one tile while the epilogue warps do the other's gate math);
+    // = 1 when there are fewer tiles than SMs: twice the CTAs, each with a shorter per-step chain
+    const int tile0 = P.tiles_per_cta * blockIdx.x;
+    const int n_my = P.n_tiles - tile0 >= P.tiles_per_cta ? P.tiles_per_cta : 1;
     const bool stash = P.g_ti != nullptr;
 
     if (threadIdx.x == 0) {
@@ -922,12 +924,14 @@ __global__ void __launch_bounds__(256) gru_bwd2_reduce_kernel(const float* __res
 }  // namespace tc
 
 int tc_gru_fwd2(const __nv_bfloat16* w_ih_img, const __nv_bfloat16* w_hh_img, const float* b_ih, const float* b_hh,
-                const uint8_t* x_ti, uint8_t* h_ti, uint8_t* g_ti, int64_t R, int nt, int n_tiles, cudaStream_t s) {
+                const uint8_t* x_ti, uint8_t* h_ti, uint8_t* g_ti, int64_t R, int nt, int n_tiles, cudaStream_t s,
+                int tiles_per_cta) {
     tc::GruFwd2Params P;
     P.w_ih_img = w_ih_img; P.w_hh_img = w_hh_img; P.b_ih = b_ih; P.b_hh = b_hh;
     P.x_ti = x_ti; P.h_ti = h_ti; P.g_ti = g_ti; P.R = R; P.nt = nt; P.n_tiles = n_tiles;
+    P.tiles_per_cta = tiles_per_cta == 1 ? 1 : 2;
     PMB_SMEM_ATTR(tc::gru_fwd2_kernel, tc::g2::SMEM_BYTES);
-    tc::gru_fwd2_kernel<<<(n_tiles + 1) / 2, tc::g2::THREADS, tc::g2::SMEM_BYTES, s>>>(P);
+    tc::gru_fwd2_kernel<<<(n_tiles + P.tiles_per_cta - 1) / P.tiles_per_cta, tc::g2::THREADS, tc::g2::SMEM_BYTES, s>>>(P);
     PMB_LAUNCH_CHECK("gru_fwd2_kernel");
     return PMB_OK;
 }
