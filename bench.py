@@ -224,15 +224,25 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def _finish_sampling(th, sampler, step_fn, min_samples=3, max_seconds=3.0):
+def _finish_sampling(th, sampler, step_fn, ms_per_step, collective=False, min_samples=3, max_seconds=3.0):
     """Short timed regions end before nvidia-smi delivers its first line: keep the GPU busy with the same step (outside
-    the timed region) until a few samples exist, so the clocks record describes this workload under load."""
-    t0, i = time.perf_counter(), 0
-    while sampler.n_samples() < min_samples and time.perf_counter() - t0 < max_seconds:
-        step_fn(i)
-        i += 1
-        if i % 8 == 0:
-            th.cuda.synchronize()
+    the timed region) until a few samples exist, so the clocks record describes this workload under load.
+    collective=True: the step contains a collective (data-parallel learner), so EVERY rank must run the same number of
+    extra steps - a fixed count derived from the (max-over-ranks, hence identical) step time instead of a rank-local
+    "until nvidia-smi answered" loop, which would desynchronise the ranks and dead-lock the next all-reduce."""
+    if collective:
+        n = int(min(4000, max(1, 450.0 / max(ms_per_step, 1e-3))))
+        for i in range(n):
+            step_fn(i)
+            if i % 8 == 7:
+                th.cuda.synchronize()
+    else:
+        t0, i = time.perf_counter(), 0
+        while sampler.n_samples() < min_samples and time.perf_counter() - t0 < max_seconds:
+            step_fn(i)
+            i += 1
+            if i % 8 == 0:
+                th.cuda.synchronize()
     th.cuda.synchronize()
     return sampler.stop()
 
@@ -418,8 +428,8 @@ def time_learner(ctx, learner, batch, steps, warmup, profile):
     ev1.record()
     ctx.barrier()
     phases = _lib.profile_end(max_phases=1024) if profile else []
-    clocks = _finish_sampling(th, sampler, lambda i: learner.train(batch, i, 0))
     ms = ctx.max_over_ranks(ev0.elapsed_time(ev1) / steps)
+    clocks = _finish_sampling(th, sampler, lambda i: learner.train(batch, i, 0), ms, collective=ctx.world > 1)
     phase_ms = {}
     for name, pms in phases:
         phase_ms[name] = phase_ms.get(name, 0.0) + pms / steps
@@ -477,6 +487,8 @@ def e2e_learner(ctx, learner, fields, B_local, T, mixer, steps):
     """Host-resident batch through the public API: H2D of every field the step reads + D2H read of the loss, timed
     by wall clock around synchronised steps (max over ranks)."""
     th = ctx.th
+    # Every rank must take the same path (the steps below contain a collective): pin first, then agree.
+    host, err = None, None
     try:
         import psutil
         input_bytes = sum(v.numel() * v.element_size() for v in fields.values())
@@ -486,6 +498,11 @@ def e2e_learner(ctx, learner, fields, B_local, T, mixer, steps):
             raise MemoryError("host has %.0f GB available, the pinned batches of %d ranks need %.0f GB"
                               % (avail / 1e9, ctx.world, need / 1e9))
         host = {k: th.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in fields.items()}
+    except Exception as ex:                              # e.g. the pod cannot pin 30 GB
+        err = repr(ex)[:200]
+    if ctx.max_over_ranks(0.0 if err is None else 1.0) > 0:
+        return {"value": None, "unit": UNIT, "error": err or "another rank could not pin its batch"}
+    try:
         hb = _DictBatch(host, B_local, T)
         learner.train(hb, 0, 0)                          # warm-up (allocates the device copies)
         ctx.barrier()
@@ -501,7 +518,9 @@ def e2e_learner(ctx, learner, fields, B_local, T, mixer, steps):
         return {"value": ctx.world * B_local / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": dt * 1e3, "steps": steps, "loss": loss,
                 "note": "per rank: pinned host batch of %d episodes -> H2D -> train -> loss.item()" % B_local}
-    except Exception as ex:                              # e.g. the pod cannot pin 30 GB
+    except Exception as ex:
+        if ctx.world > 1:
+            raise                                        # a rank-local failure inside collective steps cannot be skipped safely
         return {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 
 
@@ -591,8 +610,8 @@ def rollout_record(ctx, a, envs, precision, steps, warmup, e2e_steps, with_cpu):
     ev1.record()
     ctx.barrier()
     launches = (_lib.lib().pmb_launch_count() - launches0) // max(1, steps)
-    clocks = _finish_sampling(th, sampler, lambda i: mac.select_actions(batch, 1 + i % 3, 0))
     ms = ctx.max_over_ranks(ev0.elapsed_time(ev1) / steps)
+    clocks = _finish_sampling(th, sampler, lambda i: mac.select_actions(batch, 1 + i % 3, 0), ms)     # no collective in this step
     value = ctx.world * envs * N / (ms * 1e-3)
     rows = envs * N
     algo_bytes = rows * (O * 4 + 2 * H * 4 + A * 4 + 8 + 8)
@@ -675,6 +694,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the select_actions / configs 1-3 / weak / dp_equal sub-records")
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--cpu-envs", type=int, default=256)
+    ap.add_argument("--hang-timeout", type=int, default=420, help="seconds after which a stuck run dumps its stacks and exits")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the main config's step as a CUDA graph too")
     ap.add_argument("--action-rng", default="philox", choices=["philox", "torch"],
                     help="select_actions: where the epsilon-greedy draws come from")
@@ -709,6 +729,10 @@ def main():
     if a.impl == "reference":
         return reference_arm(a, cfg)
 
+    # a multi-rank job that stops making progress (a rank died, a collective mismatched) must not sit in NCCL's 10-minute
+    # watchdog: dump the stacks and exit after a generous bound
+    import faulthandler
+    faulthandler.dump_traceback_later(a.hang_timeout, exit=True)
     ctx = Ctx()
     th = ctx.th
     from pymarl_b200.data_parallel import shard_slice
