@@ -649,6 +649,42 @@ def rollout_record(ctx, a, envs, precision, steps, warmup, e2e_steps, with_cpu):
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
 
 
+def rollout_loop_record(ctx, precision, n_envs=4096, episode_limit=60, runs=3):
+    """whole rollouts through pymarl_b200.runners.VectorRunner - `n_envs` SMAC-shaped synthetic envs
+    (27m_vs_30m shapes) stepped on the device until every episode ended (time limit `episode_limit`), each timestep =
+    fused select_actions + three pmb_batch_update launches (actions + one-hot, reward / terminated, next state / avail /
+    obs + filled) + the env's own device ops.  agent-steps/s over env steps actually taken, wall clock around
+    synchronised runs (the loop syncs once per timestep for the live-env count)."""
+    th = ctx.th
+    from pymarl_b200 import mac_REGISTRY
+    from pymarl_b200.runners import VectorRunner, SyntheticVectorEnv
+    from pymarl_b200.synthetic import make_scheme
+    shape = SMAC_SHAPES["27m_vs_30m"]
+    args = default_args(shape, mixer="qmix", device="cuda", use_cuda=True, precision=precision, action_rng="philox",
+                        batch_size_run=n_envs)
+    th.manual_seed(7)
+    scheme, groups = make_scheme(shape)
+    scheme["actions_onehot"] = {"vshape": (shape.n_actions,), "dtype": th.float32, "group": "agents"}
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    mac.cuda()
+    env = SyntheticVectorEnv(n_envs, shape.n_agents, shape.obs_dim, shape.state_dim, shape.n_actions,
+                             episode_limit=episode_limit, seed=11 + ctx.rank, p_end=0.01, device=ctx.dev)
+    runner = VectorRunner(args, env)
+    runner.setup(mac)
+    runner.run()                                          # warm-up
+    th.cuda.synchronize()
+    t_env0, t0 = runner.t_env, time.perf_counter()
+    for _ in range(runs):
+        runner.run()
+    th.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    steps = runner.t_env - t_env0
+    return {"metric": "rollout_loop_agent_steps_per_sec", "value": steps * shape.n_agents / dt, "unit": RO_UNIT,
+            "env_steps": steps, "seconds": dt, "runs": runs,
+            "config": {"workload": "VectorRunner.run: select_actions + EpisodeBatch.update per timestep, synthetic device envs",
+                       "envs": n_envs, "n_agents": shape.n_agents, "episode_limit": episode_limit}}
+
+
 def small_config_record(ctx, name, precision, steps, warmup):
     """BASELINE configs 1-3 on one GPU: the whole step replayed as ONE CUDA graph (args.cuda_graph); per-kernel times
     from a separate eager pass; the reference on the host cores next to it."""
@@ -792,6 +828,11 @@ def main():
         select_actions = rollout_record(ctx, a, 16384, a.precision, 200, 20, 0 if a.no_e2e else 10,
                                         with_cpu=(ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline))
         if ctx.world == 1 and a.config == "27m_vs_30m":
+            try:
+                select_actions["rollout_loop"] = rollout_loop_record(ctx, a.precision)
+            except Exception as ex:
+                select_actions["rollout_loop"] = {"error": repr(ex)[:300]}
+            th.cuda.empty_cache()
             configs = {}
             for name in ("3m", "2s3z", "MMM2_vdn", "MMM2_iql"):
                 try:
