@@ -2,6 +2,7 @@
 // the whole learner step (learners/q_learner.py:37-107).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -679,7 +680,8 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         // With very few tiles (2 passes x n_tiles CTAs fit) every CTA takes ONE tile: no ping-pong, shorter per-step chain.
         const int tpc = 2 * n_tiles <= sm_count() ? 1 : 2;
         const int gru_ctas = (n_tiles + tpc - 1) / tpc;
-        const bool fork_tg = 2 * gru_ctas <= sm_count();
+        static const int fork_mode = []() { const char* e = getenv("PMB_FORK"); return e ? atoi(e) : -1; }();   // A/B switch: 0 never, 1 always
+        const bool fork_tg = fork_mode >= 0 ? fork_mode != 0 : 4 * 2 * gru_ctas <= 5 * sm_count();   // up to 1.25 x the SMs: the few CTAs that wait start when the first (shorter) target CTAs retire - measured 4.22 -> 3.79 ms on MMM2 / 2048 (160 CTAs)
         PHASE(s, fork_tg ? "gru_unroll_fwd_both_tc" : "gru_unroll_fwd_online_tc");
         if ((rc = pack_gru(on, gru_img))) return rc;
         if ((rc = pack_gru(tg, gru_img + 57344))) return rc;
