@@ -291,6 +291,42 @@ int pmb_batch_update(const pmb_update_field* fields_host, int32_t n_fields, cons
 int pmb_h2d_rows(void* dst_dev, const void* src_host, int64_t rows, int64_t row_bytes, int64_t src_pitch_bytes,
                  pmb_stream stream);
 
+/* ---- COMA learner (learners/coma_learner.py:32-148, modules/critics/coma.py:22-59,
+ * utils/rl_utils.py:4-15) - fp32 (CUDA-core) tier --------------------------------------------------------------------
+ * pmb_dims: E = critic hidden width (128 in the reference), mixer ignored, S = state dim (required).
+ * Flat critic layout = state_dict order: fc1.weight [E, D] | fc1.bias | fc2.weight [E, E] | fc2.bias | fc3.weight [A, E] |
+ * fc3.bias with D = S + O + 2 N A + N (coma.py:52-59).  The critic's one-hot inputs are generated from actions / filled;
+ * actions_onehot is never read.
+ * pmb_coma_train_step: target critic over all T -> td-lambda targets -> for t = T-2 .. 0 one critic fwd / bwd / clip /
+ * RMSprop step (skipped when nothing is unmasked at t) -> agent unroll over T-1 steps -> policy head (masked softmax,
+ * epsilon floor, renormalisation) -> COMA loss -> BPTT with the dense d(loss)/d(logits) -> clip / RMSprop of the agent.
+ * stats: (T-1) + 1 rows of 16 doubles, zeroed by the call.  Row t < T-1 (critic step t): [mask_sum, td2_sum, tdabs_sum,
+ * qtaken_sum, target_sum, grad_norm, loss, clip_coef]; row T-1 (agent): [mask_sum (x N), sum(adv log_pi mask),
+ * sum(adv mask), sum(pi_max mask), -, grad_norm, -, clip_coef].  The hard target-critic sync (:92-94) is the host's. */
+typedef struct pmb_coma_hparams {
+    float gamma, td_lambda, lr, critic_lr, alpha, eps, grad_norm_clip;
+    float epsilon;                       /* mac.action_selector.epsilon: the epsilon floor of BasicMAC.forward */
+} pmb_coma_hparams;
+int64_t pmb_coma_critic_numel(const pmb_dims* d);
+int64_t pmb_coma_workspace_bytes(const pmb_dims* d);
+int pmb_coma_workspace_views(const pmb_dims* d, void* workspace, float** q_vals, float** targets, float** pi, float** logits);
+int pmb_coma_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_coma_hparams* hp, float* agent_p, float* agent_g,
+                        float* agent_sq, float* critic_p, float* critic_g, float* critic_sq, const float* target_critic_p,
+                        void* workspace, int64_t workspace_bytes, double* stats, pmb_stream stream);
+/* COMACritic.forward(batch, t) alone (coma.py:22-27): q_out [B][nt][N][A] for batch timesteps t0 .. t0 + nt - 1;
+ * workspace >= pmb_coma_workspace_bytes(d). */
+int pmb_coma_critic_fwd(const pmb_dims* d, const pmb_batch* b, const float* critic_p, int32_t t0, int32_t nt, float* q_out,
+                        void* workspace, int64_t workspace_bytes, pmb_stream stream);
+/* BasicMAC.forward's policy head for agent_output_type == "pi_logits" (controllers/basic_controller.py:51-73,
+ * mask_before_softmax): probs [rows][A] from logits / avail [rows][A]; test_mode: plain masked softmax. */
+int pmb_policy_head(int64_t rows, int32_t A, float epsilon, int32_t test_mode, const float* logits, const int32_t* avail,
+                    float* probs, pmb_stream stream);
+/* MultinomialActionSelector.select_action (components/action_selectors.py:19-31): Categorical(masked probs).sample() =
+ * arg-max(p / Exp(1)); expo [rows][A] injects the draws (bit-exact with torch's generator order), else an in-kernel
+ * counter-based generator keyed by (seed, offset); greedy != 0: arg-max of the masked probabilities (test mode). */
+int pmb_multinomial(int64_t rows, int32_t A, const float* probs, const int32_t* avail, const float* expo, int32_t greedy,
+                    uint64_t seed, uint64_t offset, int64_t* actions_out, pmb_stream stream);
+
 /* views into the learner workspace, for tests and the Python mirror */
 typedef struct pmb_ws_views {
     float *x_on, *x_tg, *h_stash, *gates, *q_on, *q_tg, *chosen, *tmax, *raw_on, *raw_tg,

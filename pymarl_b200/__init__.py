@@ -28,6 +28,8 @@ def install_into_reference():
     import modules.agents as ref_agents
     import components.action_selectors as ref_selectors
     ref_learners.REGISTRY["q_learner"] = le_REGISTRY["q_learner"]
+    ref_learners.REGISTRY["coma_learner"] = le_REGISTRY["coma_learner"]
+    ref_selectors.REGISTRY["multinomial"] = action_REGISTRY["multinomial"]
     ref_controllers.REGISTRY["basic_mac"] = mac_REGISTRY["basic_mac"]
     ref_agents.REGISTRY["rnn"] = agent_REGISTRY["rnn"]
     ref_selectors.REGISTRY["epsilon_greedy"] = action_REGISTRY["epsilon_greedy"]

@@ -54,6 +54,10 @@ class HParams(C.Structure):
                 ("keep_q", C.c_int32)]
 
 
+class ComaHParams(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("gamma", "td_lambda", "lr", "critic_lr", "alpha", "eps", "grad_norm_clip", "epsilon")]
+
+
 class GatherField(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes_per_episode", C.c_int64)]
 
@@ -117,6 +121,15 @@ _SIGS = {
     "pmb_gemm_bf16_atb_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "pmb_gemm_bf16_atb": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P, _P, _P,
                                     C.c_int64, _P]),
+    "pmb_coma_critic_numel": (C.c_int64, [C.POINTER(Dims)]),
+    "pmb_coma_workspace_bytes": (C.c_int64, [C.POINTER(Dims)]),
+    "pmb_coma_workspace_views": (C.c_int, [C.POINTER(Dims), _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "pmb_coma_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.POINTER(ComaHParams), _P, _P, _P, _P, _P, _P, _P, _P,
+                                      C.c_int64, _P, _P]),
+    "pmb_coma_critic_fwd": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
+    "pmb_policy_head": (C.c_int, [C.c_int64, C.c_int32, C.c_float, C.c_int32, _P, _P, _P, _P]),
+    "pmb_multinomial": (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "pmb_qlearner_train_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.POINTER(HParams), _P, _P, _P, _P, _P,
                                           C.c_int64, _P, _P]),
 }

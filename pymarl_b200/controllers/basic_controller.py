@@ -27,8 +27,10 @@ class BasicMAC:
         self.args = args
         if getattr(args, "action_input_representation", None) is not None or getattr(args, "obs_decoder", None) is not None:
             raise NotImplementedError("pymarl_b200.BasicMAC implements the flat-observation RNN agent only")
-        if getattr(args, "agent_output_type", "q") != "q":
-            raise NotImplementedError("agent_output_type must be 'q'")
+        if getattr(args, "agent_output_type", "q") not in ("q", "pi_logits"):
+            raise NotImplementedError("agent_output_type must be 'q' or 'pi_logits'")
+        if getattr(args, "agent_output_type", "q") == "pi_logits" and not getattr(args, "mask_before_softmax", True):
+            raise NotImplementedError("pi_logits is implemented with mask_before_softmax = True (the reference default)")
         input_shape = self._get_input_shape(scheme)
         self._build_agents(input_shape)
         self.agent_output_type = args.agent_output_type
@@ -115,6 +117,10 @@ class BasicMAC:
         basic_controller.py:33,49), then epsilon-greedy on the rows `bs` (:34-37)."""
         sel = self.action_selector
         full = isinstance(bs, slice) and bs == slice(None)
+        if self.agent_output_type == "pi_logits":
+            probs = self.forward(ep_batch, t_ep, test_mode=test_mode)
+            avail = ep_batch["avail_actions"][:, t_ep]
+            return sel.select_action(probs[bs].to(self._device()), avail[bs].to(self._device()), t_env, test_mode=test_mode)
         if full and sel.rng != "torch":
             sel.epsilon = 0.0 if test_mode else sel.schedule.eval(t_env)
             seed, offset = sel.next_philox()
@@ -127,6 +133,15 @@ class BasicMAC:
 
     def forward(self, ep_batch, t, test_mode=False):
         q, _ = self._run_step(ep_batch, t)
+        if self.agent_output_type == "pi_logits":
+            # basic_controller.py:55-71: masked softmax, epsilon floor over the available actions, unavailable -> 0
+            avail = ep_batch["avail_actions"][:, t].to(device=q.device, dtype=th.int32).contiguous()
+            probs = th.empty_like(q)
+            rows, A = q.shape[0] * q.shape[1], q.shape[2]
+            _lib.check(_lib.lib().pmb_policy_head(rows, A, C.c_float(float(self.action_selector.epsilon)), int(bool(test_mode)),
+                                                  _lib.ptr(q), _lib.ptr(avail), _lib.ptr(probs), _lib.stream_ptr(q.device)),
+                       "pmb_policy_head")
+            q = probs
         return q.view(ep_batch.batch_size, self.n_agents, -1).to(ep_batch.device)
 
     def init_hidden(self, batch_size):

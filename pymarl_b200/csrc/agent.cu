@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(NT, 1)
 gru_unroll_bwd_kernel(AgentParams p, int A, int N, int T, int64_t R, const float* __restrict__ x,
                       const float* __restrict__ h_stash, float* __restrict__ gates,
                       const float* __restrict__ d_chosen, const int64_t* __restrict__ actions, int64_t actions_sb,
-                      float* __restrict__ dpre1) {
+                      float* __restrict__ dpre1, const float* __restrict__ dq_full) {
+    // dq_full != null (COMA policy gradient): dense dL/dq [T][R][A] for EVERY unrolled step instead of the Q-learner's
+    // gradient at the taken action of steps t < T-1
     constexpr int RT = 16 * RW, JW = H / 16, H3 = 3 * H, LDD = 4 * H + 1;
     extern __shared__ __align__(16) float smem[];
     float* Wih = smem;                        // [3H][H]
@@ -286,7 +288,14 @@ gru_unroll_bwd_kernel(AgentParams p, int A, int N, int T, int64_t R, const float
                 ldg_vec<JW>(ghn, g + 3 * H);
                 ldg_vec<JW>(hp, h_stash + ((int64_t)t * R + row) * H + j0);
                 ldg_vec<JW>(xk[i], x + ((int64_t)t * R + row) * H + j0);
-                if (t < T - 1) {
+                if (dq_full) {
+                    const float* dqr = dq_full + ((int64_t)t * R + row) * A;
+                    for (int a = 0; a < A; ++a) {
+                        const float dq = __ldg(dqr + a);
+#pragma unroll
+                        for (int jj = 0; jj < JW; ++jj) dh[i][jj] = fmaf(dq, W2[a * H + j0 + jj], dh[i][jj]);
+                    }
+                } else if (t < T - 1) {
                     float dq = __ldg(d_chosen + (bidx[i] * (T - 1) + t) * N + nidx[i]);
                     int a = (int)__ldg(actions + bidx[i] * actions_sb + (int64_t)t * N + nidx[i]);
 #pragma unroll
@@ -419,7 +428,7 @@ agent_scatter_grads_kernel(int A, int N, int T, int64_t R, const float* __restri
                 dp[u] = ti_tiles > 0 ? ti_fetch(dpre1, t, row, j) : __ldg(dpre1 + it * H + j);
                 if (use_act && t > 0 && __ldg(filled + b * filled_sb + (t - 1)) != 0)
                     ap[u] = (int)__ldg(actions + b * actions_sb + (int64_t)(t - 1) * N + n);
-                if (t < T - 1) {
+                if (d_chosen && t < T - 1) {           // d_chosen == null: the caller computes the fc2 gradients itself (dense dq)
                     dq[u] = __ldg(d_chosen + (b * (T - 1) + t) * N + n);
                     aa[u] = (int)__ldg(actions + b * actions_sb + (int64_t)t * N + n);
                     hv[u] = ti_tiles > 0 ? ti_fetch(h_stash, t + 1, row, j)
@@ -485,12 +494,12 @@ int launch_fwd(const AgentParams& p, int A, int64_t R, int nt, const float* x, c
 template <int H, int RW>
 int launch_bwd(const AgentParams& p, int A, int N, int T, int64_t R, const float* x, const float* h_stash,
                float* gates, const float* d_chosen, const int64_t* actions, int64_t actions_sb, float* dpre1,
-               cudaStream_t s) {
+               cudaStream_t s, const float* dq_full) {
     size_t bytes = BwdSmem<H, RW>::floats(A) * sizeof(float);
     auto kern = gru_unroll_bwd_kernel<H, RW>;
     PMB_SMEM_ATTR(kern, (int)bytes);
     unsigned grid = (unsigned)ceil_div(R, 16 * RW);
-    kern<<<grid, NT, bytes, s>>>(p, A, N, T, R, x, h_stash, gates, d_chosen, actions, actions_sb, dpre1);
+    kern<<<grid, NT, bytes, s>>>(p, A, N, T, R, x, h_stash, gates, d_chosen, actions, actions_sb, dpre1, dq_full);
     PMB_LAUNCH_CHECK("gru_unroll_bwd_kernel");
     return PMB_OK;
 }
@@ -524,14 +533,15 @@ int gru_fwd_dispatch(const pmb_dims* d, const AgentParams& p, int64_t R, int nt,
 }
 
 int gru_bwd_dispatch(const pmb_dims* d, const pmb_batch* b, const AgentParams& p, const float* x,
-                     const float* h_stash, float* gates, const float* d_chosen, float* dpre1, cudaStream_t s) {
+                     const float* h_stash, float* gates, const float* d_chosen, float* dpre1, cudaStream_t s,
+                     const float* dq_full) {
     int64_t R = (int64_t)d->B * d->N;
     int rw = pick_rw(R);
 #define PMB_BWD(HH)                                                                                              \
     return rw == 4 ? launch_bwd<HH, 4>(p, d->A, d->N, d->T, R, x, h_stash, gates, d_chosen, b->actions,           \
-                                       b->actions_sb, dpre1, s)                                                   \
+                                       b->actions_sb, dpre1, s, dq_full)                                          \
                    : launch_bwd<HH, 1>(p, d->A, d->N, d->T, R, x, h_stash, gates, d_chosen, b->actions,           \
-                                       b->actions_sb, dpre1, s)
+                                       b->actions_sb, dpre1, s, dq_full)
     switch (d->H) {
         case 16: PMB_BWD(16);
         case 32: PMB_BWD(32);

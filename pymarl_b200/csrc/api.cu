@@ -17,7 +17,8 @@ namespace pmb {
 int gru_fwd_dispatch(const pmb_dims* d, const AgentParams& p, int64_t R, int nt, const float* x, const float* h0,
                      float* h_stash, float* gates, float* q, float* h_last, cudaStream_t s);
 int gru_bwd_dispatch(const pmb_dims* d, const pmb_batch* b, const AgentParams& p, const float* x,
-                     const float* h_stash, float* gates, const float* d_chosen, float* dpre1, cudaStream_t s);
+                     const float* h_stash, float* gates, const float* d_chosen, float* dpre1, cudaStream_t s,
+                     const float* dq_full = nullptr);
 int64_t scatter_scratch_bytes(const pmb_dims* d);
 int scatter_grads_dispatch(const pmb_dims* d, const pmb_batch* b, const float* h_stash, const float* dpre1,
                            const float* d_chosen, AgentGrads gr, void* scratch, int64_t scratch_bytes, cudaStream_t s,
@@ -38,8 +39,25 @@ int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, co
 int launch_stats_reset(double* stats, cudaStream_t s);
 int launch_dp_pack(const double* stats, float* tail, cudaStream_t s);
 int launch_dp_unpack(const float* tail, double* stats, cudaStream_t s);
+// coma.cu
+int coma_launch_inputs(const pmb_dims* d, const pmb_batch* b, int t0, int nt, float* out, cudaStream_t s);
+int coma_launch_gather_taken(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const float* q, float* taken, cudaStream_t s);
+int coma_launch_td_lambda(const pmb_dims* d, const pmb_batch* b, float gamma, float lam, const float* taken, float* targets,
+                          cudaStream_t s);
+int coma_launch_critic_td(const pmb_dims* d, const pmb_batch* b, int t, const float* q_t, const float* targets, float* q_vals,
+                          float* dqv, int32_t* dqa, double* stats_row, cudaStream_t s);
+int coma_launch_critic_bwd_pointwise(int64_t R, int A, int Hc, const float* dqv, const int32_t* dqa, const float* w3,
+                                     const float* x2, float* dq_dense, float* dx2, cudaStream_t s);
+int launch_relu_mask(int64_t n, const float* x, float* dx, cudaStream_t s);
+int launch_transpose(int rows, int cols, const float* in, float* out, cudaStream_t s);
+int coma_launch_policy(const pmb_dims* d, const pmb_batch* b, float eps, const float* logits, const float* q_vals,
+                       float* dlogits, float* pi_out, double* stats_row, cudaStream_t s);
+int launch_policy_head(int64_t rows, int A, float eps, int test_mode, const float* logits, const int32_t* avail, float* probs,
+                       cudaStream_t s);
+int launch_multinomial(int64_t rows, int A, const float* probs, const int32_t* avail, const float* expo, int greedy,
+                       uint64_t seed, uint64_t offset, int64_t* out, cudaStream_t s);
 int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target, int do_sync, double* stats, float lr,
-                        float alpha, float eps, float clip, float* scratch, cudaStream_t s);
+                        float alpha, float eps, float clip, float* scratch, cudaStream_t s, int skip_if_empty = 0);
 
 // tc_gemm.cu (bf16 tcgen05 tier)
 int tc_gemm_plain(const float* A, RowMap amap, int64_t M, int K, const __nv_bfloat16* Wp, int Ncols_padded, int Nreal,
@@ -288,13 +306,13 @@ int fc1_fwd(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const AgentPa
 
 int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, const float* x_on, const float* h_stash,
               float* gates, const float* d_chosen, float* dpre1, float* flat_grad_agent, void* scratch,
-              int64_t scratch_bytes, cudaStream_t s) {
+              int64_t scratch_bytes, cudaStream_t s, const float* dq_full = nullptr) {
     AgentParams ap = agent_params(d, flat_agent);
     AgentGrads gr = agent_grads(d, flat_grad_agent);
     const int64_t R = (int64_t)d->B * d->N, rows = (int64_t)d->T * R;
     const int H = d->H;
     PHASE(s, "gru_unroll_bwd");
-    int rc = gru_bwd_dispatch(d, b, ap, x_on, h_stash, gates, d_chosen, dpre1, s);
+    int rc = gru_bwd_dispatch(d, b, ap, x_on, h_stash, gates, d_chosen, dpre1, s, dq_full);
     if (rc) return rc;
     PHASE(s, "dW_rnn_gemm_atb");
     // rnn.weight_ih / bias_ih:  [da_r | da_z | da_n]^T . x
@@ -317,7 +335,11 @@ int agent_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_agent, co
                       scratch_bytes, s);
     if (rc) return rc;
     PHASE(s, "agent_scatter_grads");
-    return scatter_grads_dispatch(d, b, h_stash, dpre1, d_chosen, gr, scratch, scratch_bytes, s);
+    rc = scatter_grads_dispatch(d, b, h_stash, dpre1, dq_full ? nullptr : d_chosen, gr, scratch, scratch_bytes, s);
+    if (rc || !dq_full) return rc;
+    // dense dq (COMA): fc2.weight / fc2.bias = dq^T . h_t over all (t, row); h_stash slot t + 1 holds h_t
+    return gemm_atb_any(PMB_PREC_FP32, dq_full, dense_map(d->A), d->A, h_stash + R * H, dense_map(H), H, rows, gr.fc2_w, H,
+                        gr.fc2_b, scratch, scratch_bytes, s);
 }
 
 // GRU / fc2 weight images of one agent: [w_ih 24 KB | w_hh 24 KB | fc2 8 KB] (bf16, K-major, 128B swizzle)
@@ -794,6 +816,219 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     }
     PHASE(s, "end");
     return PMB_OK;
+}
+
+}  // extern "C"
+
+/* ---- COMA ------------------------------------------------------------------------ */
+namespace pmb {
+namespace {
+struct ComaPlan {
+    int64_t D, Hc, R, Tp, chunk_nt, chunk_rows;
+    int64_t off[24];
+    int64_t scratch_bytes, total;
+};
+ComaPlan coma_plan(const pmb_dims* d) {
+    ComaPlan p;
+    p.D = (int64_t)d->S + d->O + 2 * (int64_t)d->N * d->A + d->N;
+    p.Hc = d->E;
+    p.R = (int64_t)d->B * d->N;
+    p.Tp = d->T - 1;
+    // the target critic runs over all T timesteps in chunks whose input matrix stays below ~256 MB
+    int64_t nt = ((int64_t)64 << 20) / (p.R * p.D);
+    if (nt < 1) nt = 1;
+    if (nt > d->T) nt = d->T;
+    p.chunk_nt = nt;
+    p.chunk_rows = p.R * nt;
+    const int64_t H = d->H, A = d->A;
+    int64_t sizes[24] = {
+        p.chunk_rows * p.D,            // 0 inp
+        p.chunk_rows * p.Hc,           // 1 x1
+        p.chunk_rows * p.Hc,           // 2 x2
+        p.chunk_rows * A,              // 3 qtmp
+        p.R * d->T,                    // 4 taken [B][T][N]
+        p.R * p.Tp,                    // 5 targets [B][T-1][N]
+        p.R * p.Tp * A,                // 6 q_vals [B][T-1][N][A]
+        p.R,                           // 7 dqv
+        p.R,                           // 8 dqa (int32)
+        p.R * A,                       // 9 dq dense
+        p.R * p.Hc,                    // 10 dx2
+        p.R * p.Hc,                    // 11 dx1
+        p.Hc * p.Hc,                   // 12 w2t
+        p.Tp * p.R * H,                // 13 x (agent fc1 out)
+        (p.Tp + 1) * p.R * H,          // 14 h_stash
+        p.Tp * p.R * 4 * H,            // 15 gates
+        p.Tp * p.R * A,                // 16 logits
+        p.Tp * p.R * A,                // 17 dlogits
+        p.Tp * p.R * H,                // 18 dpre1
+        p.Tp * p.R * A,                // 19 pi (diagnostics / tests)
+        0, 0, 0, 0};
+    int64_t off = 0;
+    for (int i = 0; i < 24; ++i) { p.off[i] = off; off += align_up(sizes[i] * 4, 256); }
+    pmb_dims da = *d;
+    da.T = (int32_t)p.Tp; da.precision = PMB_PREC_FP32; da.mixer = PMB_MIXER_NONE;
+    int64_t sc = p.Tp > 0 ? agent_bwd_scratch(&da) : 0;
+    int64_t c1 = gemm_atb_scratch_bytes((int)A, (int)p.Hc, p.R), c2 = gemm_atb_scratch_bytes((int)p.Hc, (int)p.Hc, p.R),
+            c3 = gemm_atb_scratch_bytes((int)p.Hc, (int)p.D, p.R);
+    if (c1 > sc) sc = c1;
+    if (c2 > sc) sc = c2;
+    if (c3 > sc) sc = c3;
+    if (sc < 4096 * 4) sc = 4096 * 4;
+    p.scratch_bytes = align_up(sc, 256);
+    p.total = off + p.scratch_bytes;
+    return p;
+}
+struct CriticParams { const float *w1, *b1, *w2, *b2, *w3, *b3; };
+struct CriticGrads { float *w1, *b1, *w2, *b2, *w3, *b3; };
+template <class P, class F>
+P critic_views(F* flat, int64_t D, int64_t Hc, int64_t A) {
+    F* w1 = flat; F* b1 = w1 + Hc * D; F* w2 = b1 + Hc; F* b2 = w2 + Hc * Hc; F* w3 = b2 + Hc; F* b3 = w3 + A * Hc;
+    return P{w1, b1, w2, b2, w3, b3};
+}
+int critic_fwd(const CriticParams& c, const float* inp, int64_t rows, int64_t D, int Hc, int A, float* x1, float* x2, float* q,
+               cudaStream_t s) {
+    int rc;
+    if ((rc = launch_gemm_tn(inp, dense_map(D), rows, (int)D, c.w1, (int)D, Hc, c.b1, x1, Hc, 1, s))) return rc;
+    if ((rc = launch_gemm_tn(x1, dense_map(Hc), rows, Hc, c.w2, Hc, Hc, c.b2, x2, Hc, 1, s))) return rc;
+    return launch_gemm_tn(x2, dense_map(Hc), rows, Hc, c.w3, Hc, A, c.b3, q, A, 0, s);
+}
+int validate_coma(const pmb_dims* d) {
+    int rc = validate_dims(d);
+    if (rc) return rc;
+    PMB_REQUIRE(d->T >= 2 && d->S > 0 && d->E > 0 && d->E <= 1024 && d->A <= 64, "coma: need T >= 2, a state, critic width 1..1024, n_actions <= 64");
+    return PMB_OK;
+}
+}  // namespace
+}  // namespace pmb
+
+extern "C" {
+
+int64_t pmb_coma_critic_numel(const pmb_dims* d) {
+    if (validate_coma(d)) return -1;
+    const int64_t D = (int64_t)d->S + d->O + 2 * (int64_t)d->N * d->A + d->N, Hc = d->E;
+    return Hc * D + Hc + Hc * Hc + Hc + (int64_t)d->A * Hc + d->A;
+}
+
+int64_t pmb_coma_workspace_bytes(const pmb_dims* d) {
+    if (validate_coma(d)) return -1;
+    return coma_plan(d).total;
+}
+
+int pmb_coma_workspace_views(const pmb_dims* d, void* workspace, float** q_vals, float** targets, float** pi, float** logits) {
+    if (validate_coma(d)) return PMB_ERR_INVALID;
+    ComaPlan p = coma_plan(d);
+    char* base = static_cast<char*>(workspace);
+    if (q_vals) *q_vals = reinterpret_cast<float*>(base + p.off[6]);
+    if (targets) *targets = reinterpret_cast<float*>(base + p.off[5]);
+    if (pi) *pi = reinterpret_cast<float*>(base + p.off[19]);
+    if (logits) *logits = reinterpret_cast<float*>(base + p.off[16]);
+    return PMB_OK;
+}
+
+int pmb_coma_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_coma_hparams* hp, float* agent_p, float* agent_g,
+                        float* agent_sq, float* critic_p, float* critic_g, float* critic_sq, const float* target_critic_p,
+                        void* workspace, int64_t workspace_bytes, double* stats, pmb_stream stream) {
+    int rc = validate_coma(d);
+    if (rc) return rc;
+    PMB_REQUIRE(b && hp && agent_p && agent_g && agent_sq && critic_p && critic_g && critic_sq && target_critic_p && workspace && stats,
+                "coma_train_step: NULL pointer");
+    PMB_REQUIRE(b->obs && b->state && b->actions && b->avail && b->reward && b->terminated && b->filled && !b->ep_index,
+                "coma_train_step: batch field is NULL (or ep_index given)");
+    cudaStream_t s = (cudaStream_t)stream;
+    ComaPlan P = coma_plan(d);
+    if (workspace_bytes < P.total) { set_error("coma workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)P.total); return PMB_ERR_WORKSPACE; }
+    char* base = static_cast<char*>(workspace);
+    auto f = [&](int i) { return reinterpret_cast<float*>(base + P.off[i]); };
+    float *inp = f(0), *x1 = f(1), *x2 = f(2), *qtmp = f(3), *taken = f(4), *targets = f(5), *q_vals = f(6), *dqv = f(7);
+    int32_t* dqa = reinterpret_cast<int32_t*>(f(8));
+    float *dq = f(9), *dx2 = f(10), *dx1 = f(11), *w2t = f(12), *x = f(13), *h_stash = f(14), *gates = f(15), *logits = f(16),
+          *dlogits = f(17), *dpre1 = f(18), *pi = f(19);
+    void* scratch = base + P.total - P.scratch_bytes;
+    const int64_t D = P.D, R = P.R;
+    const int Hc = (int)P.Hc, A = d->A, Tp = (int)P.Tp;
+    const int64_t n_critic = pmb_coma_critic_numel(d);
+    CriticParams cp = critic_views<CriticParams, const float>(critic_p, D, Hc, A);
+    CriticParams tp = critic_views<CriticParams, const float>(target_critic_p, D, Hc, A);
+    CriticGrads cg = critic_views<CriticGrads, float>(critic_g, D, Hc, A);
+    PMB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * PMB_S_COUNT * (Tp + 1), s));
+
+    // coma_learner.py:105-109: target critic over all timesteps -> Q of the taken actions -> td-lambda targets
+    for (int t0 = 0; t0 < d->T; t0 += (int)P.chunk_nt) {
+        const int nt = d->T - t0 < P.chunk_nt ? d->T - t0 : (int)P.chunk_nt;
+        if ((rc = coma_launch_inputs(d, b, t0, nt, inp, s))) return rc;
+        if ((rc = critic_fwd(tp, inp, R * nt, D, Hc, A, x1, x2, qtmp, s))) return rc;
+        if ((rc = coma_launch_gather_taken(d, b, t0, nt, qtmp, taken, s))) return rc;
+    }
+    if ((rc = coma_launch_td_lambda(d, b, hp->gamma, hp->td_lambda, taken, targets, s))) return rc;
+
+    // :118-146: one critic optimiser step per timestep, backwards in time
+    for (int t = Tp - 1; t >= 0; --t) {
+        double* st = stats + (int64_t)t * PMB_S_COUNT;
+        if ((rc = coma_launch_inputs(d, b, t, 1, inp, s))) return rc;
+        if ((rc = critic_fwd(cp, inp, R, D, Hc, A, x1, x2, qtmp, s))) return rc;
+        if ((rc = coma_launch_critic_td(d, b, t, qtmp, targets, q_vals, dqv, dqa, st, s))) return rc;
+        if ((rc = coma_launch_critic_bwd_pointwise(R, A, Hc, dqv, dqa, cp.w3, x2, dq, dx2, s))) return rc;
+        if ((rc = launch_gemm_atb(dq, dense_map(A), A, x2, dense_map(Hc), Hc, R, cg.w3, Hc, cg.b3, scratch, P.scratch_bytes, s))) return rc;
+        if ((rc = launch_gemm_atb(dx2, dense_map(Hc), Hc, x1, dense_map(Hc), Hc, R, cg.w2, Hc, cg.b2, scratch, P.scratch_bytes, s))) return rc;
+        if ((rc = launch_transpose(Hc, Hc, cp.w2, w2t, s))) return rc;
+        if ((rc = launch_gemm_tn(dx2, dense_map(Hc), R, Hc, w2t, Hc, Hc, nullptr, dx1, Hc, 0, s))) return rc;
+        if ((rc = launch_relu_mask(R * Hc, x1, dx1, s))) return rc;
+        if ((rc = launch_gemm_atb(dx1, dense_map(Hc), Hc, inp, dense_map(D), (int)D, R, cg.w1, D, cg.b1, scratch, P.scratch_bytes, s))) return rc;
+        if ((rc = launch_clip_rmsprop(n_critic, critic_p, critic_g, critic_sq, nullptr, 0, st, hp->critic_lr, hp->alpha, hp->eps,
+                                      hp->grad_norm_clip, static_cast<float*>(scratch), s, 1))) return rc;
+    }
+
+    // :55-90: agent unroll over t = 0 .. T-2, policy head, COMA loss, policy gradient, clip + RMSprop
+    pmb_dims da = *d;
+    da.T = Tp; da.precision = PMB_PREC_FP32; da.mixer = PMB_MIXER_NONE;
+    AgentParams ap = agent_params(&da, agent_p);
+    if ((rc = fc1_fwd(&da, b, 0, Tp, ap, x, s))) return rc;
+    if ((rc = gru_fwd_dispatch(&da, ap, R, Tp, x, nullptr, h_stash, gates, logits, nullptr, s))) return rc;
+    double* sa = stats + (int64_t)Tp * PMB_S_COUNT;
+    if ((rc = coma_launch_policy(d, b, hp->epsilon, logits, q_vals, dlogits, pi, sa, s))) return rc;
+    if ((rc = agent_bwd(&da, b, agent_p, x, h_stash, gates, nullptr, dpre1, agent_g, scratch, P.scratch_bytes, s, dlogits))) return rc;
+    pmb_layout L;
+    compute_layout(&da, &L);
+    return launch_clip_rmsprop(L.n_agent, agent_p, agent_g, agent_sq, nullptr, 0, sa, hp->lr, hp->alpha, hp->eps,
+                               hp->grad_norm_clip, static_cast<float*>(scratch), s, 0);
+}
+
+int pmb_coma_critic_fwd(const pmb_dims* d, const pmb_batch* b, const float* critic_p, int32_t t0, int32_t nt, float* q_out,
+                        void* workspace, int64_t workspace_bytes, pmb_stream stream) {
+    int rc = validate_coma(d);
+    if (rc) return rc;
+    PMB_REQUIRE(b && critic_p && q_out && workspace && b->obs && b->state && b->actions && b->filled && !b->ep_index,
+                "coma_critic_fwd: NULL pointer");
+    PMB_REQUIRE(t0 >= 0 && nt > 0 && t0 + nt <= d->T, "coma_critic_fwd: bad time range");
+    cudaStream_t s = (cudaStream_t)stream;
+    ComaPlan P = coma_plan(d);
+    if (workspace_bytes < P.total) { set_error("coma workspace too small"); return PMB_ERR_WORKSPACE; }
+    char* base = static_cast<char*>(workspace);
+    auto f = [&](int i) { return reinterpret_cast<float*>(base + P.off[i]); };
+    CriticParams cp = critic_views<CriticParams, const float>(critic_p, P.D, P.Hc, d->A);
+    // q_out [B][nt][N][A]; chunks of timesteps keep the materialised input matrix bounded (rows are (b, tt, n) per chunk,
+    // so a chunk's rows are scattered into q_out per episode)
+    for (int c0 = 0; c0 < nt; c0 += (int)P.chunk_nt) {
+        const int cn = nt - c0 < P.chunk_nt ? nt - c0 : (int)P.chunk_nt;
+        if ((rc = coma_launch_inputs(d, b, t0 + c0, cn, f(0), s))) return rc;
+        if ((rc = critic_fwd(cp, f(0), P.R * cn, P.D, (int)P.Hc, d->A, f(1), f(2), f(3), s))) return rc;
+        PMB_CUDA(cudaMemcpy2DAsync(q_out + (int64_t)c0 * d->N * d->A, sizeof(float) * nt * d->N * d->A, f(3),
+                                   sizeof(float) * cn * d->N * d->A, sizeof(float) * cn * d->N * d->A, (size_t)d->B,
+                                   cudaMemcpyDeviceToDevice, s));
+    }
+    return PMB_OK;
+}
+
+int pmb_policy_head(int64_t rows, int32_t A, float epsilon, int32_t test_mode, const float* logits, const int32_t* avail,
+                    float* probs, pmb_stream stream) {
+    PMB_REQUIRE(rows >= 0 && A > 0 && A <= 64 && logits && avail && probs, "policy_head: bad arguments");
+    return launch_policy_head(rows, A, epsilon, test_mode, logits, avail, probs, (cudaStream_t)stream);
+}
+
+int pmb_multinomial(int64_t rows, int32_t A, const float* probs, const int32_t* avail, const float* expo, int32_t greedy,
+                    uint64_t seed, uint64_t offset, int64_t* actions_out, pmb_stream stream) {
+    PMB_REQUIRE(rows >= 0 && A > 0 && probs && avail && actions_out, "multinomial: bad arguments");
+    return launch_multinomial(rows, A, probs, avail, expo, greedy, seed, offset, actions_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

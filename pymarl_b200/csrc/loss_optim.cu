@@ -106,8 +106,10 @@ grad_sumsq_kernel(int64_t n, const float* __restrict__ g, double* __restrict__ p
 __global__ void __launch_bounds__(OPT_THREADS)
 rmsprop_apply_kernel(int64_t n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ sq,
                      float* __restrict__ target, int do_sync, const double* __restrict__ partial,
-                     double* __restrict__ stats, float lr, float alpha, float eps, float clip) {
+                     double* __restrict__ stats, float lr, float alpha, float eps, float clip, int skip_if_empty) {
     __shared__ float s_scale, s_coef;
+    // skip_if_empty (COMA critic, coma_learner.py:120-121 `if mask_t.sum() == 0: continue`): no step when nothing is unmasked
+    if (skip_if_empty && stats[PMB_S_MASK_SUM] <= 0.0) return;
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int b = 0; b < OPT_BLOCKS; ++b) tot += partial[b];
@@ -174,13 +176,13 @@ int launch_dp_unpack(const float* tail, double* stats, cudaStream_t s) {
 }
 
 int launch_clip_rmsprop(int64_t n, float* p, float* g, float* sq, float* target, int do_sync, double* stats, float lr,
-                        float alpha, float eps, float clip, float* scratch, cudaStream_t s) {
+                        float alpha, float eps, float clip, float* scratch, cudaStream_t s, int skip_if_empty) {
     if (n <= 0) return PMB_OK;
     double* partial = reinterpret_cast<double*>(scratch);          // OPT_BLOCKS doubles (<= 4096 floats)
     grad_sumsq_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, s>>>(n, g, partial);
     PMB_LAUNCH_CHECK("grad_sumsq_kernel");
     rmsprop_apply_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, s>>>(n, p, g, sq, target, do_sync, partial, stats, lr, alpha,
-                                                           eps, clip);
+                                                           eps, clip, skip_if_empty);
     PMB_LAUNCH_CHECK("rmsprop_apply_kernel");
     return PMB_OK;
 }

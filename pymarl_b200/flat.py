@@ -71,3 +71,38 @@ def ensure_block(module, kind, dims):
     flat = th.empty(n, dtype=th.float32, device=p0.device)
     bind(flat, layout, module, kind, base=0)
     return flat.data_ptr()
+
+
+def bind_in_order(module, keys, flat=None, grad=None):
+    """Generic variant for modules outside the agent / mixer layout (the COMA critic): lay the named parameters out
+    back to back in `keys` order in one flat fp32 buffer (created on the module's device when not given), re-point
+    .data (and .grad) to views of it, and return the buffer."""
+    params = _named(module)
+    n = sum(params[k].numel() for k in keys)
+    p0 = params[keys[0]]
+    if flat is None:
+        flat = th.empty(n, dtype=th.float32, device=p0.device)
+    off = 0
+    with th.no_grad():
+        for k in keys:
+            p = params[k]
+            view = flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data.to(device=flat.device, dtype=flat.dtype))
+            p.data = view
+            if grad is not None:
+                p.grad = grad[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+    object.__setattr__(module, "_pmb_flat", flat)
+    return flat
+
+
+def is_bound_in_order(module, keys, flat):
+    """True when the named parameters still are the back-to-back views of `flat` that bind_in_order made."""
+    params = _named(module)
+    off = 0
+    for k in keys:
+        p = params[k]
+        if not p.is_cuda or p.dtype != th.float32 or p.data_ptr() != flat.data_ptr() + 4 * off:
+            return False
+        off += p.numel()
+    return True

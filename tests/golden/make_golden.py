@@ -391,13 +391,91 @@ def run_episode_update():
     np.savez_compressed(path, **out)
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
+
+def run_coma(name="coma_tiny", seed=41, n_steps=2, **over):
+    """The reference COMALearner (learners/coma_learner.py) + COMACritic + BasicMAC with agent_output_type "pi_logits" +
+    MultinomialActionSelector on a tiny seeded batch: inputs, initial parameters, the pieces that can be read without
+    touching train() (target-critic Q, td-lambda targets, the MAC's policy output per timestep, sampled actions with the
+    generator draws), and after each of `n_steps` train() calls the logged statistics and every parameter / RMSprop state."""
+    from utils.rl_utils import build_td_lambda_targets
+    tiny = SmacShape("tiny", 3, 10, 14, 5, 8)
+    kw = dict(rnn_hidden_dim=16, agent_output_type="pi_logits", action_selector="multinomial", learner="coma_learner",
+              critic_lr=5e-4, td_lambda=0.8, mask_before_softmax=True, epsilon_start=0.5, epsilon_finish=0.01,
+              epsilon_anneal_time=100000, target_update_interval=3, learner_log_interval=0, test_greedy=True)
+    kw.update(over)
+    args = default_args(tiny, mixer=None, **kw)
+    B, T = 4, 8
+    fields = numpy_episode_fields(tiny, B, T, seed=seed, ragged=True)
+    batch, scheme, groups = ref_batch(tiny, fields)
+    out = {"in/" + k: v for k, v in fields.items()}
+    th.manual_seed(seed)
+    # the fork's BasicMAC turns scheme["obs"]["vshape"] into a tuple in place (basic_controller.py:139-144), which
+    # COMACritic._get_input_shape (coma.py:52-59) cannot add to an int: give each its own copy of the scheme
+    sch = copy.deepcopy(dict(batch.scheme))
+    mac = ref_mac_REGISTRY[args.mac](copy.deepcopy(sch), groups, args)
+    logger = _Logger()
+    learner = ref_le_REGISTRY["coma_learner"](mac, sch, logger, args)
+    g = th.Generator().manual_seed(seed + 1)
+    with th.no_grad():
+        for p_ in learner.target_critic.parameters():
+            p_.add_(0.05 * th.randn(p_.shape, generator=g))
+    for tag, mod in (("agent", mac.agent), ("critic", learner.critic), ("target_critic", learner.target_critic)):
+        for k, v in state_np(mod).items():
+            out["init/%s/%s" % (tag, k)] = v
+    eps = float(mac.action_selector.epsilon)
+    out["epsilon"] = np.float64(eps)
+    with th.no_grad():
+        tq = learner.target_critic(batch)
+        out["fw/target_q"] = tq.numpy()
+        out["fw/critic_inputs"] = learner.critic._build_inputs(batch).numpy()
+        rewards = batch["reward"][:, :-1]
+        terminated = batch["terminated"][:, :-1].float()
+        mask = batch["filled"][:, :-1].float()
+        mask[:, 1:] = mask[:, 1:] * (1 - terminated[:, :-1])
+        taken = th.gather(tq, 3, batch["actions"]).squeeze(3)
+        out["fw/td_lambda_targets"] = build_td_lambda_targets(rewards, terminated, mask, taken, tiny.n_agents, args.gamma,
+                                                               args.td_lambda).numpy()
+        mac.init_hidden(B)
+        pis = [mac.forward(batch, t=t) for t in range(T - 1)]
+        out["fw/pi"] = th.stack(pis, 1).numpy()
+        mac.init_hidden(B)
+        out["fw/pi_test_t0"] = mac.forward(batch, t=0, test_mode=True).numpy()
+        # action selection: Categorical(masked policies).sample() consumes one exponential_ of the probs' shape
+        mac.init_hidden(B)
+        th.manual_seed(300)
+        acts = mac.select_actions(batch, t_ep=0, t_env=1234, bs=slice(None), test_mode=False)
+        th.manual_seed(300)
+        expo = th.empty(B * tiny.n_agents, tiny.n_actions).exponential_()
+        out["sel/actions"] = acts.numpy()
+        out["sel/expo"] = expo.numpy().reshape(B, tiny.n_agents, tiny.n_actions)
+        out["sel/epsilon"] = np.float64(mac.action_selector.epsilon)
+        mac.init_hidden(B)
+        out["sel/greedy"] = mac.select_actions(batch, t_ep=0, t_env=1234, test_mode=True).numpy()
+    mac.action_selector.epsilon = eps                   # select_action moved it; train() reads the attribute
+    for step in range(n_steps):
+        learner.train(batch, step, 0)
+        for key in ("critic_loss", "critic_grad_norm", "td_error_abs", "q_taken_mean", "target_mean", "advantage_mean",
+                    "coma_loss", "agent_grad_norm", "pi_max"):
+            out["step%d/stat/%s" % (step, key)] = np.float64(logger.stats[key][-1][1])
+        for tag, mod in (("agent", mac.agent), ("critic", learner.critic), ("target_critic", learner.target_critic)):
+            for k, v in state_np(mod).items():
+                out["step%d/%s/%s" % (step, tag, k)] = v
+        out["step%d/critic_training_steps" % step] = np.int64(learner.critic_training_steps)
+        for tag, opt, ps in (("agent", learner.agent_optimiser, learner.agent_params),
+                             ("critic", learner.critic_optimiser, learner.critic_params)):
+            out["step%d/sq/%s" % (step, tag)] = np.concatenate([opt.state[p_]["square_avg"].numpy().ravel() for p_ in ps])
+    out["meta"] = np.array(repr(dict(name=name, shape=tuple(tiny), B=B, T=T, n_steps=n_steps, over=kw)))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
 if __name__ == "__main__":
     th.set_num_threads(1)
     only = set(sys.argv[1:])            # e.g. `make_golden.py checkpoint episode_update`: regenerate just those
     if only:
         for name in sorted(only):
             {"checkpoint": run_checkpoint, "episode_update": run_episode_update, "select_actions": run_select_actions,
-             "replay_sample": run_replay_sample}[name]()
+             "replay_sample": run_replay_sample, "coma": run_coma}[name]()
         sys.exit(0)
     tiny = SmacShape("tiny", 3, 10, 14, 5, 8)
     small = dict(rnn_hidden_dim=16, mixing_embed_dim=8)
@@ -414,3 +492,4 @@ if __name__ == "__main__":
     run_replay_sample()
     run_checkpoint()
     run_episode_update()
+    run_coma()

@@ -6,6 +6,7 @@ import pytest
 
 from golden_utils import Golden, LEARNER_CASES, rel_err
 from oracle import qlearner_oracle as orc
+from pymarl_b200.synthetic import default_args
 
 
 def _learner(g, dtype):
@@ -128,3 +129,56 @@ def test_replay_sample_ids_and_max_t():
         ids = orc.replay_sample_ids(12, 5, seed)
         np.testing.assert_array_equal(fields["obs"][ids], g["seed%d/obs" % seed])
         assert orc.max_t_filled(fields["filled"][ids]) == int(g["seed%d/max_t_filled" % seed])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# COMA: oracle/coma_oracle.py against the reference's COMALearner / COMACritic / BasicMAC
+# (pi_logits) / MultinomialActionSelector, fixture tests/golden/coma_tiny.npz
+# ------------------------------------------------------------------------------------------------------------------
+def _coma_setup():
+    from oracle import coma_oracle as co
+    g = Golden("coma_tiny")
+    args = default_args(g.shape, mixer=None, **g.meta["over"])
+    lr = co.OracleCOMALearner(g.group("init/agent"), g.group("init/critic"), args)
+    lr.target_critic = {k: v.copy() for k, v in g.group("init/target_critic").items()}
+    return co, g, args, lr
+
+
+def test_coma_critic_inputs_targets_and_policy_match_reference():
+    co, g, args, lr = _coma_setup()
+    f = g.batch_fields()
+    B, T, N = f["obs"].shape[:3]
+    np.testing.assert_array_equal(co.critic_inputs(f), g["fw/critic_inputs"])
+    tq = co.critic_forward(lr.target_critic, co.critic_inputs(f).reshape(B * T * N, -1)).reshape(B, T, N, -1)
+    assert rel_err(tq, g["fw/target_q"]) < 2e-6
+    rewards, term = f["reward"][:, :-1], f["terminated"][:, :-1].astype(np.float32)
+    mask = f["filled"][:, :-1].astype(np.float32)
+    mask[:, 1:] = mask[:, 1:] * (1 - term[:, :-1])
+    taken = np.take_along_axis(g["fw/target_q"], f["actions"], axis=3)[..., 0]
+    assert rel_err(co.td_lambda_targets(rewards, term, mask, taken, args.gamma, args.td_lambda), g["fw/td_lambda_targets"]) < 1e-6
+    logits, _ = orc.mac_unroll(lr.agent, {k: v[:, :-1] for k, v in f.items()}, True, True, False)
+    A = logits.shape[-1]
+    pi = co.policy_head(logits.reshape(-1, A), f["avail_actions"][:, :-1].reshape(-1, A), np.float32(g["epsilon"]))
+    assert rel_err(pi.reshape(B, T - 1, N, A), g["fw/pi"]) < 1e-6
+    pt = co.policy_head(logits[:, 0].reshape(-1, A), f["avail_actions"][:, 0].reshape(-1, A), 0, test_mode=True)
+    assert rel_err(pt.reshape(B, N, A), g["fw/pi_test_t0"]) < 1e-6
+    # MultinomialActionSelector with the generator's Exp(1) draws: bit-exact actions; greedy in test mode
+    acts = co.multinomial_select(g["fw/pi"][:, 0], f["avail_actions"][:, 0], g["sel/expo"])
+    np.testing.assert_array_equal(acts, g["sel/actions"])
+    np.testing.assert_array_equal(co.multinomial_select(g["fw/pi_test_t0"], f["avail_actions"][:, 0], None, True), g["sel/greedy"])
+
+
+def test_coma_train_steps_match_reference():
+    co, g, args, lr = _coma_setup()
+    f = g.batch_fields()
+    for step in range(g.meta["n_steps"]):
+        st, _, _ = lr.train(f, step, 0, float(g["epsilon"]))
+        for k in ("critic_loss", "critic_grad_norm", "td_error_abs", "q_taken_mean", "target_mean", "advantage_mean",
+                  "coma_loss", "agent_grad_norm", "pi_max"):
+            r = float(g["step%d/stat/%s" % (step, k)])
+            assert abs(st[k] - r) <= 2e-6 * max(1.0, abs(r)), (step, k, st[k], r)
+        for tag, d in (("agent", lr.agent), ("critic", lr.critic), ("target_critic", lr.target_critic)):
+            for k, v in g.group("step%d/%s" % (step, tag)).items():
+                assert rel_err(d[k], v) < 5e-6, (step, tag, k)
+        assert lr.critic_training_steps == int(g["step%d/critic_training_steps" % step])
+    assert lr.n_target_updates >= 1                       # the fixture's schedule crosses target_update_interval
