@@ -685,6 +685,61 @@ def rollout_loop_record(ctx, precision, n_envs=4096, episode_limit=60, runs=3):
                        "envs": n_envs, "n_agents": shape.n_agents, "episode_limit": episode_limit}}
 
 
+COMA_KW = dict(agent_output_type="pi_logits", action_selector="multinomial", learner="coma_learner", critic_lr=5e-4,
+               td_lambda=0.8, mask_before_softmax=True, epsilon_start=0.5, epsilon_finish=0.01, epsilon_anneal_time=100000,
+               test_greedy=True)
+
+
+def coma_record(ctx, shape_name="2s3z", B=8, T=120, steps=20, warmup=3):
+    """one COMALearner.train step (target critic, td-lambda targets, T-1 critic optimiser steps,
+    agent unroll, policy gradient, two RMSprop updates) on SMAC-shaped synthetic episodes at the reference's on-policy batch
+    size (coma_smac.yaml: 8 episodes), replayed as one CUDA graph; the reference's COMALearner on the host cores beside it.
+    fp32 (CUDA-core) tier; the step is a chain of ~14 small launches per timestep, i.e. latency- not bandwidth-bound."""
+    th = ctx.th
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import copy
+    from cuda_utils import Logger
+    from pymarl_b200 import le_REGISTRY, mac_REGISTRY, _lib
+    from pymarl_b200.synthetic import make_scheme, torch_episode_fields
+    shape = SMAC_SHAPES[shape_name]
+    args = default_args(shape, mixer=None, device="cuda", use_cuda=True, learner_log_interval=10 ** 12, cuda_graph=True, **COMA_KW)
+    th.manual_seed(7)
+    scheme, groups = make_scheme(shape)
+    scheme["actions_onehot"] = {"vshape": (shape.n_actions,), "dtype": th.float32, "group": "agents"}
+    mac = mac_REGISTRY["basic_mac"](copy.deepcopy(scheme), groups, args)
+    learner = le_REGISTRY["coma_learner"](mac, scheme, Logger(), args)
+    learner.cuda()
+    fields = torch_episode_fields(shape, B, T, seed=3000, ragged=False, device=ctx.dev, with_onehot=False)
+    batch = _DictBatch(fields, B, T)
+    l0 = _lib.lib().pmb_launch_count()
+    learner.train(batch, 0, 0)
+    launches = _lib.lib().pmb_launch_count() - l0
+    for i in range(1, warmup):
+        learner.train(batch, i, 0)
+    th.cuda.synchronize()
+    ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        learner.train(batch, warmup + i, 0)
+    ev1.record()
+    th.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    rec = {"metric": "coma_learner_episodes_per_sec", "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+           "gpu_launches": int(launches), "cuda_graph": any(isinstance(v, tuple) for v in learner._graphs.values()),
+           "dtype": "f32", "workload": "COMA learner step, %s shapes" % shape_name, "batch": B, "T": T,
+           "note": "includes the one D2H read of the per-step statistics every step (the reference syncs per timestep)"}
+    try:
+        from oracle import ref_harness
+        if ref_harness.available():
+            cargs = default_args(shape, mixer=None, **COMA_KW)
+            val, cms, cores = ref_harness.time_coma_learner(shape, cargs, B, T, 3, 1)
+            rec["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "ms_per_step": cms,
+                                   "sample": "%d episodes x T=%d per step, 3 steps after 1 warm-up (reference COMALearner.train, torch CPU)" % (B, T)}
+    except Exception as ex:
+        rec["cpu_baseline"] = {"value": None, "error": repr(ex)[:200]}
+    return rec
+
+
 def small_config_record(ctx, name, precision, steps, warmup):
     """BASELINE configs 1-3 on one GPU: the whole step replayed as ONE CUDA graph (args.cuda_graph); per-kernel times
     from a separate eager pass; the reference on the host cores next to it."""
@@ -839,6 +894,10 @@ def main():
                     configs[name] = small_config_record(ctx, name, a.precision, 50, 5)
                 except Exception as ex:
                     configs[name] = {"error": repr(ex)[:300]}
+            try:
+                configs["coma_2s3z"] = coma_record(ctx)
+            except Exception as ex:
+                configs["coma_2s3z"] = {"error": repr(ex)[:300]}
 
     if ctx.rank == 0:
         line = {

@@ -154,6 +154,34 @@ def time_learner(shape, args, batch_size, T, steps, warmup, seed=0):
     return batch_size / mean, mean * 1e3, cores
 
 
+def time_coma_learner(shape, args, batch_size, T, steps, warmup, seed=0):
+    """Seconds per reference COMALearner.train step (use_cuda=False).  Returns (episodes/s, ms per step, threads)."""
+    import copy
+    import torch as th
+    from pymarl_b200.synthetic import numpy_episode_fields
+    activate()
+    from controllers import REGISTRY as mac_REGISTRY
+    from learners import REGISTRY as le_REGISTRY
+    cores = _threads()
+    args.device, args.use_cuda = "cpu", False
+    th.manual_seed(7)
+    scheme, groups, _ = scheme_of(shape)
+    scheme["actions_onehot"] = {"vshape": (shape.n_actions,), "dtype": th.float32, "group": "agents"}
+    # the fork's BasicMAC mutates scheme["obs"]["vshape"] in place, which COMACritic cannot digest: separate copies
+    mac = mac_REGISTRY[args.mac](copy.deepcopy(scheme), groups, args)
+    learner = le_REGISTRY["coma_learner"](mac, scheme, Logger(), args)
+    batch = make_batch(shape, numpy_episode_fields(shape, batch_size, T, seed=seed, ragged=False))
+    for i in range(warmup):
+        learner.train(batch, i, 0)
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        learner.train(batch, warmup + i, 0)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return batch_size / mean, mean * 1e3, cores
+
+
 def time_select_actions(shape, args, envs, steps, warmup, seed=0):
     """Reference BasicMAC.select_actions (epsilon-greedy at t_env = 0) over `envs` synthetic envs.
     Returns (agent-steps/s, ms per step, threads)."""

@@ -42,6 +42,7 @@ class COMALearner:
         self._flat = None
         self._ws = None
         self._stats = None
+        self._graphs = {}
         self.last_stats = None
 
     # ---- flat storage: agent [p | g | sq] in the Q-learner's agent layout, critic in state_dict order ---------------
@@ -78,6 +79,7 @@ class COMALearner:
                 views.append(v)
             opt.square_avg = views
         self._flat = new
+        self._graphs = {}
         return new
 
     def train(self, batch, t_env: int, episode_num: int):
@@ -109,10 +111,33 @@ class COMALearner:
         ao, co = self.agent_optimiser.defaults, self.critic_optimiser.defaults
         epsilon = float(getattr(self.mac.action_selector, "epsilon", 0.0))
         hp = _lib.ComaHParams(a.gamma, a.td_lambda, ao["lr"], co["lr"], ao["alpha"], ao["eps"], a.grad_norm_clip, epsilon)
-        _lib.check(L.pmb_coma_train_step(C.byref(dims), C.byref(pb), C.byref(hp), _lib.ptr(f["ap"]), _lib.ptr(f["ag"]),
-                                         _lib.ptr(f["asq"]), _lib.ptr(f["cp"]), _lib.ptr(f["cg"]), _lib.ptr(f["csq"]),
-                                         _lib.ptr(f["tp"]), _lib.ptr(self._ws), need, _lib.ptr(self._stats),
-                                         _lib.stream_ptr(dev)), "pmb_coma_train_step")
+        def launch():
+            _lib.check(L.pmb_coma_train_step(C.byref(dims), C.byref(pb), C.byref(hp), _lib.ptr(f["ap"]), _lib.ptr(f["ag"]),
+                                             _lib.ptr(f["asq"]), _lib.ptr(f["cp"]), _lib.ptr(f["cg"]), _lib.ptr(f["csq"]),
+                                             _lib.ptr(f["tp"]), _lib.ptr(self._ws), need, _lib.ptr(self._stats),
+                                             _lib.stream_ptr(dev)), "pmb_coma_train_step")
+        if getattr(a, "cuda_graph", False):
+            # ~14 launches per timestep (one critic optimiser step each) + the agent pass: replay them as ONE graph, keyed
+            # on everything the launches bake in (see QLearner._run_graphed); first sight eager, second captures
+            key = (tuple(getattr(dims, k) for k, _ in dims._fields_), tuple(getattr(pb, k) for k, _ in pb._fields_),
+                   tuple(getattr(hp, k) for k, _ in hp._fields_), f["ap"].data_ptr(), f["cp"].data_ptr(), self._ws.data_ptr(),
+                   self._stats.data_ptr())
+            entry = self._graphs.get(key)
+            if entry is None:
+                if len(self._graphs) >= 16:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = "seen"
+                launch()
+            else:
+                if entry == "seen":
+                    g = th.cuda.CUDAGraph()
+                    th.cuda.synchronize(dev)
+                    with th.cuda.graph(g):
+                        launch()
+                    entry = self._graphs[key] = (g, list(keep))
+                entry[0].replay()
+        else:
+            launch()
         if hasattr(self.mac, "params_changed"):
             self.mac.params_changed()
         self._last_dims = dims

@@ -171,3 +171,25 @@ def test_coma_checkpoint_round_trip(tmp_path):
     for m1, m2 in ((a.mac.agent, b.mac.agent), (a.critic, b.critic)):
         for k, v in m1.state_dict().items():
             assert th.equal(v, m2.state_dict()[k]), k
+
+
+def test_coma_cuda_graph_step_is_bit_identical():
+    """args.cuda_graph: the ~14 launches per timestep of a COMA step replayed as one graph give the bits of the eager step."""
+    from cuda_utils import to_batch
+    shape = SMAC_SHAPES["3m"]
+    fields = numpy_episode_fields(shape, 8, 16, seed=6, ragged=True)
+    rng = np.random.default_rng(9)
+    agent = orc.init_params(orc.agent_param_shapes(42, 64, 9), rng)
+    crit = co.init_critic(co.critic_param_shapes(48, 30, 3, 9), rng)
+    outs = []
+    for graph in (False, True):
+        args = default_args(shape, mixer=None, cuda_graph=graph, **COMA_KW)
+        lr, _ = build_coma(shape, args, agent, crit, crit)
+        batch = to_batch(shape, fields)
+        for i in range(4):
+            lr.train(batch, i, 0)
+        if graph:
+            assert any(isinstance(v, tuple) for v in lr._graphs.values())
+        outs.append((lr._flat["ap"].clone(), lr._flat["cp"].clone(), lr._flat["tp"].clone(), lr.last_stats.clone()))
+    for x, y in zip(*outs):
+        assert th.equal(x, y)
