@@ -35,7 +35,7 @@ int launch_mixer_bwd(const pmb_dims* d, const pmb_batch* b, const float* flat_mi
                      const float* g, float* d_agent_qs, float* flat_grad_mixer, void* scratch, int64_t scratch_bytes,
                      cudaStream_t s);
 int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
-                   float* g_out, double* stats, cudaStream_t s);
+                   float* g_out, double* stats, cudaStream_t s, double* partials = nullptr, int64_t partial_bytes = 0);
 int launch_stats_reset(double* stats, cudaStream_t s);
 int launch_dp_pack(const double* stats, float* tail, cudaStream_t s);
 int launch_dp_unpack(const float* tail, double* stats, cudaStream_t s);
@@ -45,13 +45,13 @@ int coma_launch_gather_taken(const pmb_dims* d, const pmb_batch* b, int t0, int 
 int coma_launch_td_lambda(const pmb_dims* d, const pmb_batch* b, float gamma, float lam, const float* taken, float* targets,
                           cudaStream_t s);
 int coma_launch_critic_td(const pmb_dims* d, const pmb_batch* b, int t, const float* q_t, const float* targets, float* q_vals,
-                          float* dqv, int32_t* dqa, double* stats_row, cudaStream_t s);
+                          float* dqv, int32_t* dqa, double* stats_row, double* partials, cudaStream_t s);
 int coma_launch_critic_bwd_pointwise(int64_t R, int A, int Hc, const float* dqv, const int32_t* dqa, const float* w3,
                                      const float* x2, float* dq_dense, float* dx2, cudaStream_t s);
 int launch_relu_mask(int64_t n, const float* x, float* dx, cudaStream_t s);
 int launch_transpose(int rows, int cols, const float* in, float* out, cudaStream_t s);
 int coma_launch_policy(const pmb_dims* d, const pmb_batch* b, float eps, const float* logits, const float* q_vals,
-                       float* dlogits, float* pi_out, double* stats_row, cudaStream_t s);
+                       float* dlogits, float* pi_out, double* stats_row, double* partials, cudaStream_t s);
 int launch_policy_head(int64_t rows, int A, float eps, int test_mode, const float* logits, const int32_t* avail, float* probs,
                        cudaStream_t s);
 int launch_multinomial(int64_t rows, int A, const float* probs, const int32_t* avail, const float* expo, int greedy,
@@ -264,7 +264,7 @@ WsPlan plan_workspace(const pmb_dims* d) {
             int64_t m3 = tc_mixer_bwd_img_scratch_bytes(d); if (m3 > sc) sc = m3;
         }
     }
-    if (sc < 4096 * 4) sc = 4096 * 4;
+    if (sc < 65536) sc = 65536;                  // >= the per-block partial sums of td_loss (8 x SMs x 5 doubles)
     p.off[17] = off;
     p.scratch_bytes = align_up(sc, 256);
     p.total = off + p.scratch_bytes;
@@ -766,7 +766,9 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     }
     // :86-97
     PHASE(s, "td_loss");
-    if ((rc = launch_td_loss(d, b, v.q_tot, v.t_tot, hp->gamma, v.g, stats, s))) return rc;
+    // the scratch area is free between the mixer forward and the mixer backward: per-block loss sums -> fixed-order total
+    if ((rc = launch_td_loss(d, b, v.q_tot, v.t_tot, hp->gamma, v.g, stats, s, reinterpret_cast<double*>(v.scratch),
+                             v.scratch_bytes))) return rc;
     if (hp->keep_q & 2) {              // debug: forward pass + loss sums only, intermediates stay in the workspace
         PHASE(s, "end");
         return PMB_OK;
@@ -873,7 +875,7 @@ ComaPlan coma_plan(const pmb_dims* d) {
     if (c1 > sc) sc = c1;
     if (c2 > sc) sc = c2;
     if (c3 > sc) sc = c3;
-    if (sc < 4096 * 4) sc = 4096 * 4;
+    if (sc < 65536) sc = 65536;                  // >= the per-block partial sums of the td / policy kernels
     p.scratch_bytes = align_up(sc, 256);
     p.total = off + p.scratch_bytes;
     return p;
@@ -966,7 +968,7 @@ int pmb_coma_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_coma_hp
         double* st = stats + (int64_t)t * PMB_S_COUNT;
         if ((rc = coma_launch_inputs(d, b, t, 1, inp, s))) return rc;
         if ((rc = critic_fwd(cp, inp, R, D, Hc, A, x1, x2, qtmp, s))) return rc;
-        if ((rc = coma_launch_critic_td(d, b, t, qtmp, targets, q_vals, dqv, dqa, st, s))) return rc;
+        if ((rc = coma_launch_critic_td(d, b, t, qtmp, targets, q_vals, dqv, dqa, st, static_cast<double*>(scratch), s))) return rc;
         if ((rc = coma_launch_critic_bwd_pointwise(R, A, Hc, dqv, dqa, cp.w3, x2, dq, dx2, s))) return rc;
         if ((rc = launch_gemm_atb(dq, dense_map(A), A, x2, dense_map(Hc), Hc, R, cg.w3, Hc, cg.b3, scratch, P.scratch_bytes, s))) return rc;
         if ((rc = launch_gemm_atb(dx2, dense_map(Hc), Hc, x1, dense_map(Hc), Hc, R, cg.w2, Hc, cg.b2, scratch, P.scratch_bytes, s))) return rc;
@@ -985,7 +987,7 @@ int pmb_coma_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_coma_hp
     if ((rc = fc1_fwd(&da, b, 0, Tp, ap, x, s))) return rc;
     if ((rc = gru_fwd_dispatch(&da, ap, R, Tp, x, nullptr, h_stash, gates, logits, nullptr, s))) return rc;
     double* sa = stats + (int64_t)Tp * PMB_S_COUNT;
-    if ((rc = coma_launch_policy(d, b, hp->epsilon, logits, q_vals, dlogits, pi, sa, s))) return rc;
+    if ((rc = coma_launch_policy(d, b, hp->epsilon, logits, q_vals, dlogits, pi, sa, static_cast<double*>(scratch), s))) return rc;
     if ((rc = agent_bwd(&da, b, agent_p, x, h_stash, gates, nullptr, dpre1, agent_g, scratch, P.scratch_bytes, s, dlogits))) return rc;
     pmb_layout L;
     compute_layout(&da, &L);

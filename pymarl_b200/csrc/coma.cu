@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(256)
 coma_critic_td_kernel(int B, int T, int N, int A, int t, const float* __restrict__ q_t, const float* __restrict__ targets,
                       const int64_t* __restrict__ actions, int64_t actions_sb, const uint8_t* __restrict__ term,
                       int64_t term_sb, const int64_t* __restrict__ filled, int64_t filled_sb, float* __restrict__ q_vals,
-                      float* __restrict__ dqv, int32_t* __restrict__ dqa, double* __restrict__ stats) {
+                      float* __restrict__ dqv, int32_t* __restrict__ dqa, double* __restrict__ stats,
+                      double* __restrict__ partials) {
     __shared__ double sh[8][5];
+    __shared__ int s_last;
     const int64_t R = (int64_t)B * N;
     double acc[5] = {0, 0, 0, 0, 0};
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < R; row += (int64_t)gridDim.x * blockDim.x) {
@@ -107,10 +109,25 @@ coma_critic_td_kernel(int B, int T, int N, int A, int t, const float* __restrict
 #pragma unroll
         for (int i = 0; i < 5; ++i) sh[w][i] = acc[i];
     __syncthreads();
+    // deterministic cross-block total: per-block sums, the last block (ticket in the row's last slot) adds them in order
     if (threadIdx.x < 5) {
         double s = 0;
         for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) s += sh[ww][threadIdx.x];
-        atomicAdd(stats + threadIdx.x, s);
+        partials[(int64_t)blockIdx.x * 5 + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(stats + PMB_S_COUNT - 1), 1ULL);
+        s_last = t == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 5) {
+        __threadfence();
+        const volatile double* pv = partials;
+        double tot = 0.0;
+        for (unsigned bb = 0; bb < gridDim.x; ++bb) tot += pv[(int64_t)bb * 5 + threadIdx.x];
+        stats[threadIdx.x] = tot;
     }
 }
 
@@ -158,8 +175,10 @@ __global__ void __launch_bounds__(256)
 coma_policy_kernel(int B, int T, int N, int A, float eps, const float* __restrict__ logits, const float* __restrict__ q_vals,
                    const int32_t* __restrict__ avail, int64_t avail_sb, const int64_t* __restrict__ actions, int64_t actions_sb,
                    const uint8_t* __restrict__ term, int64_t term_sb, const int64_t* __restrict__ filled, int64_t filled_sb,
-                   float* __restrict__ dlogits, float* __restrict__ pi_out, double* __restrict__ stats) {
+                   float* __restrict__ dlogits, float* __restrict__ pi_out, double* __restrict__ stats,
+                   double* __restrict__ partials) {
     __shared__ double sh[8][4];
+    __shared__ int s_last;
     const int Tp = T - 1;
     const int64_t R = (int64_t)B * N, total = (int64_t)Tp * R;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -252,7 +271,21 @@ coma_policy_kernel(int B, int T, int N, int A, float eps, const float* __restric
     if (threadIdx.x < 4) {
         double s2 = 0;
         for (int ww = 0; ww < wpb; ++ww) s2 += sh[ww][threadIdx.x];
-        atomicAdd(stats + threadIdx.x, s2);
+        partials[(int64_t)blockIdx.x * 4 + threadIdx.x] = s2;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(stats + PMB_S_COUNT - 1), 1ULL);
+        s_last = t == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 4) {
+        __threadfence();
+        const volatile double* pv = partials;
+        double tot = 0.0;
+        for (unsigned bb = 0; bb < gridDim.x; ++bb) tot += pv[(int64_t)bb * 4 + threadIdx.x];
+        stats[threadIdx.x] = tot;
     }
 }
 
@@ -360,13 +393,13 @@ int coma_launch_td_lambda(const pmb_dims* d, const pmb_batch* b, float gamma, fl
 }
 
 int coma_launch_critic_td(const pmb_dims* d, const pmb_batch* b, int t, const float* q_t, const float* targets, float* q_vals,
-                          float* dqv, int32_t* dqa, double* stats_row, cudaStream_t s) {
+                          float* dqv, int32_t* dqa, double* stats_row, double* partials, cudaStream_t s) {
     const int64_t R = (int64_t)d->B * d->N;
     int64_t grid = ceil_div(R, 256);
     if (grid > 4 * sm_count()) grid = 4 * sm_count();
     coma_critic_td_kernel<<<(unsigned)grid, 256, 0, s>>>(d->B, d->T, d->N, d->A, t, q_t, targets, b->actions, b->actions_sb,
                                                         b->terminated, b->terminated_sb, b->filled, b->filled_sb, q_vals, dqv,
-                                                        dqa, stats_row);
+                                                        dqa, stats_row, partials);
     PMB_LAUNCH_CHECK("coma_critic_td_kernel");
     return PMB_OK;
 }
@@ -393,14 +426,14 @@ int launch_transpose(int rows, int cols, const float* in, float* out, cudaStream
 }
 
 int coma_launch_policy(const pmb_dims* d, const pmb_batch* b, float eps, const float* logits, const float* q_vals,
-                       float* dlogits, float* pi_out, double* stats_row, cudaStream_t s) {
+                       float* dlogits, float* pi_out, double* stats_row, double* partials, cudaStream_t s) {
     const int64_t total = (int64_t)(d->T - 1) * d->B * d->N;
     if (total <= 0) return PMB_OK;
     int64_t grid = ceil_div(total, 8);
     if (grid > 8 * sm_count()) grid = 8 * sm_count();
     coma_policy_kernel<<<(unsigned)grid, 256, 0, s>>>(d->B, d->T, d->N, d->A, eps, logits, q_vals, b->avail, b->avail_sb,
                                                      b->actions, b->actions_sb, b->terminated, b->terminated_sb, b->filled,
-                                                     b->filled_sb, dlogits, pi_out, stats_row);
+                                                     b->filled_sb, dlogits, pi_out, stats_row, partials);
     PMB_LAUNCH_CHECK("coma_policy_kernel");
     return PMB_OK;
 }

@@ -27,8 +27,10 @@ __global__ void __launch_bounds__(256)
 td_loss_kernel(int B, int T, int W, float gamma, const float* __restrict__ q_tot, const float* __restrict__ t_tot,
                const float* __restrict__ reward, int64_t reward_sb, const uint8_t* __restrict__ terminated,
                int64_t term_sb, const int64_t* __restrict__ filled, int64_t filled_sb,
-               const int64_t* __restrict__ ep_index, float* __restrict__ g_out, double* __restrict__ stats) {
+               const int64_t* __restrict__ ep_index, float* __restrict__ g_out, double* __restrict__ stats,
+               double* __restrict__ partials) {
     __shared__ double sh[8][5];
+    __shared__ int s_last;
     const int64_t total = (int64_t)B * (T - 1) * W;
     double acc[5] = {0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -52,9 +54,29 @@ td_loss_kernel(int B, int T, int W, float gamma, const float* __restrict__ q_tot
         acc[4] += (double)(y * mask);
     }
     block_sum5(acc, sh);
+    if (!partials) {                       // stand-alone pmb_td_loss: accumulate into the caller's sums
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) atomicAdd(stats + i, acc[i]);
+        }
+        return;
+    }
+    // deterministic: every block stores its sums, the last block to finish adds them in block order (ticket = the last slot
+    // of the stats buffer, zeroed with it at the start of the step)
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) atomicAdd(stats + i, acc[i]);
+        for (int i = 0; i < 5; ++i) partials[(int64_t)blockIdx.x * 5 + i] = acc[i];
+        __threadfence();
+        const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(stats + PMB_S_COUNT - 1), 1ULL);
+        s_last = t == (unsigned long long)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 5) {
+        __threadfence();
+        const volatile double* pv = partials;
+        double tot = 0.0;
+        for (unsigned bb = 0; bb < gridDim.x; ++bb) tot += pv[(int64_t)bb * 5 + threadIdx.x];
+        stats[threadIdx.x] = tot;
     }
 }
 
@@ -143,16 +165,17 @@ rmsprop_apply_kernel(int64_t n, float* __restrict__ p, float* __restrict__ g, fl
 }  // namespace
 
 int launch_td_loss(const pmb_dims* d, const pmb_batch* b, const float* q_tot, const float* t_tot, float gamma,
-                   float* g_out, double* stats, cudaStream_t s) {
+                   float* g_out, double* stats, cudaStream_t s, double* partials, int64_t partial_bytes) {
     const int W = d->mixer == PMB_MIXER_NONE ? d->N : 1;
     const int64_t total = (int64_t)d->B * (d->T - 1) * W;
     if (total <= 0) return PMB_OK;
     int64_t grid = ceil_div(total, 256);
     int64_t cap = 8 * (int64_t)sm_count();
     if (grid > cap) grid = cap;
+    if (partials && partial_bytes < grid * 5 * (int64_t)sizeof(double)) partials = nullptr;
     td_loss_kernel<<<(unsigned)grid, 256, 0, s>>>(d->B, d->T, W, gamma, q_tot, t_tot, b->reward, b->reward_sb,
                                                   b->terminated, b->terminated_sb, b->filled, b->filled_sb, b->ep_index, g_out,
-                                                  stats);
+                                                  stats, partials);
     PMB_LAUNCH_CHECK("td_loss_kernel");
     return PMB_OK;
 }
