@@ -97,7 +97,19 @@ class EpisodeBatch:
                     out = tr.transform(out)
                 store[new_k][sl] = out.view_as(store[new_k][sl])
 
-    def _update_on_device(self, data, slices, mark_filled):
+    def update_masked(self, data, row_mask, ts, mark_filled=True):
+        """update(data, bs=<rows where row_mask is set>, ts=ts) for a batch in HBM WITHOUT a host synchronisation: `data`
+        holds a value for EVERY episode row ([batch_size, ...] per key, device tensors), `row_mask` is a device bool tensor
+        [batch_size]; rows whose mask is clear are skipped inside the kernel (their index is -1).  What a vectorised
+        runner needs each timestep (the reference's runners pass the list of live envs, parallel_runner.py:109,170-176,
+        which costs a device -> host round trip when the mask lives on the GPU)."""
+        idx = th.where(row_mask, th.arange(row_mask.numel(), device=row_mask.device), th.full_like(row_mask, -1, dtype=th.int64))
+        slices = self._parse_slices((slice(None), ts))
+        if not self._update_on_device(data, [idx, slices[1]], mark_filled, trusted_index=True):
+            rows = row_mask.nonzero().flatten()
+            self.update({k: v[rows] for k, v in data.items()}, bs=rows, ts=ts, mark_filled=mark_filled)
+
+    def _update_on_device(self, data, slices, mark_filled, trusted_index=False):
         """A batch that lives in HBM: ALL fields of the call, `filled` and the fused OneHot preprocess in ONE launch
         (pmb_batch_update) instead of one indexed assignment + one scatter per field.  Returns False (caller takes the
         generic path) for what the kernel does not cover: episode-constant fields, boolean / strided-time indices,
@@ -127,7 +139,10 @@ class EpisodeBatch:
                 if bs.dtype == th.bool:
                     return False
                 b_index = bs.to(device=self.device, dtype=th.int64).reshape(-1).contiguous()
-                lo_hi = (int(b_index.min()), int(b_index.max())) if b_index.numel() else (0, 0)
+                if trusted_index:                          # update_masked: -1 marks skipped rows, the kernel bounds-checks
+                    lo_hi = (0, 0)
+                else:
+                    lo_hi = (int(b_index.min()), int(b_index.max())) if b_index.numel() else (0, 0)
             else:
                 arr = np.asarray(bs)
                 if arr.dtype == np.bool_ or arr.ndim != 1:
@@ -137,7 +152,7 @@ class EpisodeBatch:
             nb = int(b_index.numel())
             if nb and (lo_hi[0] < -n_rows or lo_hi[1] >= n_rows):
                 raise IndexError("episode index out of range")
-            if nb and lo_hi[0] < 0:
+            if nb and lo_hi[0] < 0 and not trusted_index:
                 b_index = th.where(b_index < 0, b_index + n_rows, b_index)
         if nb == 0:
             return True

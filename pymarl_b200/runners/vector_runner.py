@@ -10,7 +10,8 @@ GPU (`SyntheticVectorEnv`: SMAC-shaped random dynamics, StarCraft II is not avai
     env.step                  -> device ops
     batch.update(reward, terminated), batch.update(state, avail_actions, obs; mark_filled)   -> one launch each
 
-and the only host synchronisation per timestep is the count of live envs.  Episode semantics follow the reference
+with NO host synchronisation per timestep: the live-env masks stay on the device and the updates are masked launches
+(`EpisodeBatch.update_masked`); the loop checks "all terminated" every 16 steps and reads the step count once per run.  Episode semantics follow the reference
 loop exactly: actions are also selected and stored in an env's final state, `terminated` is stored as 0 when the episode
 ended on the time limit (parallel_runner.py:150-156), `filled` covers t = 0 .. L, `t_env` counts env steps of training
 runs only."""
@@ -127,38 +128,33 @@ class VectorRunner:
         self.t = 0
         self.env_steps_this_run = 0
 
-    @staticmethod
-    def _rows(mask):
-        """(index argument for batch.update, number of rows): slice(None) when every env is selected."""
-        idx = mask.nonzero().flatten()                      # the one host synchronisation of a timestep
-        n = int(idx.numel())
-        return (slice(None) if n == mask.numel() else idx), n
-
     def run(self, test_mode=False):
+        """One batch of episodes.  No host synchronisation inside the loop except an all-terminated check every 16
+        timesteps: live-env masks stay on the device and every batch.update is a masked single launch."""
         self.reset()
         B, dev = self.batch_size, self.env.device
         self.mac.init_hidden(batch_size=B)
         alive = th.ones(B, dtype=th.bool, device=dev)       # envs that still step
         store = alive.clone()                               # envs whose action at this t is stored (alive one step ago)
         returns = th.zeros(B, device=dev)
+        steps = th.zeros((), dtype=th.long, device=dev)
         while True:
             actions = self.mac.select_actions(self.batch, t_ep=self.t, t_env=self.t_env, test_mode=test_mode)     # [B, N]
-            rows, n = self._rows(store)
-            self.batch.update({"actions": actions[rows].unsqueeze(-1)}, bs=rows, ts=self.t, mark_filled=False)
-            rows, n = self._rows(alive)
-            if n == 0:
-                break
+            self.batch.update_masked({"actions": actions.unsqueeze(-1)}, store, self.t, mark_filled=False)
+            if self.t >= self.episode_limit or (self.t % 16 == 15 and not bool(alive.any())):
+                break                                       # at t = limit every env has terminated (time limit)
             reward, term, limit = self.env.step(actions, alive)
             returns += reward * alive
-            if not test_mode:
-                self.env_steps_this_run += n
-            self.batch.update({"reward": reward[rows].unsqueeze(-1), "terminated": (term & ~limit)[rows].unsqueeze(-1)},
-                              bs=rows, ts=self.t, mark_filled=False)
+            steps += alive.sum()
+            self.batch.update_masked({"reward": reward.unsqueeze(-1), "terminated": (term & ~limit).unsqueeze(-1)},
+                                     alive, self.t, mark_filled=False)
             self.t += 1
-            self.batch.update({"state": self.env.get_state()[rows], "avail_actions": self.env.get_avail_actions()[rows],
-                               "obs": self.env.get_obs()[rows]}, bs=rows, ts=self.t, mark_filled=True)
+            self.batch.update_masked({"state": self.env.get_state(), "avail_actions": self.env.get_avail_actions(),
+                                      "obs": self.env.get_obs()}, alive, self.t, mark_filled=True)
             store = alive
             alive = alive & ~term
+        if not test_mode:
+            self.env_steps_this_run = int(steps)            # the one device -> host read of the run
         if not test_mode:
             self.t_env += self.env_steps_this_run
         (self.test_returns if test_mode else self.train_returns).extend(returns.tolist())
