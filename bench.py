@@ -792,7 +792,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the select_actions / configs 1-3 / weak / dp_equal sub-records")
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--cpu-envs", type=int, default=256)
-    ap.add_argument("--hang-timeout", type=int, default=420, help="seconds after which a stuck run dumps its stacks and exits")
+    ap.add_argument("--hang-timeout", type=int, default=600,
+                    help="multi-rank runs only: seconds after which a stuck job dumps its stacks and exits")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the main config's step as a CUDA graph too")
     ap.add_argument("--action-rng", default="philox", choices=["philox", "torch"],
                     help="select_actions: where the epsilon-greedy draws come from")
@@ -829,8 +830,9 @@ def main():
 
     # a multi-rank job that stops making progress (a rank died, a collective mismatched) must not sit in NCCL's 10-minute
     # watchdog: dump the stacks and exit after a generous bound
-    import faulthandler
-    faulthandler.dump_traceback_later(a.hang_timeout, exit=True)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import faulthandler
+        faulthandler.dump_traceback_later(a.hang_timeout, exit=True)
     ctx = Ctx()
     th = ctx.th
     from pymarl_b200.data_parallel import shard_slice
