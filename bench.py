@@ -538,10 +538,10 @@ def dp_self_check(ctx):
     out = {"ok": True, "world": ctx.world, "batch": cfg["batch"], "T": cfg["T"]}
     fields = torch_episode_fields(shape, cfg["batch"], cfg["T"], seed=4242, ragged=True, device=ctx.dev, with_onehot=False)
     batch = _DictBatch(fields, cfg["batch"], cfg["T"])
-    for prec, tol_s, tol_p in (("fp32", 1e-6, 1e-4), ("bf16", 1e-3, 1e-2)):
+    for prec, tol_s, tol_p, exch in (("fp32", 1e-6, 1e-4, "peer"), ("bf16", 1e-3, 1e-2, "peer"), ("bf16", 1e-3, 1e-2, "nccl")):
         res = []
         for dp in (False, True):
-            lr = build_learner(ctx, cfg, prec, data_parallel=dp)
+            lr = build_learner(ctx, cfg, prec, data_parallel=dp, dp_exchange=exch)
             lr._flat["sq"].fill_(1e-2)
             p0 = lr._flat["p"].clone()
             lr.train(batch, 0, 0)
@@ -568,8 +568,15 @@ def dp_self_check(ctx):
         same = bool(th.equal(ref, lr._flat["p"]))
         flag = th.tensor([int(ok and same)], device=ctx.dev)
         ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
-        out[prec] = {"loss_rel": e_loss, "grad_norm_rel": e_gn, "params_rel": e_par, "worst_tensor": worst,
-                     "update_rel_l2": e_upd, "replicas_bit_identical": same, "tol": [tol_s, tol_p]}
+        fused = lr._px is not None
+        if fused:
+            same = same and lr._px.error_word() == 0
+            flag2 = th.tensor([int(same)], device=ctx.dev)
+            ctx.dist.all_reduce(flag2, op=ctx.dist.ReduceOp.MIN)
+            out["ok"] = out["ok"] and bool(flag2.item())
+        out[prec + "_" + exch] = {"loss_rel": e_loss, "grad_norm_rel": e_gn, "params_rel": e_par, "worst_tensor": worst,
+                                  "update_rel_l2": e_upd, "replicas_bit_identical": same, "tol": [tol_s, tol_p],
+                                  "exchange": "fused peer-memory kernel" if fused else "nccl all-reduce"}
         out["ok"] = out["ok"] and bool(flag.item())
         del lr
     return out
@@ -795,6 +802,8 @@ def main():
     ap.add_argument("--hang-timeout", type=int, default=600,
                     help="multi-rank runs only: seconds after which a stuck job dumps its stacks and exits")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the main config's step as a CUDA graph too")
+    ap.add_argument("--dp-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused exchange + update kernel over NVLink peer memory (falls back to nccl when unavailable) or NCCL")
     ap.add_argument("--action-rng", default="philox", choices=["philox", "torch"],
                     help="select_actions: where the epsilon-greedy draws come from")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
@@ -851,7 +860,7 @@ def main():
     # needs the full batch, so generate that once and let the strong run use its first B_local episodes
     want_weak = strong and ctx.world > 1 and extras
     B_gen = Bg if want_weak else B_local
-    learner = build_learner(ctx, cfg, a.precision, dp_shard_batch=False, cuda_graph=a.cuda_graph)
+    learner = build_learner(ctx, cfg, a.precision, dp_shard_batch=False, cuda_graph=a.cuda_graph, dp_exchange=a.dp_exchange)
     fields_all = torch_episode_fields(shape, B_gen, T, seed=1000 + ctx.rank, ragged=a.ragged, device=ctx.dev, with_onehot=False)
     weak = None
     if want_weak:
@@ -869,6 +878,9 @@ def main():
     batch = _DictBatch(fields, B_local, T)
     input_bytes = sum(v.numel() * v.element_size() for v in fields.values())
 
+    exchange_desc = "single GPU" if ctx.world == 1 else (
+        "exchange + clip + RMSprop fused in one kernel over NVLink peer memory" if getattr(learner, "_px", None) is not None
+        else "one NCCL all-reduce of [grads | loss sums] per step")
     ms, phase_ms, launches, clocks = time_learner(ctx, learner, batch, a.steps, a.warmup, profile=not a.cuda_graph)
     if a.cuda_graph:
         phase_ms = profile_pass(learner, batch, 3)
@@ -916,7 +928,7 @@ def main():
             "config": {"workload": _workload_name(cfg), "name": a.config, "n_agents": N, "obs": O, "state": S, "n_actions": A,
                        "T": T, "global_batch": Bg if strong else ctx.world * Bg, "batch_per_gpu": B_local, "mixer": cfg["mixer"],
                        "episodes": "ragged" if a.ragged else "full-length",
-                       "parallelism": "dp%d: episodes sharded, one NCCL all-reduce of [grads | loss sums] per step" % ctx.world,
+                       "parallelism": "dp%d: episodes sharded; %s" % (ctx.world, exchange_desc),
                        "cuda_graph": bool(a.cuda_graph),
                        "l2_policy": "inputs (%.1f GB per GPU) exceed L2" % (input_bytes / 1e9)},
             "roofline": rec["roofline"], "step_roofline": rec["step_roofline"], "phases_ms": rec["phases_ms"],

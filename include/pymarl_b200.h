@@ -205,6 +205,26 @@ int pmb_clip_rmsprop_update(int64_t n, float* flat_p, float* flat_g, float* flat
 int pmb_dp_pack(int64_t n, float* flat_g, const double* stats, pmb_stream stream);
 int pmb_dp_unpack(int64_t n, const float* flat_g, double* stats, pmb_stream stream);
 
+/* Fused exchange + update over NVLink peer memory (csrc/dp_peer.cu): ONE kernel per rank replaces pack -> all-reduce ->
+ * unpack -> pmb_clip_rmsprop_update.  Every rank keeps its flat gradient in an exchange buffer of
+ * pmb_dp_exchange_floats(n) floats ([n grads | 16 loss-sum floats | flags], zero-initialised once) that the other ranks of
+ * the node map with CUDA IPC: pmb_ipc_export on the owner gives a 64-byte handle + byte offset (the pointer must come from
+ * cudaMalloc, e.g. torch's caching allocator without expandable segments), the host plumbing exchanges them (any
+ * all-gather), pmb_ipc_open maps a peer's buffer.  pmb_dp_fused_allreduce_update(world <= 8, rank, bufs[world] (own
+ * buffer at index rank), n, step = 1, 2, 3, ... (consecutive), ...): one-shot all-reduce in rank order (bit-identical sums
+ * on every rank), global grad norm, clip, RMSprop and optional hard target sync of the replicated parameters; afterwards the
+ * own exchange buffer holds the global normalised / clipped gradient and stats the global sums.  scratch: 4 n + 2048 bytes,
+ * zeroed ONCE and kept for the life of the exchange (it holds the grid barrier's counter).  All ranks must call it with the
+ * same step id; a peer that does not show up within ~2 s raises the error word (scratch tail) instead of hanging. */
+int pmb_ipc_export(const void* dev_ptr, void* handle_out_64_bytes, int64_t* offset_out);
+int pmb_ipc_open(const void* handle_64_bytes, int64_t offset, void** ptr_out);
+int pmb_ipc_close(void* mapped_ptr, int64_t offset);
+int64_t pmb_dp_exchange_floats(int64_t n);
+int pmb_dp_fused_allreduce_update(int32_t world, int32_t rank, void* const* bufs, int64_t n, int64_t step, float* flat_p,
+                                  float* flat_sq, float* flat_target, int32_t do_target_sync, double* stats, float lr,
+                                  float alpha, float eps, float grad_norm_clip, void* scratch, int64_t scratch_bytes,
+                                  pmb_stream stream);
+
 /* ---- K7: epsilon-greedy action selection (components/action_selectors.py:44-62) --------- */
 /* q [rows_b][N][A] f32, avail [rows_b][N][A] i32.  Draw modes:
  *   u != NULL, expo != NULL : injected draws (u [b][N] uniform, expo [b][N][A] Exp(1)), the

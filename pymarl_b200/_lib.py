@@ -112,6 +112,12 @@ _SIGS = {
                                           C.c_float, _P, _P]),
     "pmb_dp_pack": (C.c_int, [C.c_int64, _P, _P, _P]),
     "pmb_dp_unpack": (C.c_int, [C.c_int64, _P, _P, _P]),
+    "pmb_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "pmb_ipc_open": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p)]),
+    "pmb_ipc_close": (C.c_int, [_P, C.c_int64]),
+    "pmb_dp_exchange_floats": (C.c_int64, [C.c_int64]),
+    "pmb_dp_fused_allreduce_update": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int64, C.c_int64, _P, _P, _P,
+                                                C.c_int32, _P, C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int64, _P]),
     "pmb_epsilon_greedy": (C.c_int, [C.c_int64, C.c_int32, _P, _P, C.c_float, _P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "pmb_select_actions_workspace_bytes": (C.c_int64, [C.POINTER(Dims)]),
     "pmb_select_actions_step": (C.c_int, [C.POINTER(Dims), C.POINTER(Batch), C.c_int32, _P, _P, C.c_float, _P, _P,

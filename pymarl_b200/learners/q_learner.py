@@ -82,6 +82,7 @@ class QLearner:
         self._workspace = None
         self._stats = None
         self._dp_scratch = None         # 4096 floats for the replicated clip + RMSprop of the data-parallel path
+        self._px = None                 # data_parallel.PeerExchange when the fused NVLink exchange is in use
         self._graphs = {}               # CUDA graphs of the step (args.cuda_graph)
         self.last_stats = None          # device tensor [16] float64 of the latest step
 
@@ -114,9 +115,18 @@ class QLearner:
             if ok:
                 return f
         n = layout.n_total
+        # Data parallel: the gradient lives in an exchange buffer the other ranks of the node map through CUDA IPC, and ONE
+        # fused kernel per step does all-reduce + clip + RMSprop over NVLink (data_parallel.PeerExchange, csrc/dp_peer.cu).
+        # Built collectively; when any rank cannot (args.dp_exchange = "nccl", >8 ranks, several nodes, no IPC) every rank
+        # falls back to one NCCL all-reduce + the stand-alone update kernel.
+        self._px = None
+        if data_parallel.is_active() and getattr(self.args, "data_parallel", True) \
+                and getattr(self.args, "dp_exchange", "peer") == "peer":
+            px = data_parallel.PeerExchange(n, dev)
+            self._px = px if px.ok else None
         # the gradient buffer carries PMB_DP_TAIL_FLOATS extra floats: the loss sums of the data-parallel exchange
         new = dict(p=th.zeros(n, dtype=th.float32, device=dev),
-                   g=th.zeros(n + _lib.DP_TAIL_FLOATS, dtype=th.float32, device=dev),
+                   g=self._px.grad_view() if self._px is not None else th.zeros(n + _lib.DP_TAIL_FLOATS, dtype=th.float32, device=dev),
                    sq=th.zeros(n, dtype=th.float32, device=dev), target=th.zeros(n, dtype=th.float32, device=dev),
                    layout=layout)
         _flat.bind(new["p"], layout, self.mac.agent, "agent", grad=new["g"])
@@ -209,7 +219,11 @@ class QLearner:
         else:                                   # a rank without episodes still takes part in the exchange
             f["g"].zero_()
             self._stats.zero_()
-        if dp:
+        if dp and self._px is not None:
+            # exchange + update fused into one kernel over NVLink peer memory
+            self._px.fused_update(f["p"], f["sq"], f["target"], hp.do_target_sync, self._stats, hp.lr, hp.alpha, hp.eps,
+                                  hp.grad_norm_clip, s)
+        elif dp:
             # one exchange per step: [gradients of sum((td*mask)^2) | the five loss sums as (hi, lo) floats]
             _lib.check(L.pmb_dp_pack(n, _lib.ptr(f["g"]), _lib.ptr(self._stats), s), "pmb_dp_pack")
             data_parallel.allreduce_step(f["g"])
