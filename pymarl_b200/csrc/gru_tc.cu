@@ -62,6 +62,22 @@ __device__ __forceinline__ uint4 gf_philox4x32_10(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float gf_u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
 
+// position of the n-th (0-based) set bit of m; needs popc(m) > n.  Five popc steps instead of the fns.b32 emulation.
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+    int pos = 0;
+    int c = __popc(m & 0xffffu);
+    if (n >= c) { n -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xffu);
+    if (n >= c) { n -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xfu);
+    if (n >= c) { n -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);
+    if (n >= c) { n -= c; pos += 2; m >>= 2; }
+    c = (int)(m & 1u);
+    if (n >= c) pos += 1;
+    return pos;
+}
+
 // 16 fp32 values (columns 16c .. 16c+15 of row r) -> two 16-byte chunks of a tile image
 __device__ __forceinline__ void store_row16(uint8_t* tile, uint32_t r, int c16, const float (&f)[16]) {
     uint4 a = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -90,14 +106,23 @@ __device__ __forceinline__ void load_row16(const uint8_t* tile, uint32_t r, int 
 // prefetched (first version) 176 us for 16384 x 27 rows; one 256-byte bulk copy per row 320 us (the copy engine's
 // per-operation cost); 16-byte cp.async by one loader warp 244 us (too few bytes in flight per warp).
 // Warps 0-7 / 8-15: epilogue of slot 0 / 1 (TWO threads per row, 32 hidden columns each in fp32 registers: with one
-// thread per row the 2 epilogue warps per scheduler could not hide the gate-math latencies; the q / selection part of a
-// row is done by its column-half-0 thread), warp 16: MMA issuer (gates of tile k, then fc2 of tile k-1), warp 17: loader.
+// thread per row the 2 epilogue warps per scheduler could not hide the gate-math latencies), warp 16: MMA issuer, warp 17:
+// loader, warp 18: avail loader.  What the per-role wait profile (tools/ro_role_profile.py) changed: a slot's chain per
+// tile was loads -> h_0 operand -> 16 gate MMAs -> gate math -> new hidden state out -> fc2 -> q + selection, 14.5 k cycles,
+// with the selection (one thread per row, 5.3 k cycles) and the wait for the gate MMAs (4.9 k) the longest links.  Now (1)
+// the x halves of the gate MMAs are issued as soon as the tile's inputs have landed, before the epilogue has written the
+// h_0 operand; (2) the two threads of a row split the q chunks / availability bits / Philox draws of the selection and
+// the column-half-1 thread hands its partial result over through 16 bytes of shared memory and a 64-thread named barrier;
+// the availability bits and the draws are computed BEFORE the fc2 MMAs are waited for; (3) the new hidden state leaves
+// through the staging tiles with two tensor-map bulk STORES issued by the loader thread (rows beyond R are clipped by the
+// tensor map) instead of 8 x (LDS + coalesced STG) per epilogue thread.
 namespace ro {
 constexpr int WIH = 0, WHH = 24576, W2 = 49152;
 constexpr int SLOT0 = 57344;
 constexpr int S_X = 0, S_HT = 16384, S_HS = 32768, S_AV = S_HS + 32768;      // S_HS: two fp32 tiles (columns 0-31, 32-63)
 constexpr int AV_BYTES = 18432;                               // staged avail rows: 128 * A * 4 <= this (A <= 36)
-constexpr int SLOT_BYTES = S_AV + AV_BYTES + 2048;            // 86016 = 84 KB (multiple of 1024)
+constexpr int S_XC = S_AV + AV_BYTES;                         // 16 bytes per row: selection hand-over between the two threads of a row
+constexpr int SLOT_BYTES = S_XC + 2048;                       // 86016 = 84 KB (multiple of 1024)
 constexpr int BIAS = SLOT0 + 2 * SLOT_BYTES;
 constexpr int BIAS_FLOATS = 128 + 64 + 64 + 64;               // brz | bin | bhn | b2
 constexpr int BARS = BIAS + BIAS_FLOATS * 4;
@@ -107,8 +132,24 @@ constexpr int MMA_W = 16, LOAD_W = 17, AV_W = 18;
 static_assert(SLOT_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "rollout kernel shared memory");
 }  // namespace ro
 
+// Per-role wait / phase accounting (build with PMB_EXTRA_NVCC_FLAGS=-DPMB_RO_PROFILE, read with tools/ro_role_profile.py)
+#ifdef PMB_RO_PROFILE
+__device__ unsigned long long g_ro_prof[16];
+#define RWAIT(idx, bar, par) do { long long _t0 = clock64(); mbar_wait(bar, par); if (lane == 0) prof_acc[idx] += clock64() - _t0; } while (0)
+#define RMARK(var) long long var = clock64()
+#define RADD(idx, expr) do { if (lane == 0) prof_acc[idx] += (expr); } while (0)
+#else
+#define RWAIT(idx, bar, par) mbar_wait(bar, par)
+#define RMARK(var)
+#define RADD(idx, expr)
+#endif
 __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParams P, int av_smem,
-                                                                     const __grid_constant__ CUtensorMap tmap_h0) {
+                                                                     const __grid_constant__ CUtensorMap tmap_h0,
+                                                                     const __grid_constant__ CUtensorMap tmap_h1) {
+#ifdef PMB_RO_PROFILE
+    long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = clock64();
+#endif
     using namespace ro;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -116,13 +157,13 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BARS);
     uint64_t* w_full = bars;
     uint64_t* in_full = bars + 1;        // [2] x tile and h_0 tiles landed
-    uint64_t* xh_free = bars + 3;        // [2] x / hidden-state staging of the slot may be refilled (8 epilogue warps)
+    uint64_t* xh_free = bars + 3;        // [2] x tile dead, new hidden state staged (8 epilogue warps): store it, refill the slot
     uint64_t* hb_ready = bars + 5;       // [2] bf16 h operand written: arrival pair per tile (h_0, then h_1)
     uint64_t* gates_full = bars + 7;     // [2]
     uint64_t* q_full = bars + 9;         // [2]
-    uint64_t* tmem_free = bars + 11;     // [2] q drained
+    uint64_t* tmem_free = bars + 11;     // [2] q drained (8 warps)
     uint64_t* av_full = bars + 13;       // [2] avail rows landed
-    uint64_t* av_free = bars + 15;       // [2] selection done with the avail rows (4 warps)
+    uint64_t* av_free = bars + 15;       // [2] selection done with the avail rows (8 warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,8 +172,8 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&in_full[i], 1); mbar_init(&xh_free[i], 8); mbar_init(&hb_ready[i], 8);
-            mbar_init(&av_full[i], 1); mbar_init(&av_free[i], 4);
-            mbar_init(&gates_full[i], 1); mbar_init(&q_full[i], 1); mbar_init(&tmem_free[i], 4);
+            mbar_init(&av_full[i], 1); mbar_init(&av_free[i], 8);
+            mbar_init(&gates_full[i], 1); mbar_init(&q_full[i], 1); mbar_init(&tmem_free[i], 8);
         }
         fence_barrier_init();
     }
@@ -148,6 +189,9 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+#ifdef PMB_RO_PROFILE
+    if (threadIdx.x == 0) prof_acc[13] = clock64() - prof_t0;      // prologue
+#endif
 
     if (warp == LOAD_W) {
         // ===== loader =====
@@ -158,13 +202,38 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
             bulk_copy_g2s(smem + W2, P.w2_img, 8192, w_full);
         }
         // the staging of a slot is released in two steps (x / hidden state after the gate math, avail after the selection),
-        // so the next tile's big copies are in flight while the current one still selects; avail has its own warp
+        // so the next tile's big copies are in flight while the current one still selects; avail has its own warp.
+        // Use k of a slot starts by storing the new hidden state the slot's previous tile (k - 2) left in the staging tiles.
         if (lane == 0) {
-            for (int k = 0; k < n_my; ++k) {
+            for (int k = 0; k < n_my + 2; ++k) {
                 const int s = k & 1, u = k >> 1;
+                if (k >= 2 && k - 2 >= n_my) continue;
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
                 uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
-                mbar_wait(&xh_free[s], (uint32_t)((u & 1) ^ 1));
+                RWAIT(0, &xh_free[s], (uint32_t)((u & 1) ^ 1));
+                if (k >= 2 && P.h_last) {
+                    const int64_t ptile = tile - 2 * (int64_t)gridDim.x;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&tmap_h1)),
+                                     "r"(32 * hf), "r"((int)(ptile * TILE_ROWS)), "r"(smem_u32(sl + S_HS + hf * TILE_BYTES))
+                                     : "memory");
+                    bulk_commit_group();
+                    bulk_wait_group_read<0>();                     // the staging tiles may be refilled
+                }
+                if (k >= n_my) continue;
+                // the slot's NEXT tile into L2 now: its copies can only start when this tile's gate math is over, and the
+                // chain math -> store -> load -> h_0 operand -> gate MMAs -> math of a slot is what bounds the kernel
+                if (k + 2 < n_my) {
+                    const int64_t ntile = tile + 2 * (int64_t)gridDim.x;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.x_ti + ntile * TILE_BYTES), "r"(TILE_BYTES) : "memory");
+                    if (P.h0) {
+                        const int64_t nrow0 = ntile * TILE_ROWS;
+                        const int64_t nrows = P.R - nrow0 < TILE_ROWS ? P.R - nrow0 : TILE_ROWS;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.h0 + nrow0 * 64), "r"((uint32_t)(nrows * 256)) : "memory");
+                    }
+                }
                 mbar_arrive_expect_tx(&in_full[s], TILE_BYTES + (P.h0 ? 2 * TILE_BYTES : 0));
                 bulk_copy_g2s(sl + S_X, P.x_ti + tile * TILE_BYTES, TILE_BYTES, &in_full[s]);
                 if (P.h0) {
@@ -178,6 +247,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                             : "memory");
                 }
             }
+            bulk_wait_group<0>();                                  // the hidden-state stores have completed
         }
     } else if (warp == AV_W) {
         // ===== avail loader: one copy per env the tile touches (an env's N x A block is contiguous; the batch stride is free) =====
@@ -188,7 +258,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                 uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
                 const int64_t row0 = tile * TILE_ROWS;
                 const int rows_here = (int)(P.R - row0 < TILE_ROWS ? P.R - row0 : TILE_ROWS);
-                mbar_wait(&av_free[s], (uint32_t)((u & 1) ^ 1));
+                RWAIT(1, &av_free[s], (uint32_t)((u & 1) ^ 1));
                 if (lane == 0) mbar_arrive_expect_tx(&av_full[s], (uint32_t)(rows_here * P.A * 4));
                 __syncwarp();
                 const int64_t e0 = (int64_t)((uint32_t)row0 / (uint32_t)P.N);
@@ -216,10 +286,9 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                               idq, kk != 0);
                 umma_commit(&q_full[s]);
             };
-            auto gates = [&](int k) {
+            auto gates_x = [&](int k) {                            // the halves that only need the x tile
                 const int s = k & 1;
                 const uint32_t xt = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_X);
-                const uint32_t ht = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_HT);
                 const uint32_t tm = tmem_base + 256 * s;
                 tc_fence_after();
 #pragma unroll
@@ -227,12 +296,18 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                     umma_bf16(tm, umma_desc_sw128(xt + kk * 32, 16, 1024), umma_desc_sw128(wih + kk * 32, 16, 1024), id128,
                               kk != 0);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)                     //       + h . W_h{r,z}^T
-                    umma_bf16(tm, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024), id128, 1);
-#pragma unroll
                 for (int kk = 0; kk < 4; ++kk)                     // n, input part
                     umma_bf16(tm + 128, umma_desc_sw128(xt + kk * 32, 16, 1024),
                               umma_desc_sw128(wih + 16384 + kk * 32, 16, 1024), id64, kk != 0);
+            };
+            auto gates_h = [&](int k) {                            // the halves that need the h_0 operand; commits both
+                const int s = k & 1;
+                const uint32_t ht = smem_u32(smem + SLOT0 + s * SLOT_BYTES + S_HT);
+                const uint32_t tm = tmem_base + 256 * s;
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)                     // r|z += h . W_h{r,z}^T
+                    umma_bf16(tm, umma_desc_sw128(ht + kk * 32, 16, 1024), umma_desc_sw128(whh + kk * 32, 16, 1024), id128, 1);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)                     // n, hidden part
                     umma_bf16(tm + 192, umma_desc_sw128(ht + kk * 32, 16, 1024),
@@ -240,63 +315,54 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                 umma_commit(&gates_full[s]);
             };
             mbar_wait(w_full, 0);
-            // Whatever is ready is issued: the gates of the next tile (inputs landed, h_0 operand written, accumulators
-            // drained) or fc2 of the oldest tile whose new hidden state is written.  A fixed order (gates k, fc2 k-1) made
-            // fc2 of one tile wait for the LOADS of the next one.  The tests are ordered so that no parity test can see a
-            // stale phase: in_full(u) implies the slot's previous use is over; fc2 is only tried after its tile's gates.
-            int kg = 0, kf = 0;
+            // Whatever is ready is issued: the x halves of the gates of the next tile (inputs landed, accumulators drained),
+            // the h halves of the oldest tile whose h_0 operand is written, or fc2 of the oldest tile whose new hidden state
+            // is written.  A fixed order (gates k, fc2 k-1) made fc2 of one tile wait for the LOADS of the next one.  The
+            // tests are ordered so that no parity test can see a stale phase: in_full(u) implies the slot's previous use
+            // is over; the h halves are only tried after the tile's x halves, fc2 only after its h halves; hb_ready
+            // alternates h_0 (parity 0) / h_1 (parity 1) per tile and the epilogue writes the next h_0 only after q_full.
+            int kx = 0, kg = 0, kf = 0;
             while (kf < n_my) {
-                if (kg < n_my) {
-                    const int s = kg & 1, u = kg >> 1;
-                    if (mbar_try_wait(&in_full[s], (uint32_t)(u & 1)) && mbar_try_wait(&hb_ready[s], 0) &&
-                        mbar_try_wait(&tmem_free[s], (uint32_t)((u & 1) ^ 1))) {
-                        gates(kg);
-                        ++kg;
+                if (kx < n_my) {
+                    const int s = kx & 1, u = kx >> 1;
+                    if (mbar_try_wait(&in_full[s], (uint32_t)(u & 1)) && mbar_try_wait(&tmem_free[s], (uint32_t)((u & 1) ^ 1))) {
+                        RMARK(tg0);
+                        gates_x(kx);
+                        RADD(2, clock64() - tg0);
+                        ++kx;
                     }
                 }
+                if (kg < kx && mbar_try_wait(&hb_ready[kg & 1], 0)) {
+                    RMARK(tg0);
+                    gates_h(kg);
+                    RADD(2, clock64() - tg0);
+                    ++kg;
+                }
                 if (kf < kg && mbar_try_wait(&hb_ready[kf & 1], 1)) {
+                    RMARK(tf0);
                     fc2(kf);
+                    RADD(2, clock64() - tf0);
                     ++kf;
                 }
             }
         }
-    } else {
-        // ===== epilogue of slot s: hidden state in, gate math, hidden state out, q, selection =====
-        const int s = warp >> 3, q4 = warp & 3, ch = (warp >> 2) & 1;
-        uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
-        const uint32_t tlane = tmem_base + 256 * s + ((uint32_t)(q4 * 32) << 16);
+    } else if (warp < 8) {
+        // ===== gate group: EVERY tile of the CTA, slots alternating.  Gate math out of TMEM, new hidden state (bf16 operand
+        // of fc2 and fp32 staging tile).  The h_0 operand of a tile is written by the selection group, a tile ahead. =====
+        const int q4 = warp & 3, ch = warp >> 2;
         const uint32_t r = q4 * 32 + lane;                        // tile row of this thread; it owns columns 32 ch .. +31
-        uint8_t* hs = sl + S_HS + ch * TILE_BYTES;                // the fp32 staging tile of this column half
         const float* bias_c = bias + 32 * ch;
-        for (int k = s; k < n_my; k += 2) {
-            const int u = k >> 1;
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-            const int64_t row = tile * TILE_ROWS + r;
-            const bool valid = row < P.R;
-            float h[32];
-            mbar_wait(&in_full[s], (uint32_t)(u & 1));
-            if (valid && P.h0) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 v = *reinterpret_cast<const float4*>(hs + sw128_offset(r, (uint32_t)j4));
-                    h[4 * j4] = v.x; h[4 * j4 + 1] = v.y; h[4 * j4 + 2] = v.z; h[4 * j4 + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) h[j] = 0.f;
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = h[16 * c + j];
-                store_row16(sl + S_HT, r, 2 * ch + c, f);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hb_ready[s]);
-
-            mbar_wait(&gates_full[s], (uint32_t)(u & 1));
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k & 1, u = k >> 1;
+            uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
+            uint8_t* hs = sl + S_HS + ch * TILE_BYTES;            // the fp32 staging tile of this column half
+            const uint32_t tlane = tmem_base + 256 * s + ((uint32_t)(q4 * 32) << 16);
+            RWAIT(3, &in_full[s], (uint32_t)(u & 1));          // (complete long before the gate MMAs are: makes the staged h_0 visible here)
+#ifdef PMB_RO_PROFILE
+            if (threadIdx.x == 0 && k == 0) prof_acc[14] = clock64() - prof_t0;      // kernel entry -> first tile landed
+#endif
+            RWAIT(4, &gates_full[s], (uint32_t)(u & 1));
+            RMARK(tm0);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -305,64 +371,104 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                 tmem_ld_32x16(tlane + 64 + 32 * ch + 16 * c, az);
                 tmem_ld_32x16(tlane + 128 + 32 * ch + 16 * c, ain);
                 tmem_ld_32x16(tlane + 192 + 32 * ch + 16 * c, ahn);
-                float br[16], bz[16], bn[16], bh[16];                 // 16-byte loads of the bias table (same address in all lanes)
+                tmem_wait_ld();
+                // four columns at a time: biases (16-byte loads, same address in all lanes) and h_0 (again from the staging
+                // tile: not kept in registers across the MMA wait) are loaded right where they are used
+                uint32_t pk[8];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
-                    *reinterpret_cast<float4*>(&br[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 16 * c + 4 * j4);
-                    *reinterpret_cast<float4*>(&bz[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 64 + 16 * c + 4 * j4);
-                    *reinterpret_cast<float4*>(&bn[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 128 + 16 * c + 4 * j4);
-                    *reinterpret_cast<float4*>(&bh[4 * j4]) = *reinterpret_cast<const float4*>(bias_c + 192 + 16 * c + 4 * j4);
-                }
-                tmem_wait_ld();
-                float fh[16];
+                    const float4 br = *reinterpret_cast<const float4*>(bias_c + 16 * c + 4 * j4);
+                    const float4 bz = *reinterpret_cast<const float4*>(bias_c + 64 + 16 * c + 4 * j4);
+                    const float4 bn = *reinterpret_cast<const float4*>(bias_c + 128 + 16 * c + 4 * j4);
+                    const float4 bh = *reinterpret_cast<const float4*>(bias_c + 192 + 16 * c + 4 * j4);
+                    float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float* hp = reinterpret_cast<float*>(hs + sw128_offset(r, (uint32_t)(4 * c + j4)));
+                    if (P.h0) h4 = *reinterpret_cast<const float4*>(hp);
+                    const float brv[4] = {br.x, br.y, br.z, br.w}, bzv[4] = {bz.x, bz.y, bz.z, bz.w};
+                    const float bnv[4] = {bn.x, bn.y, bn.z, bn.w}, bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+                    const float hv4[4] = {h4.x, h4.y, h4.z, h4.w};
+                    float o[4];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int jj = 16 * c + j;
-                    const float rg = fast_sigmoid(__uint_as_float(ar[j]) + br[j]);
-                    const float zg = fast_sigmoid(__uint_as_float(az[j]) + bz[j]);
-                    const float hn = __uint_as_float(ahn[j]) + bh[j];
-                    const float ng = fast_tanh(__uint_as_float(ain[j]) + bn[j] + rg * hn);
-                    const float hv = ng + zg * (h[jj] - ng);
-                    h[jj] = hv;
-                    fh[j] = hv;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * j4 + jj;
+                        const float rg = fast_sigmoid(__uint_as_float(ar[j]) + brv[jj]);
+                        const float zg = fast_sigmoid(__uint_as_float(az[j]) + bzv[jj]);
+                        const float hn = __uint_as_float(ahn[j]) + bhv[jj];
+                        const float ng = fast_tanh(__uint_as_float(ain[j]) + bnv[jj] + rg * hn);
+                        o[jj] = ng + zg * (hv4[jj] - ng);
+                    }
+                    pk[2 * j4] = pack_bf16x2(o[0], o[1]);
+                    pk[2 * j4 + 1] = pack_bf16x2(o[2], o[3]);
+                    // new hidden state: in place in the staging tile of this column half, in the layout the tensor map
+                    // describes; the loader thread stores both staging tiles with two bulk tensor copies once all 8 warps arrived
+                    if (P.h_last) *reinterpret_cast<float4*>(hp) = make_float4(o[0], o[1], o[2], o[3]);
                 }
-                store_row16(sl + S_HT, r, 2 * ch + c, fh);
+                *reinterpret_cast<uint4*>(sl + S_HT + sw128_offset(r, (uint32_t)(2 * (2 * ch + c)))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(sl + S_HT + sw128_offset(r, (uint32_t)(2 * (2 * ch + c) + 1))) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&hb_ready[s]);
-            // new hidden state: own half row into the (dead) h_0 staging tile, then the warp writes its 32 half rows out
-            // with coalesced 16-byte stores (four 128-byte segments per instruction)
-            if (P.h_last) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    *reinterpret_cast<float4*>(hs + sw128_offset(r, (uint32_t)j4)) =
-                        make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
-                __syncwarp();
-                const int64_t trow0 = tile * TILE_ROWS;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t rr = (uint32_t)(q4 * 32 + 4 * i + (lane >> 3));
-                    const int cj = lane & 7;
-                    if (trow0 + rr < P.R)
-                        *reinterpret_cast<float4*>(P.h_last + (trow0 + rr) * 64 + 32 * ch + cj * 4) =
-                            *reinterpret_cast<const float4*>(hs + sw128_offset(rr, (uint32_t)cj));
-                }
-                __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&hb_ready[s]);                         // h_1 operand written: fc2 may be issued
+                mbar_arrive(&xh_free[s]);                          // gate MMAs complete, new hidden state staged
             }
+            RADD(8, clock64() - tm0);
+        }
+    } else {
+        // ===== selection group: q = fc2(h) out of TMEM and the epsilon-greedy selection of EVERY tile, one tile behind the
+        // gate group.  The two threads of a row split the 16-action chunks: column half 0 takes chunks 0 and 2, column half 1
+        // chunks 1 and 3 and the Philox draws.  Everything that does not need q (the availability bits, the draws) is done
+        // before the fc2 MMAs are waited for.
+        const int q4 = warp & 3, ch = (warp >> 2) & 1;
+        const uint32_t r = q4 * 32 + lane;
+        const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
+        // h_0 of tile k2 (fp32 staging tile, or zeros) -> bf16 operand tile of its slot.  Done while the gate group is still
+        // busy with tile k2 - 1, so the gate MMAs of k2 are complete when the gate group gets there.  The operand tile is free:
+        // its last readers, the fc2 MMAs of tile k2 - 2, completed before this group selected for that tile.
+        auto h0_operand = [&](int k2) {
+            const int s2 = k2 & 1, u2 = k2 >> 1;
+            uint8_t* sl2 = smem + SLOT0 + s2 * SLOT_BYTES;
+            const uint8_t* hs2 = sl2 + S_HS + ch * TILE_BYTES;
+            RWAIT(15, &in_full[s2], (uint32_t)(u2 & 1));
+            RMARK(tp0);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float f[16];
+                if (P.h0) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        *reinterpret_cast<float4*>(&f[4 * j4]) = *reinterpret_cast<const float4*>(hs2 + sw128_offset(r, (uint32_t)(4 * c + j4)));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = 0.f;
+                }
+                store_row16(sl2 + S_HT, r, 2 * ch + c, f);
+            }
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&xh_free[s]);              // gate MMAs complete, staging read: x / h tiles may be refilled
-            // q = fc2(h).  (Both halves wait: the next tile's h_0 operand must not overwrite HT under the fc2 MMAs.)
-            mbar_wait(&q_full[s], (uint32_t)(u & 1));
-            if (ch != 0) continue;                                // q and the selection belong to the column-half-0 thread
-            tc_fence_after();
-            float* qo = P.q ? P.q + row * P.A : nullptr;
-            const bool q_vec = (P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.q) & 15) == 0;
+            if (lane == 0) mbar_arrive(&hb_ready[s2]);
+            RADD(7, clock64() - tp0);
+        };
+        if (n_my > 0) h0_operand(0);
+        for (int k = 0; k < n_my; ++k) {
+            const int s = k & 1, u = k >> 1;
+            uint8_t* sl = smem + SLOT0 + s * SLOT_BYTES;
+            const uint32_t tlane = tmem_base + 256 * s + ((uint32_t)(q4 * 32) << 16);
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+            const int64_t row = tile * TILE_ROWS + r;
+            const bool valid = row < P.R;
             const bool select = P.actions_out != nullptr && valid;
+            float* qo = P.q ? P.q + row * P.A : nullptr;
             const int32_t* av = nullptr;
             bool av_vec = true;
-            if (av_smem) mbar_wait(&av_full[s], (uint32_t)(u & 1));
+            // first what the gate group will wait for next: the h_0 operand of the next tile (its inputs landed while this
+            // group selected for the previous tile)
+            if (k + 1 < n_my) h0_operand(k + 1);
+            if (av_smem) RWAIT(6, &av_full[s], (uint32_t)(u & 1));
+            RMARK(tq0);
+            uint32_t oks2[2] = {0u, 0u};                           // availability bits of the own chunks ch, ch + 2
+            uint32_t rnd_x = 0u, rnd_y = 0u;
             if (select) {
                 if (av_smem) av = reinterpret_cast<const int32_t*>(sl + S_AV) + r * P.A;
                 else {
@@ -370,15 +476,46 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                     av = P.avail + bb * P.avail_sb + (row - bb * P.N) * P.A;
                     av_vec = (P.A & 3) == 0 && (P.avail_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
                 }
-            }
-            float best = -INFINITY;
-            int bidx = 0x7fffffff, cnt = 0;
-            uint32_t ok_lo = 0u, ok_hi = 0u;                      // available actions 0..31 / 32..63
-            // four chunks of 16 actions, the action index a compile-time constant in each (the first version looped over
-            // c0 with 64-bit variable shifts and spent ~6000 cycles per tile here)
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c0 = 16 * cc;
+                for (int i = 0; i < 2; ++i) {
+                    const int c0 = 16 * (ch + 2 * i);
+                    if (c0 < A_pad) {
+                        int avj[16];
+                        if (av_vec && c0 + 16 <= P.A) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const int4 w4 = *(reinterpret_cast<const int4*>(av + c0) + j4);
+                                avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? av[c0 + j] : 0;
+                        }
+                        uint32_t oks = 0u;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) oks |= (avj[j] != 0 ? 1u : 0u) << j;
+                        const int left = P.A - c0;                                   // actions of this chunk that exist
+                        oks &= left >= 16 ? 0xffffu : ((1u << (left > 0 ? left : 0)) - 1u);
+                        oks2[i] = oks;
+                    }
+                }
+                if (ch == 1 && !P.expo) {
+                    // Philox mode (same arithmetic as epsilon_greedy_kernel): word x -> epsilon test, word y -> rank
+                    const uint4 r0 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
+                                                                 ((uint32_t)(row >> 32) << 16)),
+                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+                    rnd_x = r0.x; rnd_y = r0.y;
+                }
+            }
+            RADD(10, clock64() - tq0);
+            RWAIT(5, &q_full[s], (uint32_t)(u & 1));
+            RMARK(tq1);
+            tc_fence_after();
+            float best = -INFINITY;
+            int bidx = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int c0 = 16 * (ch + 2 * i);
                 if (c0 < A_pad) {
                     uint32_t aq[16];
                     tmem_ld_32x16(tlane + c0, aq);
@@ -405,29 +542,19 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
                             }
                         }
                         if (select) {
-                            int avj[16];
-                            if (av_vec && c0 + 16 <= P.A) {
+                            // arg-max of the chunk as a tournament (depth 4 instead of a 16-long dependent chain); the lower
+                            // index is kept unless the higher one is strictly greater: lowest index wins, as in a scan
+                            const uint32_t oks = oks2[i];
+                            float tv[16];
+                            int ti[16];
 #pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) {
-                                    const int4 w4 = *(reinterpret_cast<const int4*>(av + c0) + j4);
-                                    avj[4 * j4] = w4.x; avj[4 * j4 + 1] = w4.y; avj[4 * j4 + 2] = w4.z; avj[4 * j4 + 3] = w4.w;
-                                }
-                            } else {
+                            for (int j = 0; j < 16; ++j) { tv[j] = (oks >> j) & 1u ? qv[j] : -INFINITY; ti[j] = j; }
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) avj[j] = c0 + j < P.A ? av[c0 + j] : 0;
-                            }
-                            uint32_t oks = 0u;
+                            for (int st = 1; st < 16; st <<= 1)
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) oks |= (avj[j] != 0 ? 1u : 0u) << j;
-                            const int left = P.A - c0;                               // actions of this chunk that exist
-                            oks &= left >= 16 ? 0xffffu : ((1u << (left > 0 ? left : 0)) - 1u);
-                            cnt += __popc(oks);
-                            if (cc < 2) ok_lo |= oks << (16 * (cc & 1)); else ok_hi |= oks << (16 * (cc & 1));
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float v = (oks >> j) & 1u ? qv[j] : -INFINITY;
-                                if (v > best) { best = v; bidx = c0 + j; }          // ascending a, strict >: lowest index wins
-                            }
+                                for (int j = 0; j < 16; j += 2 * st)
+                                    if (tv[j + st] > tv[j]) { tv[j] = tv[j + st]; ti[j] = ti[j + st]; }
+                            if (tv[0] > best) { best = tv[0]; bidx = c0 + ti[0]; }    // chunks ascending, strict >
                         }
                     }
                 }
@@ -435,42 +562,65 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_free[s]);
-            if (select) {
-                if (bidx == 0x7fffffff) bidx = 0;                              // all -inf / NaN: first index
-                int ridx;
-                float uu;
-                if (P.expo) {
-                    // reference arithmetic with injected draws: argmax_a (avail[a] / cnt) / Exp(1)[a]
-                    const float prob = __fdiv_rn(1.0f, (float)cnt);
-                    float rbest = -INFINITY;
-                    ridx = 0x7fffffff;
-                    for (int a = 0; a < P.A; ++a) {
-                        const bool oka = ((a < 32 ? ok_lo >> a : ok_hi >> (a - 32)) & 1u) != 0u;
-                        const float ratio = __fdiv_rn(oka ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
-                        if (ratio > rbest) { rbest = ratio; ridx = a; }
-                    }
-                    if (ridx == 0x7fffffff) ridx = 0;
-                    uu = __ldg(P.u + row);
-                } else {
-                    // Philox mode (same arithmetic as epsilon_greedy_kernel): word x -> epsilon test, word y -> rank
-                    const uint4 r0 = gf_philox4x32_10(make_uint4((uint32_t)P.offset, (uint32_t)(P.offset >> 32), (uint32_t)row,
-                                                                 ((uint32_t)(row >> 32) << 16)),
-                                                      make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-                    uu = 1.0f - gf_u01(r0.x);                  // [0, 1)
-                    int kq = (int)((1.0f - gf_u01(r0.y)) * (float)cnt);
-                    if (kq >= cnt) kq = cnt - 1;
-                    // the kq-th set bit of the availability mask
-                    const int c_lo = __popc(ok_lo);
-                    ridx = cnt <= 0 ? 0 : (kq < c_lo ? (int)__fns(ok_lo, 0u, kq + 1) : 32 + (int)__fns(ok_hi, 0u, kq - c_lo + 1));
+            if (P.actions_out) {
+                // hand-over: 16 bytes per row (best q bits | index | availability bits of chunks 1, 3 | draws) and a
+                // 64-thread named barrier per row quarter.  Both warps wait on it, so the half-1 warp never runs a tile ahead
+                // of its partner: neither the barrier nor the slot's hand-over block can be reused early.
+                uint4* xc = reinterpret_cast<uint4*>(sl + S_XC) + r;
+                const int bar_id = 1 + q4;
+                if (ch == 1) {
+                    const uint32_t explore = (1.0f - gf_u01(rnd_x)) < P.epsilon ? 1u : 0u;      // u in [0, 1)
+                    *xc = make_uint4(__float_as_uint(best), (uint32_t)bidx, oks2[0] | (oks2[1] << 16), (rnd_y & ~1u) | explore);
                 }
-                int pick = (cnt > 0 && uu < P.epsilon) ? ridx : bidx;
-                if (pick >= P.A) pick = 0;
-                P.actions_out[row] = pick;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                if (ch == 0 && select) {
+                    const uint4 o = *xc;
+                    const float best1 = __uint_as_float(o.x);
+                    const int bidx1 = (int)o.y;
+                    if (bidx1 != 0x7fffffff && (best1 > best || (best1 == best && bidx1 < bidx))) { best = best1; bidx = bidx1; }
+                    const uint32_t ok_lo = oks2[0] | (o.z << 16);                // available actions 0..31
+                    const uint32_t ok_hi = oks2[1] | (o.z & 0xffff0000u);        //                   32..63
+                    const int cnt = __popc(ok_lo) + __popc(ok_hi);
+                    if (bidx == 0x7fffffff) bidx = 0;                              // all -inf / NaN: first index
+                    int ridx;
+                    bool explore;
+                    if (P.expo) {
+                        // reference arithmetic with injected draws: argmax_a (avail[a] / cnt) / Exp(1)[a]
+                        const float prob = __fdiv_rn(1.0f, (float)cnt);
+                        float rbest = -INFINITY;
+                        ridx = 0x7fffffff;
+                        for (int a = 0; a < P.A; ++a) {
+                            const bool oka = ((a < 32 ? ok_lo >> a : ok_hi >> (a - 32)) & 1u) != 0u;
+                            const float ratio = __fdiv_rn(oka ? prob : 0.0f, __ldg(P.expo + row * P.A + a));
+                            if (ratio > rbest) { rbest = ratio; ridx = a; }
+                        }
+                        if (ridx == 0x7fffffff) ridx = 0;
+                        explore = __ldg(P.u + row) < P.epsilon;
+                    } else {
+                        explore = (o.w & 1u) != 0u;
+                        int kq = (int)((1.0f - gf_u01(o.w)) * (float)cnt);
+                        if (kq >= cnt) kq = cnt - 1;
+                        // the kq-th set bit of the availability mask
+                        const int c_lo = __popc(ok_lo);
+                        ridx = cnt <= 0 ? 0 : (kq < c_lo ? nth_set_bit(ok_lo, kq) : 32 + nth_set_bit(ok_hi, kq - c_lo));
+                    }
+                    int pick = (cnt > 0 && explore) ? ridx : bidx;
+                    if (pick >= P.A) pick = 0;
+                    P.actions_out[row] = pick;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&av_free[s]);
+            RADD(9, clock64() - tq1);
         }
     }
+#ifdef PMB_RO_PROFILE
+    if (lane == 0) {
+        for (int i = 0; i < 11; ++i) if (prof_acc[i]) atomicAdd(&g_ro_prof[i], (unsigned long long)prof_acc[i]);
+        for (int i = 13; i < 16; ++i) if (prof_acc[i]) atomicAdd(&g_ro_prof[i], (unsigned long long)prof_acc[i]);
+        if (threadIdx.x == 0) { atomicAdd(&g_ro_prof[11], (unsigned long long)(clock64() - prof_t0)); atomicAdd(&g_ro_prof[12], 1ull); }
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_W) {
@@ -753,10 +903,12 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
     // avail rows are staged through shared memory by bulk copies when they fit and are 16-byte granular
     const int av_smem = P.actions_out && P.avail && (P.A & 3) == 0 && 128 * P.A * 4 <= tc::ro::AV_BYTES && (P.avail_sb & 3) == 0 &&
                         ((int64_t)P.N * P.A & 3) == 0 && (reinterpret_cast<uintptr_t>(P.avail) & 15) == 0;
-    // tensor map of the fp32 hidden state [R][64]: boxes of 128 rows x 32 columns, 128-byte swizzle, zero fill beyond R
-    CUtensorMap tmap;
+    // tensor maps of the fp32 hidden state [R][64], in and out: boxes of 128 rows x 32 columns, 128-byte swizzle; loads
+    // fill rows beyond R with zeros, stores clip them
+    CUtensorMap tmap, tmap_out;
     memset(&tmap, 0, sizeof(tmap));
-    if (P.h0) {
+    memset(&tmap_out, 0, sizeof(tmap_out));
+    if (P.h0 || P.h_last) {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -774,17 +926,30 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
         const cuuint64_t gstride[1] = {256};
         const cuuint32_t box[2] = {32, 128};
         const cuuint32_t estr[2] = {1, 1};
-        const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P.h0), gdim, gstride, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { set_error("tc_gru_fwd: cuTensorMapEncodeTiled failed"); return PMB_ERR_CUDA; }
+        for (int io = 0; io < 2; ++io) {
+            const float* base = io ? P.h_last : P.h0;
+            if (!base) continue;
+            const CUresult cr = encode(io ? &tmap_out : &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
+                                       gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { set_error("tc_gru_fwd: cuTensorMapEncodeTiled failed"); return PMB_ERR_CUDA; }
+        }
     }
     PMB_SMEM_ATTR(tc::gru_rollout_kernel, tc::ro::SMEM_BYTES);
     const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
-    tc::gru_rollout_kernel<<<grid, tc::ro::THREADS, tc::ro::SMEM_BYTES, s>>>(P, av_smem, tmap);
+    tc::gru_rollout_kernel<<<grid, tc::ro::THREADS, tc::ro::SMEM_BYTES, s>>>(P, av_smem, tmap, tmap_out);
     PMB_LAUNCH_CHECK("gru_rollout_kernel");
     return PMB_OK;
 }
+
+#ifdef PMB_RO_PROFILE
+extern "C" int pmb_debug_ro_prof(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tc::g_ro_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_ro_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 
 // one partial block per CTA of the persistent grid (grid <= SM count of the current device), with 2x head room

@@ -1,3 +1,5 @@
+#include <cstdlib>
+#include <algorithm>
 // bf16 tensor-core tier: C[m, n] = sum_k A[m, k] * W[n, k] on tcgen05 with fp32 accumulation in TMEM.
 //
 //   A  fp32 in global memory, addressed through RowMap (the EpisodeBatch fields are consumed in
@@ -515,12 +517,17 @@ int launch_tc_gemm(const GemmParams& P, const Epi& epi, cudaStream_t s) {
 namespace fs {
 constexpr int MAX_CHUNKS = 5;
 constexpr int GROUP_ROWS = 16, GROUPS = BM / GROUP_ROWS;     // (8 rows x 6 slots measured no better: 8.5 vs 8.2 ms)
-constexpr int N_SLOTS = 3;
-constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_PROD = N_SLOTS, STORE_W = PROD_W + N_PROD, FIRST_CONV_W = STORE_W + 1, N_CONV = 8;
+constexpr int N_SLOTS = 3;                                   // learner step (both nets: W is 16 KB per k-chunk)
+constexpr int N_SLOTS_1NET = 5;                              // rollout step: W of one net is half the size, two more slots fit
+#ifndef PMB_FC1_NCONV
+#define PMB_FC1_NCONV 8
+#endif
+constexpr int N_EPI = 4, MMA_W = 4, PROD_W = 5, N_CONV = PMB_FC1_NCONV;
 constexpr int RPW = GROUP_ROWS / N_CONV;                     // rows of a group per converter warp
-constexpr int THREADS = 32 * (FIRST_CONV_W + N_CONV);
+// NS staging slots, one producer warp each (every producer warp owns one staging slot: parity waits are only safe one
+// phase apart), then the converter warps
+constexpr int threads_for(int ns) { return 32 * (PROD_W + ns + N_CONV); }
 static_assert(RPW >= 1 && RPW * N_CONV == GROUP_ROWS, "group rows must divide over the converter warps");
-static_assert(N_PROD == N_SLOTS, "every producer warp owns one staging slot (parity waits are only safe one phase apart)");
 }  // namespace fs
 
 struct Fc1StreamParams {
@@ -541,7 +548,7 @@ struct Fc1StreamParams {
     uint8_t* x_on; uint8_t* x_tg;  // tile images [T][n_tiles][16 KB]
     uint32_t* relu_mask;           // [T][n_tiles][2][128]
     int use_act;
-    int l2_prefetch;               // 1: prefetch the next tile's runs into L2
+    int l2_prefetch;               // n > 0: prefetch the runs of the CTA's n-th next tile into L2 (off by default)
     int n_nets;                    // 2: online + target (learner step), 1: online only (rollout step)
     int t0;                        // batch timestep of item t = 0 (rollout: the step index; obs is addressed at t0 + t)
 };
@@ -571,18 +578,21 @@ __device__ unsigned long long g_fc1_prof[16];
 #define TMARK(var)
 #define TADD(idx, expr)
 #endif
-template <int NC>
-__global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamParams P) {
+template <int NC, int NS>
+__global__ void __launch_bounds__(fs::threads_for(NS), 1) fc1_stream_kernel(Fc1StreamParams P) {
 #ifdef PMB_FC1_PROFILE
-    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
 #endif
     using namespace fs;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int N_SLOTS = NS, N_PROD = NS, FIRST_CONV_W = PROD_W + NS;
     constexpr int tile_bytes = NC * A_STAGE_BYTES;
-    uint8_t* w_s = smem;                                    // [n_chunks][16 KB]
-    uint8_t* a_s = smem + tile_bytes;                       // [n_chunks][16 KB]
+    // W of a k-chunk: 128 rows x 128 B (online | target); the rollout step keeps the online half only
+    const int w_chunk = P.n_nets == 2 ? A_STAGE_BYTES : A_STAGE_BYTES / 2;
+    uint8_t* w_s = smem;                                    // [n_chunks][w_chunk]
+    uint8_t* a_s = smem + NC * w_chunk;                     // [n_chunks][16 KB]
     uint8_t* stage = a_s + tile_bytes;                      // [N_SLOTS][slot_bytes]
     int* rowoff = reinterpret_cast<int*>(stage + N_SLOTS * P.slot_bytes);   // [N_SLOTS][16] byte offset of a row in its slot
     int* rown = rowoff + N_SLOTS * GROUP_ROWS;                              // [N_SLOTS][16] agent index of the row
@@ -617,8 +627,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
         // same warp, so consecutive uses of a slot are program-ordered (a parity wait must never be two phases ahead).
         const int pw = warp - PROD_W;
         if (pw == 0 && lane == 0) {
-            mbar_arrive_expect_tx(w_full, (uint32_t)tile_bytes);
-            bulk_copy_g2s(w_s, P.Wp, (uint32_t)tile_bytes, w_full);
+            mbar_arrive_expect_tx(w_full, (uint32_t)(NC * w_chunk));
+            for (int c = 0; c < NC; ++c)
+                bulk_copy_g2s(w_s + c * w_chunk, reinterpret_cast<const uint8_t*>(P.Wp) + c * A_STAGE_BYTES, (uint32_t)w_chunk, w_full);
         }
         // Lane i owns the i-th contiguous run of a group (one episode each) and computes its descriptor - global
         // address, staging offset, head / interior / tail split - in closed form, in parallel with the other lanes
@@ -631,6 +642,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
             for (int g = 0; g < GROUPS; ++g, ++git) {
                 const int slot = git % N_SLOTS;
                 if (slot != pw) continue;
+                TMARK(pp0);
                 uint8_t* sl = stage + slot * P.slot_bytes;
                 int* ro = rowoff + slot * GROUP_ROWS;
                 int* rn = rown + slot * GROUP_ROWS;
@@ -652,9 +664,10 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                     ga = reinterpret_cast<const char*>(P.obs + ep_row(P.ep_index, (int64_t)b0 + lane) * P.obs_sb +
                                                        ((t + P.t0) * P.N + n0) * (int64_t)P.O);
                     phase = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15);
-                    // staging offset: same 16-byte phase as the source; 48 bytes of slack per run keep the runs - and the
-                    // up to 15 bytes copied before / after each of them - disjoint
-                    cur = (((uint32_t)lr * P.O * 4u + 15u) & ~15u) + 48u * lane + phase;
+                    // staging offset: same 128-BYTE phase as the source (the copy engine then moves whole lines: with only the
+                    // 16-byte phase matched every line is split and shifted); 320 bytes of slack per run keep the runs - and
+                    // the up to 15 bytes copied before / after each of them - disjoint
+                    cur = (((uint32_t)lr * P.O * 4u + 127u) & ~127u) + 320u * lane + (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 127);
                     // ONE bulk copy per run, widened to 16-byte boundaries on both sides (the extra bytes stay inside the
                     // 16-byte granules the run touches anyway - never another page - and land in the slack).  The first
                     // version copied the aligned interior and fetched head / tail with 4-byte cp.async: with the 32
@@ -664,8 +677,8 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 const uint32_t tx = __reduce_add_sync(0xffffffffu, cp_bytes);
                 // L2 prefetch of the same group of this CTA's NEXT tile: the staging ring is all the shared memory that is
                 // left (3 x 18 KB in flight per SM), so the copies should see L2 latency, not loaded-HBM latency
-                if (P.l2_prefetch && cnt > 0 && item + gridDim.x < n_items) {
-                    const int64_t item2 = item + gridDim.x;
+                if (P.l2_prefetch && cnt > 0 && item + (int64_t)P.l2_prefetch * gridDim.x < n_items) {
+                    const int64_t item2 = item + (int64_t)P.l2_prefetch * gridDim.x;
                     const int64_t t2 = item2 / P.n_tiles, tile2 = item2 - t2 * P.n_tiles;
                     const int64_t q0 = tile2 * BM + g * GROUP_ROWS;
                     int rows2 = P.R - q0 < GROUP_ROWS ? (int)(P.R - q0) : GROUP_ROWS;
@@ -689,7 +702,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 const int rj = lane < first_cnt ? 0 : 1 + (lane - first_cnt) / P.N;
                 const int lrj = rj == 0 ? 0 : first_cnt + (rj - 1) * P.N;
                 const uint32_t cur_j = __shfl_sync(0xffffffffu, cur, rj & 31);
+                TADD(10, clock64() - pp0);                         // producer: descriptors of the group (before the slot wait)
                 TWAIT(0, &st_empty[slot], ((git / N_SLOTS) & 1) ^ 1);
+                TMARK(pp1);
                 if (lane < GROUP_ROWS) {
                     ro[lane] = lane < rows_here ? (int)(cur_j + (uint32_t)(lane - lrj) * P.O * 4u) : -1;   // rows beyond R: zeros
                     rn[lane] = (rj == 0 ? n00 : 0) + (lane - lrj);
@@ -699,6 +714,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 if (lane == 0) {
                     if (tx) mbar_arrive_expect_tx(&st_full[slot], tx); else mbar_arrive(&st_full[slot]);
                 }
+                TADD(11, clock64() - pp1);                         // producer: tables, copies, arrival
             }
         }
     } else if (warp >= FIRST_CONV_W) {
@@ -798,7 +814,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 const uint32_t tm = tmem_base + 128u * b;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const uint32_t a_addr = smem_u32(a_s + c * A_STAGE_BYTES), w_addr = smem_u32(w_s + c * A_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(a_s + c * A_STAGE_BYTES), w_addr = smem_u32(w_s + c * w_chunk);
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk)
                         umma_bf16(tm, umma_desc_sw128(a_addr + kk * 32, 16, 1024), umma_desc_sw128(w_addr + kk * 32, 16, 1024),
@@ -808,10 +824,9 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
                 umma_commit(&tfull[b]);
             }
         }
-    } else if (warp == STORE_W) {
-        // (idle: the obs image is written by the converters.  One warp copying the finished A tile out with 16-byte loads /
-        // stores took longer than the MMAs - 8.65 against 7.23 ms)
     } else {
+        // (no store warp: the obs image is written by the converters.  One warp copying the finished A tile out with 16-byte
+        // loads / stores took longer than the MMAs - 8.65 against 7.23 ms)
         // ===== epilogue: one row per thread; x = relu(acc [+ id/bias table] + act table) -> bf16 tile images + mask.
         // (Eight epilogue warps, one per row and net, measured slower: 7.21 -> 7.53 ms.) =====
         const uint32_t r = (uint32_t)(warp * 32 + lane);
@@ -890,6 +905,7 @@ __global__ void __launch_bounds__(fs::THREADS, 1) fc1_stream_kernel(Fc1StreamPar
 #ifdef PMB_FC1_PROFILE
     if (lane == 0) {
         for (int i = 0; i < 8; ++i) if (prof_acc[i]) atomicAdd(&g_fc1_prof[i], (unsigned long long)prof_acc[i]);
+        for (int i = 10; i < 12; ++i) if (prof_acc[i]) atomicAdd(&g_fc1_prof[i], (unsigned long long)prof_acc[i]);
         if (threadIdx.x == 0) { atomicAdd(&g_fc1_prof[8], (unsigned long long)(clock64() - prof_t0)); atomicAdd(&g_fc1_prof[9], 1ull); }
     }
 #endif
@@ -1028,7 +1044,9 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     // the streaming kernel packs its own W (fc1_stream_pack_kernel) and needs the agent-id table only when the one-hot
     // columns do not fit the K padding
     const int n_chunks_s = (d->O + tc::BK - 1) / tc::BK;
-    const int slot_bytes_s = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 48 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
+    // a group is at most (GROUP_ROWS - 1) / N + 2 contiguous runs, each displaced by < 320 bytes (see the producer)
+    const int max_runs_s = std::min(tc::fs::GROUP_ROWS, (tc::fs::GROUP_ROWS - 1) / d->N + 2);
+    const int slot_bytes_s = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 320 * max_runs_s + 128, 128);
     const int64_t smem_need_s = 1024 + 2 * (int64_t)n_chunks_s * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes_s +
                                 2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
     const bool use_stream = tile_images && n_chunks_s <= tc::fs::MAX_CHUNKS && smem_need_s <= 232448;
@@ -1062,7 +1080,7 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
                          reinterpret_cast<uint8_t*>(x_on), reinterpret_cast<uint8_t*>(x_tg), t0, nt, d->N, d->A,
                          d->obs_last_action, n_tiles, R, relu_mask};
         const int n_chunks = (d->O + tc::BK - 1) / tc::BK;
-        const int slot_bytes = (int)align_up((int64_t)tc::fs::GROUP_ROWS * d->O * 4 + 48 * (tc::fs::GROUP_ROWS + 2) + 64, 128);
+        const int slot_bytes = slot_bytes_s;
         const int64_t smem_need = 1024 + 2 * (int64_t)n_chunks * tc::A_STAGE_BYTES + tc::fs::N_SLOTS * (int64_t)slot_bytes +
                                   2 * tc::fs::N_SLOTS * tc::fs::GROUP_ROWS * 4 + 256;
         if (n_chunks <= tc::fs::MAX_CHUNKS && smem_need <= 232448) {
@@ -1083,13 +1101,29 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
             Q.x_on = reinterpret_cast<uint8_t*>(x_on); Q.x_tg = reinterpret_cast<uint8_t*>(x_tg);
             Q.relu_mask = relu_mask; Q.use_act = d->obs_last_action;
             Q.n_nets = x_tg ? 2 : 1; Q.t0 = t0;
-            Q.l2_prefetch = 1;
+            // L2 prefetch of the CTA's next tile(s): measured (round 2, same box, alternating) as a LOSS - rollout step 0.196 ms
+            // with one tile ahead, 0.217 ms with two, 0.190 ms without; learner fc1 8.1-8.4 / 8.8 / 8.0 ms - the copies of the
+            // ring already keep the memory system busy and the prefetch instructions cost the producers issue time.
+            // PMB_FC1_PREFETCH = tiles ahead keeps the experiment available.
+            Q.l2_prefetch = 0;
+            { const char* e = getenv("PMB_FC1_PREFETCH"); if (e) Q.l2_prefetch = atoi(e); }
             const int64_t n_items = (int64_t)nt * n_tiles;
             const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
+            // one net (rollout step): W takes half the shared memory, the staging ring gets two more slots when they fit -
+            // the stream is bound by the bytes in flight per SM (slot turn-around ~3500 cycles: 3 x 18 KB give 4.6 TB/s)
+            const int64_t smem_1net = 1024 + (int64_t)n_chunks * (tc::A_STAGE_BYTES / 2) + (int64_t)n_chunks * tc::A_STAGE_BYTES +
+                                      tc::fs::N_SLOTS_1NET * (int64_t)slot_bytes + 2 * tc::fs::N_SLOTS_1NET * tc::fs::GROUP_ROWS * 4 + 256;
+            const bool wide_ring = Q.n_nets == 1 && smem_1net <= 232448;
 #define PMB_FC1_STREAM_LAUNCH(NC)                                                                                            \
     case NC:                                                                                                                 \
-        PMB_SMEM_ATTR(tc::fc1_stream_kernel<NC>, (int)smem_need); \
-        tc::fc1_stream_kernel<NC><<<grid, tc::fs::THREADS, (size_t)smem_need, s>>>(Q);                                       \
+        if (wide_ring) {                                                                                                     \
+            PMB_SMEM_ATTR((tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS_1NET>), (int)smem_1net);                               \
+            tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS_1NET>                                                                  \
+                <<<grid, tc::fs::threads_for(tc::fs::N_SLOTS_1NET), (size_t)smem_1net, s>>>(Q);                              \
+        } else {                                                                                                             \
+            PMB_SMEM_ATTR((tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS>), (int)smem_need);                                     \
+            tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS><<<grid, tc::fs::threads_for(tc::fs::N_SLOTS), (size_t)smem_need, s>>>(Q); \
+        }                                                                                                                    \
         break;
             switch (n_chunks) {
                 PMB_FC1_STREAM_LAUNCH(1)
