@@ -1,3 +1,4 @@
+#include <cstdlib>
 // extern "C" surface of libpymarl_b200.so (see include/pymarl_b200.h) and the orchestration of
 // the whole learner step (learners/q_learner.py:37-107).
 #include <stdarg.h>
@@ -110,6 +111,11 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorName(e), file, line, what);
     return PMB_ERR_CUDA;
+}
+
+bool rollout_pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PMB_ROLLOUT_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 // SM count of the CURRENT device (cached per device ordinal)

@@ -32,6 +32,22 @@ cudaError_t set_smem_attr(const void* func, int bytes);     // MaxDynamicSharedM
     } while (0)
 
 int  sm_count();
+
+// Launch with programmatic stream serialization (programmatic dependent launch): the kernel may start while its
+// predecessor in the stream is still running - once every CTA of the predecessor has executed
+// griddepcontrol.launch_dependents or exited - and must execute griddepcontrol.wait before it touches anything the
+// predecessor reads or writes.  A predecessor that never triggers gives the ordinary stream order.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+bool rollout_pdl_enabled();                       // PMB_ROLLOUT_PDL=0 turns the dependent launches of the rollout step off
 int  validate_dims(const pmb_dims* d);
 
 inline __host__ __device__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

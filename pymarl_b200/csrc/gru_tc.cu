@@ -189,6 +189,12 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    // Programmatic dependent launch, both ways.  The next kernel of the stream (the streaming fc1 of the next rollout
+    // step) may be scheduled onto SMs as the CTAs of this grid leave them; it waits before it overwrites the x images.
+    // This kernel was itself scheduled while the fc1 of this step was finishing: everything above (barriers, TMEM,
+    // biases - parameters, not written by fc1) ran under its tail; the two loader threads wait before the first byte of
+    // x / hidden state / avail is fetched, and every other role only ever acts on what they fetched.
+    pdl_launch_dependents();
 #ifdef PMB_RO_PROFILE
     if (threadIdx.x == 0) prof_acc[13] = clock64() - prof_t0;      // prologue
 #endif
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
         // so the next tile's big copies are in flight while the current one still selects; avail has its own warp.
         // Use k of a slot starts by storing the new hidden state the slot's previous tile (k - 2) left in the staging tiles.
         if (lane == 0) {
+            pdl_wait();
             for (int k = 0; k < n_my + 2; ++k) {
                 const int s = k & 1, u = k >> 1;
                 if (k >= 2 && k - 2 >= n_my) continue;
@@ -252,6 +259,7 @@ __global__ void __launch_bounds__(ro::THREADS, 1) gru_rollout_kernel(GruFwdParam
     } else if (warp == AV_W) {
         // ===== avail loader: one copy per env the tile touches (an env's N x A block is contiguous; the batch stride is free) =====
         if (av_smem) {
+            pdl_wait();
             for (int k = 0; k < n_my; ++k) {
                 const int s = k & 1, u = k >> 1;
                 const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
@@ -937,7 +945,7 @@ int tc_gru_fwd(const tc::GruFwdParams& P, cudaStream_t s) {
     }
     PMB_SMEM_ATTR(tc::gru_rollout_kernel, tc::ro::SMEM_BYTES);
     const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
-    tc::gru_rollout_kernel<<<grid, tc::ro::THREADS, tc::ro::SMEM_BYTES, s>>>(P, av_smem, tmap, tmap_out);
+    PMB_CUDA(launch_pdl(tc::gru_rollout_kernel, dim3(grid), dim3(tc::ro::THREADS), tc::ro::SMEM_BYTES, s, rollout_pdl_enabled(), P, av_smem, tmap, tmap_out));
     PMB_LAUNCH_CHECK("gru_rollout_kernel");
     return PMB_OK;
 }

@@ -620,6 +620,10 @@ __global__ void __launch_bounds__(fs::threads_for(NS), 1) fc1_stream_kernel(Fc1S
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_items = (int64_t)P.T * P.n_tiles;
+    // programmatic dependent launch (rollout step only; see gru_rollout_kernel): the next kernel may be scheduled as the
+    // CTAs of this grid leave; this kernel reads nothing its predecessor writes and only its epilogue warps write something
+    // the predecessor (the GRU step of the previous rollout step) may still be reading - the x images
+    pdl_launch_dependents();
 
     if (warp >= PROD_W && warp < PROD_W + N_PROD) {
         // one producer warp per staging slot: the address walk of a warp is ~300 dependent integer instructions per
@@ -849,6 +853,7 @@ __global__ void __launch_bounds__(fs::threads_for(NS), 1) fc1_stream_kernel(Fc1S
         int n_cur, n_nxt;
         int a_prev = fetch_prev(blockIdx.x, n_cur);
         uint32_t ti = 0;
+        pdl_wait();                                            // before the first store to the x images
         for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++ti) {
             const int b = ti & 1;
             const int a_next = fetch_prev(item + gridDim.x, n_nxt);
@@ -1118,8 +1123,8 @@ int tc_fc1_fwd_both(const pmb_dims* d, const pmb_batch* b, int t0, int nt, const
     case NC:                                                                                                                 \
         if (wide_ring) {                                                                                                     \
             PMB_SMEM_ATTR((tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS_1NET>), (int)smem_1net);                               \
-            tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS_1NET>                                                                  \
-                <<<grid, tc::fs::threads_for(tc::fs::N_SLOTS_1NET), (size_t)smem_1net, s>>>(Q);                              \
+            PMB_CUDA(launch_pdl(tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS_1NET>, dim3(grid),                                 \
+                                dim3(tc::fs::threads_for(tc::fs::N_SLOTS_1NET)), (size_t)smem_1net, s, rollout_pdl_enabled(), Q)); \
         } else {                                                                                                             \
             PMB_SMEM_ATTR((tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS>), (int)smem_need);                                     \
             tc::fc1_stream_kernel<NC, tc::fs::N_SLOTS><<<grid, tc::fs::threads_for(tc::fs::N_SLOTS), (size_t)smem_need, s>>>(Q); \
