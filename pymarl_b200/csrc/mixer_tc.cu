@@ -9,6 +9,7 @@
 //                        operands are bulk-copied tile images read MN-major (no conversion): a CTA owns a 256 x 256
 //                        output tile (two 128 x 256 fp32 accumulators = all 512 TMEM columns) and a slice of the rows;
 //                        64 rows per pipeline stage, 3 stages.  Slices are summed in a fixed order (deterministic).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mixer_tc.cuh"
@@ -148,24 +149,36 @@ __global__ void __launch_bounds__(32 * MB_WARPS) mix_bwd_img_kernel(MixBwdParams
 // one XOR on the packed product, group membership tests are hoisted into two per-lane bounds, and the 16 per-lane
 // d_q partials are reduced with a 4-stage reduce-scatter (15 shuffles instead of 60) that leaves one group sum per
 // lane for a single coalesced store.
+//
+// NT > 0: the agent count as a compile-time constant.  The ncu source page of the run-time form showed 1107 warp
+// instructions per row, a third of them ISETP / SEL: every `cb < n_cblk`, `cb < n_w1`, `cb == cb_b1` test of the unrolled
+// 16-block loops was re-evaluated per row (the kernel ran at IPC 2.7 and 34 % of the DRAM bandwidth: issue-bound).  With N
+// known all of them fold (only block N / 2 keeps a per-lane parity test).  NT = 0 keeps the run-time form.
+template <int NT>
 __global__ void __launch_bounds__(32 * MB_WARPS, 3) mix_bwd_img16_kernel(MixBwdParams P) {
     __shared__ float red[MB_WARPS][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t n_warps = (int64_t)gridDim.x * MB_WARPS;          // multiple of 8: (row & 7) is fixed per warp
-    const int N = P.N;
+    const int N = NT ? NT : P.N;
+    const int NCB = NT ? (NT + 4) / 2 : P.n_cblk;                   // == tc_mix_cblks
     float dv2w0 = 0.f, dv2w1 = 0.f, dv2b = 0.f;
     const int j = (lane >> 2) ^ wib;                                // logical 16-byte chunk (row & 7 == wib)
     const int h = j >> 2;                                           // group parity: this lane sees group 2*cb + h
     const int e0 = (j & 3) * 8 + (lane & 3) * 2;
     const float v2w0 = __ldg(P.v2_w + e0), v2w1 = __ldg(P.v2_w + e0 + 1);
     const int n_w1 = (N - h + 1) >> 1;                              // cb < n_w1  <=>  group 2*cb + h is a w1 group
+    // the same test in a form that folds for a constant N: blocks below N / 2 hold w1 groups for both parities, block
+    // N / 2 only for an odd N and the even parity
+    auto is_w1 = [&](int cb) -> bool {
+        return NT ? (cb < NT / 2 || (cb == NT / 2 && (NT & 1) != 0 && h == 0)) : cb < n_w1;
+    };
     // block index / need-partner flags of the three special groups for this lane
     const int cb_b1 = N >> 1, cb_wf = (N + 1) >> 1, cb_v0 = (N + 2) >> 1;
     const bool sw_b1 = h != (N & 1), sw_wf = h != ((N + 1) & 1), sw_v0 = h != ((N + 2) & 1);
     const int my_grp = 2 * (lane & 15) + h;                         // the group whose d_q this lane ends up holding
 
     for (int64_t m = (int64_t)blockIdx.x * MB_WARPS + wib; m < P.rows_total; m += n_warps) {
-        uint8_t* base = P.raw_img + (m >> 7) * (int64_t)P.n_cblk * 16384 + (m & 127) * 128 + lane * 4;
+        uint8_t* base = P.raw_img + (m >> 7) * (int64_t)NCB * 16384 + (m & 127) * 128 + lane * 4;
         int64_t mq = -1;
         if (m < P.BT) {
             const uint32_t b = (uint32_t)m / (uint32_t)P.T;          // B*T < 2^31 (checked by the launcher)
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(32 * MB_WARPS, 3) mix_bwd_img16_kernel(MixBwdP
             if (t < P.T - 1) mq = (int64_t)b * (P.T - 1) + t;
         }
         if (mq < 0) {                                               // no online-mixer row here: d_raw = 0
-            for (int cb = 0; cb < P.n_cblk; ++cb) *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = 0u;
+            for (int cb = 0; cb < NCB; ++cb) *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = 0u;
             continue;
         }
         const float gm = __ldg(P.g + mq);
@@ -183,8 +196,8 @@ __global__ void __launch_bounds__(32 * MB_WARPS, 3) mix_bwd_img16_kernel(MixBwdP
 #pragma unroll
         for (int cb = 0; cb < 16; ++cb) {
             wv[cb] = 0u; qv[cb] = 0.f;
-            if (cb < P.n_cblk) wv[cb] = *reinterpret_cast<const uint32_t*>(base + (int64_t)cb * 16384);
-            if (cb < n_w1) qv[cb] = __ldg(qs + 2 * cb);
+            if (cb < NCB) wv[cb] = *reinterpret_cast<const uint32_t*>(base + (int64_t)cb * 16384);
+            if (is_w1(cb)) qv[cb] = __ldg(qs + 2 * cb);
         }
         float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
@@ -227,11 +240,11 @@ __global__ void __launch_bounds__(32 * MB_WARPS, 3) mix_bwd_img16_kernel(MixBwdP
             const uint32_t nz = (((mag + 0x7fff7fffu) | mag) & 0x80008000u) >> 15;      // 1 per non-zero half
             uint32_t out = (prod ^ (w & 0x80008000u)) & (nz * 0xffffu);
             part[cb] = fmaf(fabsf(mt_lo(w)), dp0, fabsf(mt_hi(w)) * dp1);               // garbage for non-w1 groups: not stored
-            out = cb < n_w1 ? out : 0u;
+            out = is_w1(cb) ? out : 0u;
             out = cb == cb_b1 && !sw_b1 ? d_b1 : out;
             out = cb == cb_wf && !sw_wf ? d_wf : out;
             out = cb == cb_v0 && !sw_v0 ? d_v0 : out;
-            if (cb < P.n_cblk) *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = out;
+            if (cb < NCB) *reinterpret_cast<uint32_t*>(base + (int64_t)cb * 16384) = out;
         }
         // reduce-scatter over the 16 lanes of a parity: after the stage with distance d a lane keeps the half of
         // its values selected by (lane & d); lane l ends with the sum for block l & 15
@@ -464,8 +477,18 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
     tc::MixBwdParams B;
     B.raw_img = raw_img; B.agent_qs = agent_qs; B.g = g; B.v2_w = mp.v2_w; B.d_qs = d_agent_qs; B.v2_partial = v2_partial;
     B.BT = (int64_t)d->B * d->T; B.rows_total = tc_mix_row_tiles(d) * 128; B.T = d->T; B.N = d->N; B.n_cblk = tc_mix_cblks(d);
-    if (B.n_cblk <= 16 && B.rows_total < (1ll << 31)) tc::mix_bwd_img16_kernel<<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
-    else tc::mix_bwd_img_kernel<34><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
+    if (B.n_cblk <= 16 && B.rows_total < (1ll << 31)) {
+        static const bool generic = []() { const char* e = getenv("PMB_MIXBWD_GENERIC"); return e && atoi(e) != 0; }();   // A/B switch
+        switch (generic ? 0 : d->N) {
+#define PMB_MB16(n) case n: tc::mix_bwd_img16_kernel<n><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B); break;
+            PMB_MB16(1) PMB_MB16(2) PMB_MB16(3) PMB_MB16(4) PMB_MB16(5) PMB_MB16(6) PMB_MB16(7) PMB_MB16(8) PMB_MB16(9)
+            PMB_MB16(10) PMB_MB16(11) PMB_MB16(12) PMB_MB16(13) PMB_MB16(14) PMB_MB16(15) PMB_MB16(16) PMB_MB16(17)
+            PMB_MB16(18) PMB_MB16(19) PMB_MB16(20) PMB_MB16(21) PMB_MB16(22) PMB_MB16(23) PMB_MB16(24) PMB_MB16(25)
+            PMB_MB16(26) PMB_MB16(27) PMB_MB16(28) PMB_MB16(29)
+#undef PMB_MB16
+            default: tc::mix_bwd_img16_kernel<0><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B); break;
+        }
+    } else tc::mix_bwd_img_kernel<34><<<grid, 32 * tc::MB_WARPS, 0, s>>>(B);
     PMB_LAUNCH_CHECK("mix_bwd_img_kernel");
     tc::mix_v2_reduce_kernel<<<33, 256, 0, s>>>(v2_partial, grid, gv2_w, gv2_b);
     PMB_LAUNCH_CHECK("mix_v2_reduce_kernel");
