@@ -454,7 +454,7 @@ MixDwPlan mix_dw_plan(const pmb_dims* d) {
     return p;
 }
 int mix_bwd_grid(const pmb_dims* d) {
-    int64_t g = 8 * (int64_t)sm_count();
+    int64_t g = 6 * (int64_t)sm_count();          // two full waves at 3 resident CTAs per SM (8 x SMs was 2.67 waves)
     int64_t mx = ceil_div(tc_mix_row_tiles(d) * 128, tc::MB_WARPS);
     if (g > mx) g = mx;
     return (int)(g < 1 ? 1 : g);
