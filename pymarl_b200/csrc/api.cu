@@ -151,7 +151,7 @@ cudaError_t set_smem_attr(const void* func, int bytes) {
 // Side stream + fork / join events of the CURRENT device, created on first use (never while a graph is being captured:
 // the learner runs every new configuration once eagerly before it captures).  The forward pass forks the target net's
 // recurrence onto the side stream when both recurrences fit on the device side by side.
-struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr; };
 static int side_stream(SideStream** out) {
     constexpr int kMaxDev = 64;
     static SideStream table[kMaxDev];
@@ -165,6 +165,8 @@ static int side_stream(SideStream** out) {
         PMB_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
         PMB_CUDA(cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming));
         PMB_CUDA(cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming));
+        PMB_CUDA(cudaEventCreateWithFlags(&e.fork2, cudaEventDisableTiming));
+        PMB_CUDA(cudaEventCreateWithFlags(&e.join2, cudaEventDisableTiming));
     }
     *out = &e;
     return PMB_OK;
@@ -202,6 +204,7 @@ namespace {
 struct WsPlan {
     int64_t off[18];
     int64_t scratch_bytes;
+    int64_t mixdw_bytes;
     int64_t total;
 };
 
@@ -273,7 +276,10 @@ WsPlan plan_workspace(const pmb_dims* d) {
     if (sc < 65536) sc = 65536;                  // >= the per-block partial sums of td_loss (8 x SMs x 5 doubles)
     p.off[17] = off;
     p.scratch_bytes = align_up(sc, 256);
-    p.total = off + p.scratch_bytes;
+    // behind the scratch area: the slice partials of the hypernet weight-gradient GEMM when it runs on the side stream next
+    // to the agent's BPTT (which owns the scratch area then)
+    p.mixdw_bytes = (tc_mix && d->H == 64) ? tc_mixer_dw_scratch_bytes(d) : 0;
+    p.total = off + p.scratch_bytes + p.mixdw_bytes;
     return p;
 }
 
@@ -781,11 +787,31 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
     }
     // :100-101 backward
     PHASE(s, "mixer_bwd");
+    // The hypernet weight-gradient GEMM (d_raw^T . [state | 1]) feeds nothing but the optimiser.  When the agent's BPTT kernel
+    // (one CTA per row tile) leaves SMs idle - small configs, or a batch sharded over many GPUs - it runs on the side stream
+    // on those SMs, with its own partial-sum area behind the scratch, and joins before the clip / RMSprop kernels.
+    SideStream* side_dw = nullptr;
     if (tc_mixer) {
-        if ((rc = tc_mixer_bwd_img(d, mixer_params(d, flat_p + L.n_agent), state_img, raw_img, v.chosen, v.g, v.d_chosen,
-                                   flat_g + L.offset[PMB_P_HW1_W], flat_g + L.offset[PMB_P_HW1_B],
-                                   flat_g + L.offset[PMB_P_V2_W], flat_g + L.offset[PMB_P_V2_B], v.scratch, v.scratch_bytes,
-                                   s))) return rc;
+        static const int dw_fork_mode = []() { const char* e = getenv("PMB_DW_FORK"); return e ? atoi(e) : -1; }();   // A/B: 0 never, 1 whenever it fits
+        const int free_sms = sm_count() - n_tiles;
+        const bool fork_dw = tc_agent && plan.mixdw_bytes > 0 && dw_fork_mode != 0 && free_sms >= tc_mixer_dw_ctas(d);
+        if (!fork_dw) {
+            if ((rc = tc_mixer_bwd_img(d, mixer_params(d, flat_p + L.n_agent), state_img, raw_img, v.chosen, v.g, v.d_chosen,
+                                       flat_g + L.offset[PMB_P_HW1_W], flat_g + L.offset[PMB_P_HW1_B],
+                                       flat_g + L.offset[PMB_P_V2_W], flat_g + L.offset[PMB_P_V2_B], v.scratch,
+                                       v.scratch_bytes, s))) return rc;
+        } else {
+            if ((rc = tc_mixer_bwd_img_dq(d, mixer_params(d, flat_p + L.n_agent), raw_img, v.chosen, v.g, v.d_chosen,
+                                          flat_g + L.offset[PMB_P_V2_W], flat_g + L.offset[PMB_P_V2_B], v.scratch,
+                                          v.scratch_bytes, s))) return rc;
+            if ((rc = side_stream(&side_dw))) return rc;
+            PMB_CUDA(cudaEventRecord(side_dw->fork2, s));
+            PMB_CUDA(cudaStreamWaitEvent(side_dw->stream, side_dw->fork2, 0));
+            if ((rc = tc_mixer_dw(d, state_img, raw_img, flat_g + L.offset[PMB_P_HW1_W], flat_g + L.offset[PMB_P_HW1_B],
+                                  reinterpret_cast<char*>(v.scratch) + plan.scratch_bytes, plan.mixdw_bytes, free_sms,
+                                  side_dw->stream))) return rc;
+            PMB_CUDA(cudaEventRecord(side_dw->join2, side_dw->stream));
+        }
     } else if (d->mixer != PMB_MIXER_NONE) {
         if ((rc = launch_mixer_bwd(d, b, flat_p + L.n_agent, v.chosen, v.raw_on, v.g, v.d_chosen, flat_g + L.n_agent,
                                    v.scratch, v.scratch_bytes, s))) return rc;
@@ -816,6 +842,7 @@ int pmb_qlearner_train_step(const pmb_dims* d, const pmb_batch* b, const pmb_hpa
         }
     } else if ((rc = agent_bwd(d, b, flat_p, v.x_on, v.h_stash, v.gates, v.d_chosen, v.x_tg, flat_g, v.scratch,
                                v.scratch_bytes, s))) return rc;
+    if (side_dw) PMB_CUDA(cudaStreamWaitEvent(s, side_dw->join2, 0));
     // :102-107
     PHASE(s, "clip_rmsprop_update");
     if (!hp->skip_update) {

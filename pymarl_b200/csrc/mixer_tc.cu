@@ -439,14 +439,16 @@ mix_dw_reduce_kernel(const float* __restrict__ partial, int slices, int c_rows, 
 
 namespace {
 struct MixDwPlan { int n_ct, n_kt, slices, ldk; int64_t n_halves, halves_per_slice; };
-MixDwPlan mix_dw_plan(const pmb_dims* d) {
+// ctas_avail: SMs the weight-gradient GEMM may take (0 = all of them); it runs next to the agent's BPTT kernel on the
+// side stream when that kernel leaves SMs idle (few row tiles), see pmb_qlearner_train_step
+MixDwPlan mix_dw_plan(const pmb_dims* d, int ctas_avail = 0) {
     MixDwPlan p;
     p.n_ct = (tc_mix_cblks(d) + 3) / 4;
     p.n_kt = (tc_state_chunks(d) + 3) / 4;
     p.ldk = tc_state_chunks(d) * 64;
     p.n_halves = tc_mix_row_tiles(d) * 2;
     int64_t tiles = (int64_t)p.n_ct * p.n_kt;
-    int64_t sl = sm_count() / tiles;
+    int64_t sl = (ctas_avail > 0 && ctas_avail < sm_count() ? ctas_avail : sm_count()) / tiles;
     if (sl > p.n_halves / 8) sl = p.n_halves / 8;
     if (sl < 1) sl = 1;
     p.slices = (int)sl;
@@ -459,21 +461,26 @@ int mix_bwd_grid(const pmb_dims* d) {
     if (g > mx) g = mx;
     return (int)(g < 1 ? 1 : g);
 }
+int64_t mix_v2_partial_bytes(const pmb_dims* d) { return align_up((int64_t)mix_bwd_grid(d) * 33 * 4, 256); }
 }  // namespace
 
-int64_t tc_mixer_bwd_img_scratch_bytes(const pmb_dims* d) {
+int tc_mixer_dw_ctas(const pmb_dims* d) { return ((tc_mix_cblks(d) + 3) / 4) * ((tc_state_chunks(d) + 3) / 4); }
+
+// the slice count only shrinks with ctas_avail: the full-device plan bounds every plan
+int64_t tc_mixer_dw_scratch_bytes(const pmb_dims* d) {
     MixDwPlan p = mix_dw_plan(d);
-    return align_up((int64_t)mix_bwd_grid(d) * 33 * 4, 256) + align_up((int64_t)p.slices * p.n_ct * 256 * p.ldk * 4, 256);
+    return align_up((int64_t)p.slices * p.n_ct * 256 * p.ldk * 4, 256);
 }
 
-int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* state_img, uint8_t* raw_img,
-                     const float* agent_qs, const float* g, float* d_agent_qs, float* gw_cat, float* gb_cat, float* gv2_w,
-                     float* gv2_b, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+int64_t tc_mixer_bwd_img_scratch_bytes(const pmb_dims* d) { return mix_v2_partial_bytes(d) + tc_mixer_dw_scratch_bytes(d); }
+
+// part 1: d_raw in place, d_agent_qs, V.2 gradients (scratch: mix_v2_partial_bytes, the start of the step's scratch area)
+int tc_mixer_bwd_img_dq(const pmb_dims* d, const MixerParams& mp, uint8_t* raw_img, const float* agent_qs, const float* g,
+                        float* d_agent_qs, float* gv2_w, float* gv2_b, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
     if (d->E != 32) { set_error("tc_mixer_bwd_img: mixing_embed_dim must be 32"); return PMB_ERR_INVALID; }
-    if (scratch_bytes < tc_mixer_bwd_img_scratch_bytes(d)) { set_error("tc_mixer_bwd_img: scratch too small"); return PMB_ERR_WORKSPACE; }
+    if (scratch_bytes < mix_v2_partial_bytes(d)) { set_error("tc_mixer_bwd_img: scratch too small"); return PMB_ERR_WORKSPACE; }
     const int grid = mix_bwd_grid(d);
     float* v2_partial = static_cast<float*>(scratch);
-    float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up((int64_t)grid * 33 * 4, 256));
     tc::MixBwdParams B;
     B.raw_img = raw_img; B.agent_qs = agent_qs; B.g = g; B.v2_w = mp.v2_w; B.d_qs = d_agent_qs; B.v2_partial = v2_partial;
     B.BT = (int64_t)d->B * d->T; B.rows_total = tc_mix_row_tiles(d) * 128; B.T = d->T; B.N = d->N; B.n_cblk = tc_mix_cblks(d);
@@ -492,8 +499,15 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
     PMB_LAUNCH_CHECK("mix_bwd_img_kernel");
     tc::mix_v2_reduce_kernel<<<33, 256, 0, s>>>(v2_partial, grid, gv2_w, gv2_b);
     PMB_LAUNCH_CHECK("mix_v2_reduce_kernel");
+    return PMB_OK;
+}
 
-    MixDwPlan p = mix_dw_plan(d);
+// part 2: hypernet weight / bias gradients = d_raw^T . [state | 1] (scratch: tc_mixer_dw_scratch_bytes)
+int tc_mixer_dw(const pmb_dims* d, const uint8_t* state_img, const uint8_t* raw_img, float* gw_cat, float* gb_cat,
+                void* scratch, int64_t scratch_bytes, int ctas_avail, cudaStream_t s) {
+    if (scratch_bytes < tc_mixer_dw_scratch_bytes(d)) { set_error("tc_mixer_dw: scratch too small"); return PMB_ERR_WORKSPACE; }
+    float* partial = static_cast<float*>(scratch);
+    MixDwPlan p = mix_dw_plan(d, ctas_avail);
     tc::MixDwParams W;
     W.raw_img = raw_img; W.state_img = state_img; W.partial = partial;
     W.n_cblk = tc_mix_cblks(d); W.n_chunks = tc_state_chunks(d); W.n_ct = p.n_ct; W.n_kt = p.n_kt; W.ldk = p.ldk;
@@ -506,6 +520,16 @@ int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
                                                                           d->S, gw_cat, gb_cat);
     PMB_LAUNCH_CHECK("mix_dw_reduce_kernel");
     return PMB_OK;
+}
+
+int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* state_img, uint8_t* raw_img,
+                     const float* agent_qs, const float* g, float* d_agent_qs, float* gw_cat, float* gb_cat, float* gv2_w,
+                     float* gv2_b, void* scratch, int64_t scratch_bytes, cudaStream_t s) {
+    if (scratch_bytes < tc_mixer_bwd_img_scratch_bytes(d)) { set_error("tc_mixer_bwd_img: scratch too small"); return PMB_ERR_WORKSPACE; }
+    int rc = tc_mixer_bwd_img_dq(d, mp, raw_img, agent_qs, g, d_agent_qs, gv2_w, gv2_b, scratch, scratch_bytes, s);
+    if (rc) return rc;
+    const int64_t off = mix_v2_partial_bytes(d);
+    return tc_mixer_dw(d, state_img, raw_img, gw_cat, gb_cat, static_cast<char*>(scratch) + off, scratch_bytes - off, 0, s);
 }
 
 }  // namespace pmb

@@ -29,6 +29,13 @@ int tc_mixer_fwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* st
 
 // backward: d_raw in place, d_agent_qs, V.2 gradients, then hypernet weight / bias gradients = d_raw^T . [state | 1]
 int64_t tc_mixer_bwd_img_scratch_bytes(const pmb_dims* d);
+// the two halves of tc_mixer_bwd_img, so that the weight-gradient GEMM can run on a side stream next to the agent's BPTT
+int tc_mixer_bwd_img_dq(const pmb_dims* d, const MixerParams& mp, uint8_t* raw_img, const float* agent_qs, const float* g,
+                        float* d_agent_qs, float* gv2_w, float* gv2_b, void* scratch, int64_t scratch_bytes, cudaStream_t s);
+int tc_mixer_dw_ctas(const pmb_dims* d);                 // CTAs of the weight-gradient GEMM with one row slice
+int64_t tc_mixer_dw_scratch_bytes(const pmb_dims* d);
+int tc_mixer_dw(const pmb_dims* d, const uint8_t* state_img, const uint8_t* raw_img, float* gw_cat, float* gb_cat,
+                void* scratch, int64_t scratch_bytes, int ctas_avail, cudaStream_t s);
 int tc_mixer_bwd_img(const pmb_dims* d, const MixerParams& mp, const uint8_t* state_img, uint8_t* raw_img,
                      const float* agent_qs, const float* g, float* d_agent_qs, float* gw_cat, float* gb_cat, float* gv2_w,
                      float* gv2_b, void* scratch, int64_t scratch_bytes, cudaStream_t s);
