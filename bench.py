@@ -517,7 +517,10 @@ def e2e_learner(ctx, learner, fields, B_local, T, mixer, steps):
                   and (k != "state" or mixer == "qmix"))
         return {"value": ctx.world * B_local / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": dt * 1e3, "steps": steps, "loss": loss,
-                "note": "per rank: pinned host batch of %d episodes -> H2D -> train -> loss.item()" % B_local}
+                "note": "per rank: pinned host batch of %d episodes -> H2D -> train -> loss.item()%s" % (
+                    B_local, " (QLearner.train streams the host batch in %d-episode chunks: copy of chunk i+1 under the "
+                    "compute of chunk i, one update)" % learner._hs["bufs"][0]["obs"].shape[0]
+                    if getattr(learner, "_hs", None) else "")}
     except Exception as ex:
         if ctx.world > 1:
             raise                                        # a rank-local failure inside collective steps cannot be skipped safely

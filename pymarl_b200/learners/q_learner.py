@@ -84,6 +84,7 @@ class QLearner:
         self._dp_scratch = None         # 4096 floats for the replicated clip + RMSprop of the data-parallel path
         self._px = None                 # data_parallel.PeerExchange when the fused NVLink exchange is in use
         self._graphs = {}               # CUDA graphs of the step (args.cuda_graph)
+        self._hs = None                 # host-batch streaming state (copy stream, two chunk buffers, accumulators)
         self.last_stats = None          # device tensor [16] float64 of the latest step
 
     # ---- flat storage -----------------------------------------------------------------------
@@ -219,6 +220,13 @@ class QLearner:
         else:                                   # a rank without episodes still takes part in the exchange
             f["g"].zero_()
             self._stats.zero_()
+        self._exchange_and_update(hp, f, dev, dp)
+
+    def _exchange_and_update(self, hp, f, dev, dp):
+        """What follows a skip_update step: the data-parallel exchange and the replicated clip + RMSprop update."""
+        L = _lib.lib()
+        s = _lib.stream_ptr(dev)
+        n = f["layout"].n_total
         if dp and self._px is not None:
             # exchange + update fused into one kernel over NVLink peer memory
             self._px.fused_update(f["p"], f["sq"], f["target"], hp.do_target_sync, self._stats, hp.lr, hp.alpha, hp.eps,
@@ -233,6 +241,92 @@ class QLearner:
                                                  hp.alpha, hp.eps, hp.grad_norm_clip, _lib.ptr(self._dp_scratch), s),
                        "pmb_clip_rmsprop_update")
 
+    # ---- host-resident batches, streamed ----------------------------------------------------------
+    # A batch that lives in host memory (buffer_cpu_only, run.py:214) is PCIe-bound: 29 GB at 27m_vs_30m / 4096.  Episodes
+    # are independent and the step's gradient is a plain sum over them, so the batch is cut into chunks of
+    # args.host_stream_chunk episodes (default 512): chunk i + 1 crosses PCIe on a copy stream into the other of two
+    # chunk-sized device buffers while chunk i runs as a skip_update step (un-normalised gradient + the five loss sums);
+    # the chunk gradients and sums are added up and ONE exchange / clip / RMSprop update follows - the same arithmetic as
+    # the data-parallel path with the chunks in the role of the ranks.  The device then holds two chunks and a chunk-sized
+    # workspace instead of the whole batch (7 GB + 6.5 GB instead of 29 GB + 52 GB) and the compute hides under the copy.
+    def _host_stream_plan(self, batch, dp):
+        a = self.args
+        chunk = int(getattr(a, "host_stream_chunk", 512))
+        if chunk <= 0 or getattr(a, "cuda_graph", False) or (hasattr(batch, "ep_ids") and hasattr(batch, "buffer")):
+            return None
+        if batch["obs"].is_cuda:
+            return None
+        lo, hi = 0, batch.batch_size
+        if dp and getattr(a, "dp_shard_batch", True):
+            lo, hi = data_parallel.shard_slice(batch.batch_size, data_parallel.rank(), data_parallel.world_size())
+        if hi - lo < 2 * chunk:
+            return None
+        return lo, hi, chunk
+
+    def _train_streamed(self, batch, names, plan, f, dev, dp, hp):
+        lo, hi, chunk = plan
+        L = _lib.lib()
+        a = self.args
+        n = f["layout"].n_total
+        main = th.cuda.current_stream(dev)
+        st = self._hs
+        if st is None or st["dev"] != dev:
+            st = self._hs = dict(dev=dev, copy=th.cuda.Stream(dev), bufs=[{}, {}],
+                                 copied=[th.cuda.Event(), th.cuda.Event()], done=[th.cuda.Event(), th.cuda.Event()],
+                                 g=None, sums=th.zeros(5, dtype=th.float64, device=dev))
+        if st["g"] is None or st["g"].numel() != n:
+            st["g"] = th.zeros(n, dtype=th.float32, device=dev)
+        src = {k: batch[k] for k in names}
+        for slot in st["bufs"]:
+            for k in names:
+                t = src[k]
+                shape = (chunk,) + tuple(t.shape[1:])
+                if k not in slot or slot[k].shape != shape or slot[k].dtype != t.dtype:
+                    slot[k] = th.empty(shape, dtype=t.dtype, device=dev)
+        st["g"].zero_()
+        st["sums"].zero_()
+        st["copy"].wait_stream(main)             # the chunk buffers may still be read by the previous call's kernels
+        hp_chunk = _lib.HParams(hp.gamma, hp.lr, hp.alpha, hp.eps, hp.grad_norm_clip, 0, 1, hp.keep_q)
+        T = src["obs"].shape[1]
+        N, O = src["obs"].shape[2], src["obs"].shape[3]
+        S = 1
+        if "state" in src:
+            for dim in src["state"].shape[2:]:
+                S *= int(dim)
+        keep = []
+        dims = None
+        for i, s0 in enumerate(range(lo, hi, chunk)):
+            s1 = min(s0 + chunk, hi)
+            nb, slot = s1 - s0, i & 1
+            with th.cuda.stream(st["copy"]):
+                if i >= 2:
+                    st["copy"].wait_event(st["done"][slot])
+                for k in names:
+                    st["bufs"][slot][k][:nb].copy_(src[k][s0:s1], non_blocking=True)
+                st["copied"][slot].record(st["copy"])
+            main.wait_event(st["copied"][slot])
+            fields = {k: st["bufs"][slot][k][:nb] for k in names}
+            dims = self._layout_dims(B=nb, T=T, O=O, S=S)
+            pb = _lib.make_batch(fields, need_state=(a.mixer == "qmix"), keep=keep)
+            need = self._ensure_workspace(self._layout_dims(B=chunk, T=T, O=O, S=S), dev)
+            _lib.check(L.pmb_qlearner_train_step(C.byref(dims), C.byref(pb), C.byref(hp_chunk), _lib.ptr(f["p"]),
+                                                 _lib.ptr(f["g"]), _lib.ptr(f["sq"]), _lib.ptr(f["target"]),
+                                                 _lib.ptr(self._workspace), need, _lib.ptr(self._stats),
+                                                 _lib.stream_ptr(dev)), "pmb_qlearner_train_step")
+            st["g"].add_(f["g"][:n])
+            st["sums"].add_(self._stats[:5])
+            st["done"][slot].record(main)
+        f["g"][:n].copy_(st["g"])
+        self._stats[:5].copy_(st["sums"])
+        if not dp:
+            _lib.check(L.pmb_clip_rmsprop_update(n, _lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["sq"]),
+                                                 _lib.ptr(f["target"]), hp.do_target_sync, _lib.ptr(self._stats), hp.lr,
+                                                 hp.alpha, hp.eps, hp.grad_norm_clip, _lib.ptr(self._dp_scratch),
+                                                 _lib.stream_ptr(dev)), "pmb_clip_rmsprop_update")
+        else:
+            self._exchange_and_update(hp, f, dev, True)
+        return dims
+
     def train(self, batch, t_env: int, episode_num: int):
         a = self.args
         f = self._ensure_flat()
@@ -242,6 +336,9 @@ class QLearner:
         if a.mixer == "qmix":
             names.append("state")
         dp = data_parallel.is_active() and getattr(a, "data_parallel", True)
+        stream_plan = self._host_stream_plan(batch, dp)
+        if stream_plan is not None:
+            return self._train_host_batch(batch, names, stream_plan, f, dev, dp, t_env, episode_num)
         fields, ep_index, B, T = self._step_fields(batch, names, dev, dp)
         obs = fields["obs"]
         N, O = obs.shape[2], obs.shape[3]
@@ -265,6 +362,21 @@ class QLearner:
             self._run_graphed(dims, pb, hp, f, need, dev, keep)
         else:
             self._launch(dims, pb, hp, f, need, dev, dp)
+        self._after_step(dims, do_sync, t_env, episode_num)
+
+    def _train_host_batch(self, batch, names, stream_plan, f, dev, dp, t_env, episode_num):
+        a = self.args
+        if self._dp_scratch is None or self._dp_scratch.device != dev:
+            self._dp_scratch = th.empty(4096, dtype=th.float32, device=dev)
+        do_sync = (episode_num - self.last_target_update_episode) / a.target_update_interval >= 1.0
+        od = self.optimiser.defaults
+        hp = _lib.HParams(a.gamma, od["lr"], od["alpha"], od["eps"], a.grad_norm_clip, int(do_sync), int(dp),
+                          int(getattr(a, "keep_q", 0)))
+        dims = self._train_streamed(batch, names, stream_plan, f, dev, dp, hp)
+        self._after_step(dims, do_sync, t_env, episode_num)
+
+    def _after_step(self, dims, do_sync, t_env, episode_num):
+        a = self.args
         self.optimiser.step_count += 1
         if hasattr(self.mac, "params_changed"):
             self.mac.params_changed()          # the rollout path caches packed weight images between updates

@@ -277,3 +277,54 @@ def test_rollout_weight_image_cache_follows_parameter_updates():
         mac.init_hidden(48)
         q = mac.forward(batch, t)
         assert th.equal(q, fresh_q(t)), (t, change)
+
+
+@pytest.mark.parametrize("mixer,precision", [("qmix", "fp32"), ("qmix", "bf16"), ("vdn", "bf16"), (None, "fp32")])
+def test_streamed_host_batch_equals_device_batch(mixer, precision):
+    """A host-resident (pinned) batch is trained in chunks of args.host_stream_chunk episodes that cross PCIe on a copy
+    stream while the previous chunk computes (un-normalised gradients and loss sums added up, ONE update): over three
+    steps - the second with a target sync - the loss, the grad norm and the post-update parameters equal the whole batch
+    trained from device memory in one piece up to the summation order (1e-6 relative; loss sums are doubles), a ragged
+    last chunk included, and two streamed runs give identical bits."""
+    from cuda_utils import build_learner, to_batch
+    shape = SMAC_SHAPES["2s3z"]
+    B, T, chunk = 38, 14, 8                                   # chunks of 8, 8, 8, 8, 6 episodes
+    fields = numpy_episode_fields(shape, B, T, seed=11, ragged=True)
+    args = default_args(shape, mixer=mixer, learner_log_interval=0, precision=precision, target_update_interval=1)
+    rng = np.random.default_rng(5)
+    d_in = shape.obs_dim + shape.n_actions + shape.n_agents
+    agent = orc.init_params(orc.agent_param_shapes(d_in, 64, shape.n_actions), rng)
+    mix = orc.init_params(orc.qmix_param_shapes(shape.state_dim, shape.n_agents, 32), rng) if mixer == "qmix" else None
+    dev_batch = to_batch(shape, fields)
+    host_batch = to_batch(shape, fields, device="cpu")
+    for k, v in host_batch.data.transition_data.items():
+        host_batch.data.transition_data[k] = v.pin_memory()
+
+    def run(batch, **over):
+        lr, _ = build_learner(shape, copy.copy(args), agent, agent, mix, mix)
+        for k, v in over.items():
+            setattr(lr.args, k, v)
+        lr._ensure_flat()
+        lr._flat["sq"].fill_(1e-2)
+        out = []
+        for step, ep in ((0, 0), (1, 1), (2, 1)):             # the second step syncs the targets
+            lr.train(batch, step, ep)
+            out.append((lr.stats(), lr._flat["p"].clone(), lr._flat["target"].clone()))
+        return lr, out
+
+    _, ref = run(dev_batch)
+    lr_s, got = run(host_batch, host_stream_chunk=chunk)
+    assert lr_s._hs is not None and lr_s._hs["bufs"][0]["obs"].shape[0] == chunk        # the streamed path ran
+    _, again = run(host_batch, host_stream_chunk=chunk)
+    tol = 2e-6 if precision == "fp32" else 2e-5               # bf16 tier: per-tile partial sums regroup with the chunks
+    for (s0, p0, t0), (s1, p1, t1), (s2, p2, t2) in zip(ref, got, again):
+        for k in ("loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+            assert abs(s0[k] - s1[k]) <= tol * max(1.0, abs(s0[k])), (k, s0[k], s1[k])
+        assert s0["mask_sum"] == s1["mask_sum"]
+        err = float((p0 - p1).abs().max() / p0.abs().max())
+        assert err <= 10 * tol, err
+        assert float((t0 - t1).abs().max() / t0.abs().max()) <= 10 * tol
+        assert th.equal(p1, p2) and s1 == s2
+    # a host batch smaller than two chunks takes the one-piece path
+    lr_o, _ = run(host_batch, host_stream_chunk=32)
+    assert lr_o._hs is None
