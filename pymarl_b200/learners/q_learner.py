@@ -254,6 +254,8 @@ class QLearner:
         chunk = int(getattr(a, "host_stream_chunk", 512))
         if chunk <= 0 or getattr(a, "cuda_graph", False) or (hasattr(batch, "ep_ids") and hasattr(batch, "buffer")):
             return None
+        if dp and not getattr(a, "host_stream_dp", False):
+            return None        # with data parallelism every rank holds 1/world of the batch already; opt-in (not measured on GPUs)
         if batch["obs"].is_cuda:
             return None
         lo, hi = 0, batch.batch_size
