@@ -258,9 +258,10 @@ class QLearner:
             return None        # with data parallelism every rank holds 1/world of the batch already; opt-in (not measured on GPUs)
         if batch["obs"].is_cuda:
             return None
-        lo, hi = 0, batch.batch_size
+        n_ep = int(batch["obs"].shape[0])
+        lo, hi = 0, n_ep
         if dp and getattr(a, "dp_shard_batch", True):
-            lo, hi = data_parallel.shard_slice(batch.batch_size, data_parallel.rank(), data_parallel.world_size())
+            lo, hi = data_parallel.shard_slice(n_ep, data_parallel.rank(), data_parallel.world_size())
         if hi - lo < 2 * chunk:
             return None
         return lo, hi, chunk

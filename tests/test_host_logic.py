@@ -196,3 +196,37 @@ def test_reference_checkpoint_loads_on_cpu_modules():
     flat = np.concatenate([sq.numpy().ravel() for sq in learner.optimiser.square_avg])
     np.testing.assert_array_equal(flat, g["loaded/square_avg_flat"])
     assert learner.optimiser.step_count == 2
+
+
+def test_host_stream_plan_decides_from_batch_location_and_size():
+    """QLearner._host_stream_plan: only a host-resident batch of at least two chunks is streamed; device batches, zero-copy
+    replay samples, graph replay and (unless opted in) data-parallel runs take the one-piece path."""
+    shape = SmacShape("3m", 3, 30, 48, 9, 61)
+    scheme, groups = make_scheme(shape)
+    args = default_args(shape, mixer="qmix")
+    mac = mac_REGISTRY["basic_mac"](scheme, groups, args)
+    learner = le_REGISTRY["q_learner"](mac, scheme, None, args)
+
+    class HostBatch(dict):
+        pass
+
+    def batch(n):
+        b = HostBatch(obs=th.zeros(n, 2, 3, 30))
+        b.batch_size = n
+        return b
+
+    assert learner._host_stream_plan(batch(1024), False) == (0, 1024, 512)
+    assert learner._host_stream_plan(batch(1023), False) is None
+    args.host_stream_chunk = 8
+    assert learner._host_stream_plan(batch(38), False) == (0, 38, 8)
+    assert learner._host_stream_plan(batch(15), False) is None
+    assert learner._host_stream_plan(batch(38), True) is None              # data parallel: opt-in only
+    args.cuda_graph = True
+    assert learner._host_stream_plan(batch(38), False) is None
+    args.cuda_graph = False
+    args.host_stream_chunk = 0
+    assert learner._host_stream_plan(batch(38), False) is None
+    indexed = batch(38)
+    indexed.ep_ids, indexed.buffer = th.arange(38), object()
+    args.host_stream_chunk = 8
+    assert learner._host_stream_plan(indexed, False) is None
